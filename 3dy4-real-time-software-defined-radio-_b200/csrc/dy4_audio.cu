@@ -1,0 +1,260 @@
+// dy4_audio.cu — audio back end: mono delay, 38 kHz mix, the two rational
+// resamplers, L/R combine and int16 conversion, in one kernel.
+//
+// Replaces, from backend() src/project.cpp:95-134 and main() :307-317:
+//   delayBlock            filter.cpp:229-251  (50-sample delay = an index offset here)
+//   pointwiseMultiply     filter.cpp:253-266  (nco * stereo-band * 2)
+//   resampleBlockConvolveFIR x2  filter.cpp:142-173  (mono path and L-R path)
+//   pointwiseAdd/Subtract filter.cpp:267-290, interleave :291-301
+//   float -> int16        project.cpp:313-316 (truncate toward zero, NaN -> 0)
+// y[m] = sum_j h[phase + j*U] * x[floor(m*D/U) - j], phase = (m*D) mod U: only the
+// non-zero taps of the zero-stuffed signal are visited, only kept outputs computed.
+//
+// U == 1 (modes 0,1): a decimating 101-tap FIR.  The mono path (delayed IF) and
+// the difference path (mixed signal) use the same taps and indices, so the pair
+// (IF[i-50], mixed[i]) rides in one packed f32x2 exactly like (I,Q) in the front end.
+// U == 147 (modes 2,3): per-output phase, taps read from a transposed
+// [tap][phase] table; one thread per output.
+#include "dy4_common.cuh"
+#include "dy4_kernels.h"
+#include "dy4_internal.h"
+
+namespace {
+
+__constant__ TapPairs c_audio2[4];   // (h,h) pairs of the 101-tap audio low-pass, modes with U == 1
+
+__device__ __forceinline__ int16_t pcm16(float x)
+{
+    // project.cpp:314-315: NaN -> 0, else static_cast<short>(x*16384): cvttss2si then low 16 bits
+    if (x != x) return 0;
+    return (int16_t)(uint16_t)(__float2int_rz(__fmul_rn(x, 16384.0f)) & 0xffff);
+}
+
+// history-extended reads: index i is relative to the chunk start, may be negative
+__device__ __forceinline__ float if_at(const float* row, const float* tail, int n, int i)
+{
+    return i < 0 ? tail[DY4_IF_TAIL + i] : (i < n ? __ldg(row + i) : 0.0f);
+}
+__device__ __forceinline__ float mix_at(const float* nco, const float* sband, const float* tail, int n, int i)
+{
+    if (i < 0) return tail[DY4_MIX_TAIL + i];
+    if (i >= n) return 0.0f;
+    return __fmul_rn(__fmul_rn(__ldg(nco + i), __ldg(sband + i)), 2.0f);       // filter.cpp:264
+}
+
+template <int D, int R, int NT, bool EXACT, bool STEREO>
+__global__ void __launch_bounds__(NT)
+k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+           const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
+           const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
+           int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio,
+           u64 nz, int mode)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    constexpr int T = NT * R;
+    constexpr int CH = D * R;
+    constexpr int HALO = 112;
+    constexpr int DELAY = DY4_NTAPS / 2;            // project.cpp:251: mono_delay_state has num_taps/2 = 50 entries
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * T;
+    const int s = blockIdx.y;
+    const float* row = if_in + (long long)s * if_stride;
+    const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+    const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
+    const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
+    const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
+
+    // logical pair p <-> IF-rate index i = D*m0 - HALO + p ; pair = (delayed IF, mixed)
+    constexpr int NP = D * T + HALO;
+    for (int p = tid; p < NP; p += NT) {
+        const int i = D * m0 - HALO + p;
+        float2 v;
+        v.x = if_at(row, itail, n_if, i - DELAY);
+        v.y = STEREO ? mix_at(nrow, srow, mtail, n_if, i) : 0.0f;
+        sm[p + 2 * (p / CH)] = v;
+    }
+    __syncthreads();
+
+    u64 acc[R];
+    const u64* w = reinterpret_cast<const u64*>(sm) + (CH + 2) * tid;
+    pair_decim_fir<D, R, EXACT, HALO - (DY4_NTAPS - 1)>(w, reinterpret_cast<const u64*>(c_audio2[mode].t), nz, acc);
+
+    const int m = m0 + tid * R;
+    const int left = n_audio - m;
+    if (left <= 0) return;
+    if (STEREO) {
+        float o[2 * R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float mono, diff;
+            upk2(acc[r], mono, diff);
+            o[2 * r] = __fadd_rn(mono, diff);       // project.cpp:131  left
+            o[2 * r + 1] = __fsub_rn(mono, diff);   // project.cpp:132  right
+        }
+        if (left >= R) {
+            if (audio) {
+                float4* d = reinterpret_cast<float4*>(audio + (long long)s * audio_stride + 2LL * m);
+#pragma unroll
+                for (int r = 0; r < 2 * R; r += 4) d[r / 4] = make_float4(o[r], o[r + 1], o[r + 2], o[r + 3]);
+            }
+            if (pcm) {
+                uint4* d = reinterpret_cast<uint4*>(pcm + (long long)s * pcm_stride + 2LL * m);
+#pragma unroll
+                for (int r = 0; r < 2 * R; r += 8) {
+                    uint4 q;
+                    q.x = (uint16_t)pcm16(o[r]) | ((uint32_t)(uint16_t)pcm16(o[r + 1]) << 16);
+                    q.y = (uint16_t)pcm16(o[r + 2]) | ((uint32_t)(uint16_t)pcm16(o[r + 3]) << 16);
+                    q.z = (uint16_t)pcm16(o[r + 4]) | ((uint32_t)(uint16_t)pcm16(o[r + 5]) << 16);
+                    q.w = (uint16_t)pcm16(o[r + 6]) | ((uint32_t)(uint16_t)pcm16(o[r + 7]) << 16);
+                    d[r / 8] = q;
+                }
+            }
+        } else {
+            for (int r = 0; r < 2 * R; r++) if (r < 2 * left) {
+                if (audio) audio[(long long)s * audio_stride + 2LL * m + r] = o[r];
+                if (pcm) pcm[(long long)s * pcm_stride + 2LL * m + r] = pcm16(o[r]);
+            }
+        }
+    } else {
+        float o[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { float d; upk2(acc[r], o[r], d); }
+        if (left >= R && R % 8 == 0) {
+            if (audio) {
+                float4* d = reinterpret_cast<float4*>(audio + (long long)s * audio_stride + m);
+#pragma unroll
+                for (int r = 0; r < R; r += 4) d[r / 4] = make_float4(o[r], o[r + 1], o[r + 2], o[r + 3]);
+            }
+            if (pcm) {
+                uint4* d = reinterpret_cast<uint4*>(pcm + (long long)s * pcm_stride + m);
+#pragma unroll
+                for (int r = 0; r < R; r += 8) {
+                    uint4 q;
+                    q.x = (uint16_t)pcm16(o[r]) | ((uint32_t)(uint16_t)pcm16(o[r + 1]) << 16);
+                    q.y = (uint16_t)pcm16(o[r + 2]) | ((uint32_t)(uint16_t)pcm16(o[r + 3]) << 16);
+                    q.z = (uint16_t)pcm16(o[r + 4]) | ((uint32_t)(uint16_t)pcm16(o[r + 5]) << 16);
+                    q.w = (uint16_t)pcm16(o[r + 6]) | ((uint32_t)(uint16_t)pcm16(o[r + 7]) << 16);
+                    d[r / 8] = q;
+                }
+            }
+        } else {
+            for (int r = 0; r < R; r++) if (r < left) {
+                if (audio) audio[(long long)s * audio_stride + m + r] = o[r];
+                if (pcm) pcm[(long long)s * pcm_stride + m + r] = pcm16(o[r]);
+            }
+        }
+    }
+}
+
+// ---- U > 1: one thread per output, tile of NT outputs per block ---------------------------------------
+template <int NT, bool EXACT, bool STEREO>
+__global__ void __launch_bounds__(NT)
+k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+             const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
+             const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
+             int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
+             const float* __restrict__ taps_poly, int up_pad, int span_max)
+{
+    extern __shared__ __align__(16) float sm_f[];
+    constexpr int DELAY = DY4_NTAPS / 2;
+    float* s_ifd = sm_f;                 // delayed IF over the tile's span
+    float* s_mix = sm_f + span_max;      // mixed signal over the same span
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * NT;
+    const int s = blockIdx.y;
+    const float* row = if_in + (long long)s * if_stride;
+    const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+    const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
+    const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
+    const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
+
+    const int m_last = min(m0 + NT, n_audio) - 1;
+    const int i_lo = (int)(((long long)m0 * down) / up) - (DY4_NTAPS - 1);
+    const int i_hi = (int)(((long long)m_last * down) / up);
+    const int span = i_hi - i_lo + 1;
+    for (int p = tid; p < span; p += NT) {
+        const int i = i_lo + p;
+        s_ifd[p] = if_at(row, itail, n_if, i - DELAY);
+        if (STEREO) s_mix[p] = mix_at(nrow, srow, mtail, n_if, i);
+    }
+    __syncthreads();
+
+    const int m = m0 + tid;
+    if (m >= n_audio) return;
+    const long long n = (long long)m * down;
+    const int phase = (int)(n % up);
+    const int base = (int)(n / up) - i_lo;          // position of x[floor(mD/U)] in the span
+    float mono = 0.0f, diff = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < DY4_NTAPS; j++) {
+        const float h = __ldg(taps_poly + j * up_pad + phase);
+        if (EXACT) {
+            mono = __fadd_rn(mono, __fmul_rn(h, s_ifd[base - j]));
+            if (STEREO) diff = __fadd_rn(diff, __fmul_rn(h, s_mix[base - j]));
+        } else {
+            mono = fmaf(h, s_ifd[base - j], mono);
+            if (STEREO) diff = fmaf(h, s_mix[base - j], diff);
+        }
+    }
+    if (STEREO) {
+        const float l = __fadd_rn(mono, diff), r = __fsub_rn(mono, diff);
+        if (audio) *reinterpret_cast<float2*>(audio + (long long)s * audio_stride + 2LL * m) = make_float2(l, r);
+        if (pcm) *reinterpret_cast<uint32_t*>(pcm + (long long)s * pcm_stride + 2LL * m) = (uint16_t)pcm16(l) | ((uint32_t)(uint16_t)pcm16(r) << 16);
+    } else {
+        if (audio) audio[(long long)s * audio_stride + m] = mono;
+        if (pcm) pcm[(long long)s * pcm_stride + m] = pcm16(mono);
+    }
+}
+
+template <int D, int R, int NT, bool EXACT, bool STEREO>
+cudaError_t launch_u1(const Dy4AudioArgs& a, cudaStream_t st)
+{
+    constexpr int T = NT * R;
+    const size_t smem = sizeof(float2) * dy4_padded_pairs(D, R, NT);
+    auto kern = k_audio_u1<D, R, NT, EXACT, STEREO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.n_audio + T - 1) / T, a.n_streams);
+    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride,
+                                 a.pcm, a.pcm_stride, a.n_if, a.n_audio, a.neg_zero2, a.mode);
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t dispatch_u1(const Dy4AudioArgs& a, cudaStream_t st)
+{
+    constexpr int R = 8, NT = 128;
+    if (a.stereo) return a.exact ? launch_u1<D, R, NT, true, true>(a, st) : launch_u1<D, R, NT, false, true>(a, st);
+    return a.exact ? launch_u1<D, R, NT, true, false>(a, st) : launch_u1<D, R, NT, false, false>(a, st);
+}
+
+template <bool EXACT, bool STEREO>
+cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
+{
+    constexpr int NT = 128;
+    const int span_max = (int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 3;
+    const size_t smem = sizeof(float) * 2 * span_max;
+    dim3 grid((a.n_audio + NT - 1) / NT, a.n_streams);
+    k_audio_poly<NT, EXACT, STEREO><<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
+                                                            a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
+                                                            a.up, a.down, a.taps_poly, a.up_pad, span_max);
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t dy4_launch_audio(const Dy4AudioArgs& a, cudaStream_t st)
+{
+    if (a.n_audio <= 0 || a.n_streams <= 0) return cudaSuccess;
+    if (a.up == 1 && a.down == 5) return dispatch_u1<5>(a, st);
+    if (a.up == 1 && a.down == 8) return dispatch_u1<8>(a, st);
+    if (a.up > 1) {
+        if (a.stereo) return a.exact ? launch_poly<true, true>(a, st) : launch_poly<false, true>(a, st);
+        return a.exact ? launch_poly<true, false>(a, st) : launch_poly<false, false>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t dy4_upload_taps_audio(const TapPairs* audio4) { return cudaMemcpyToSymbol(c_audio2, audio4, sizeof(TapPairs) * 4); }

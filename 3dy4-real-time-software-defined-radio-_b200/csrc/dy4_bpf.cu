@@ -1,0 +1,96 @@
+// dy4_bpf.cu — pilot (18.5-19.5 kHz) and stereo-band (22-54 kHz) band-pass filters
+// computed together from ONE staged tile of IF samples.
+//
+// Replaces the two blockConvolveFIR calls of backend(), src/project.cpp:120-121
+// (src/filter.cpp:66-83): y[n] = sum_k h[k] x[n-k], 101 taps, full rate.
+// The two filters share the input, so the pair (pilot, stereo-band) rides in one
+// packed f32x2 accumulator: x is staged in shared memory duplicated as (x,x) and
+// multiplies the constant-bank pair (h_pilot[k], h_stereo[k]).  R consecutive
+// outputs per thread; the input index descends so taps are applied in ascending
+// k for every output.  EXACT arithmetic (dy4_common.cuh): the pilot output feeds
+// the PLL and must be bit-identical to the reference.
+#include "dy4_common.cuh"
+#include "dy4_kernels.h"
+#include "dy4_internal.h"
+
+namespace {
+
+__constant__ TapPairs c_bpf2[4];   // (pilot[k], stereo-band[k]) pairs, per mode
+
+template <int R, int NT, bool EXACT>
+__global__ void __launch_bounds__(NT)
+k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+           float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if,
+           u64 nz, int mode)
+{
+    constexpr int T = NT * R;
+    constexpr int HALO = 128;                       // >= 100, keeps 16-byte alignment of global loads
+    constexpr int NP = T + HALO;                    // logical (x,x) pairs per tile
+    __shared__ __align__(16) float2 sm[NP + 2 * (NP / R) + 8];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * T;
+    const float* row = if_in + (long long)blockIdx.y * if_stride;
+    const float* tail = if_tail + (long long)blockIdx.y * DY4_IF_TAIL;
+
+    // stage 4 samples per step as 4 duplicated pairs; logical pair p <-> sample n0 - HALO + p
+    for (int u = tid; u < NP / 4; u += NT) {
+        const int i = n0 - HALO + 4 * u;            // multiple of 4, never straddles 0
+        float4 v;
+        if (i < 0) v = *reinterpret_cast<const float4*>(tail + DY4_IF_TAIL + i);
+        else if (i + 3 < n_if) v = __ldg(reinterpret_cast<const float4*>(row + i));
+        else { v.x = i < n_if ? row[i] : 0.f; v.y = i + 1 < n_if ? row[i + 1] : 0.f; v.z = i + 2 < n_if ? row[i + 2] : 0.f; v.w = 0.f; }
+        const int p = 4 * u;
+        float4* d = reinterpret_cast<float4*>(&sm[p + 2 * (p / R)]);
+        d[0] = make_float4(v.x, v.x, v.y, v.y);
+        d[1] = make_float4(v.z, v.z, v.w, v.w);
+    }
+    __syncthreads();
+
+    // output r of this thread is sample n0 + tid*R + r; tap k reads logical pair HALO + tid*R + r - k
+    // = tid*R + q with q = (HALO-100) + r + 100 - k
+    constexpr int C0 = HALO - (DY4_NTAPS - 1);
+    const u64* w = reinterpret_cast<const u64*>(sm) + (R + 2) * tid;
+    const u64* hh = reinterpret_cast<const u64*>(c_bpf2[mode].t);
+    u64 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int q = R - 1 + (DY4_NTAPS - 1); q >= 0; q--) {
+        const u64 x = w[C0 + q + 2 * ((C0 + q) / R)];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r + (DY4_NTAPS - 1) - q;
+            if (k >= 0 && k < DY4_NTAPS) acc[r] = tap2<EXACT>(acc[r], x, hh[k], nz);
+        }
+    }
+
+    float op[R], os[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) upk2(acc[r], op[r], os[r]);
+    const long long o = (long long)blockIdx.y * out_stride + n0 + tid * R;
+    const int left = n_if - (n0 + tid * R);
+    if (left >= R) {
+#pragma unroll
+        for (int r = 0; r < R; r += 4) {
+            *reinterpret_cast<float4*>(pilot + o + r) = make_float4(op[r], op[r + 1], op[r + 2], op[r + 3]);
+            *reinterpret_cast<float4*>(sband + o + r) = make_float4(os[r], os[r + 1], os[r + 2], os[r + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = op[r]; sband[o + r] = os[r]; }
+    }
+}
+
+}  // namespace
+
+cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
+{
+    if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
+    constexpr int R = 8, NT = 128;
+    dim3 grid((a.n_if + NT * R - 1) / (NT * R), a.n_streams);
+    k_twin_bpf<R, NT, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf4) { return cudaMemcpyToSymbol(c_bpf2, bpf4, sizeof(TapPairs) * 4); }

@@ -1,0 +1,145 @@
+"""Batched receiver: host-side handle over the throughput tier of include/dy4_b200.h.
+
+What `project <mode> <mono|stereo>` (reference src/project.cpp:137-330) does to one
+stdin stream, done to `n_streams` independent streams at once on one B200.  torch
+is used only to own device/pinned memory and streams; the library sees raw pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, check
+from .modes import mode_params
+
+FLAG_EXACT_AUDIO = 1
+KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails")
+
+
+def launch_count():
+    """Kernels launched by libdy4b200.so in this process so far."""
+    return int(lib.dy4_launch_count())
+
+
+class Pipeline:
+    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False):
+        self.mode, self.stereo, self.n_streams, self.device = int(mode), bool(stereo), int(n_streams), int(device)
+        self.params = mode_params(mode)
+        self.channels = 2 if stereo else 1
+        self._h = C.c_void_p()
+        check(lib.dy4_pipeline_create(self.mode, int(self.stereo), self.n_streams, self.device,
+                                      FLAG_EXACT_AUDIO if exact_audio else 0, C.byref(self._h)), "dy4_pipeline_create")
+
+    def close(self):
+        if self._h:
+            lib.dy4_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        check(lib.dy4_pipeline_reset(self._h), "dy4_pipeline_reset")
+
+    # ---- device-resident ---------------------------------------------------------------------
+    def process(self, iq, n_blocks=None, want=("pcm",), out=None, stream=None):
+        """iq: torch uint8 CUDA tensor [n_streams, >= n_blocks*block_size].  Returns a dict of torch tensors
+        for the names in `want` ("pcm", "audio", "if").  Asynchronous on `stream` (default: current stream)."""
+        import torch
+        p = self.params
+        assert iq.is_cuda and iq.dtype == torch.uint8 and iq.dim() == 2 and iq.shape[0] == self.n_streams
+        assert iq.stride(1) == 1
+        if n_blocks is None:
+            n_blocks = iq.shape[1] // p.block_size
+        dev = iq.device
+        out = dict(out or {})
+        na = n_blocks * p.audio_per_block * self.channels
+        if "pcm" in want and "pcm" not in out:
+            out["pcm"] = torch.empty((self.n_streams, na), dtype=torch.int16, device=dev)
+        if "audio" in want and "audio" not in out:
+            out["audio"] = torch.empty((self.n_streams, na), dtype=torch.float32, device=dev)
+        if "if" in want and "if" not in out:
+            out["if"] = torch.empty((self.n_streams, n_blocks * p.if_per_block), dtype=torch.float32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else None
+        check(lib.dy4_pipeline_process(self._h, C.c_void_p(iq.data_ptr()), iq.stride(0), int(n_blocks),
+                                       ptr("pcm"), ptr("audio"), ptr("if"), C.c_void_p(stream.cuda_stream)),
+              "dy4_pipeline_process")
+        return out
+
+    # ---- host buffers (H2D / compute / D2H overlapped inside the library) ------------------------
+    def process_host(self, iq, n_blocks=None, want=("pcm",), out=None, chunk_blocks=0):
+        """iq: uint8 host array/tensor [n_streams, >= n_blocks*block_size] (pinned torch tensor recommended).
+        Synchronous.  Returns numpy arrays (or fills the arrays/tensors passed in `out`)."""
+        p = self.params
+        a = _host_view(iq)
+        assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[0] == self.n_streams and a.strides[1] == 1
+        if n_blocks is None:
+            n_blocks = a.shape[1] // p.block_size
+        na = n_blocks * p.audio_per_block * self.channels
+        out = dict(out or {})
+        if "pcm" in want and "pcm" not in out:
+            out["pcm"] = np.empty((self.n_streams, na), np.int16)
+        if "audio" in want and "audio" not in out:
+            out["audio"] = np.empty((self.n_streams, na), np.float32)
+        hp = lambda k: C.c_void_p(_host_view(out[k]).ctypes.data) if k in out else None
+        check(lib.dy4_pipeline_process_host(self._h, C.c_void_p(a.ctypes.data), a.strides[0], int(n_blocks),
+                                            hp("pcm"), hp("audio"), int(chunk_blocks)), "dy4_pipeline_process_host")
+        return out
+
+    # ---- diagnostics ----------------------------------------------------------------------------
+    def debug_pilot_nco(self):
+        """(pilot, nco) of the last sub-chunk as torch tensors (copies)."""
+        import torch
+        dp, dn, stride, n = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_int()
+        check(lib.dy4_pipeline_debug_buffers(self._h, C.byref(dp), C.byref(dn), C.byref(stride), C.byref(n)), "dy4_pipeline_debug_buffers")
+        res = []
+        for ptr in (dp, dn):
+            t = torch.empty((self.n_streams, n.value), dtype=torch.float32, device="cuda:%d" % self.device)
+            rc = _cudart().cudaMemcpy2D(C.c_void_p(t.data_ptr()), C.c_size_t(n.value * 4), ptr, C.c_size_t(stride.value * 4),
+                                        C.c_size_t(n.value * 4), C.c_size_t(self.n_streams), 3)
+            assert rc == 0, rc
+            res.append(t)
+        return res
+
+    def profile(self, enable=True):
+        check(lib.dy4_pipeline_profile(self._h, int(enable)), "dy4_pipeline_profile")
+
+    def profile_get(self, reset=True):
+        ms = (C.c_double * len(KERNELS))()
+        n = (C.c_longlong * len(KERNELS))()
+        check(lib.dy4_pipeline_profile_get(self._h, ms, n, int(reset)), "dy4_pipeline_profile_get")
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(KERNELS)}
+
+    def get_state(self):
+        buf = np.empty(lib.dy4_pipeline_state_size(self._h), np.uint8)
+        check(lib.dy4_pipeline_get_state(self._h, C.c_void_p(buf.ctypes.data)), "dy4_pipeline_get_state")
+        return buf
+
+    def set_state(self, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        assert buf.size == lib.dy4_pipeline_state_size(self._h)
+        check(lib.dy4_pipeline_set_state(self._h, C.c_void_p(buf.ctypes.data)), "dy4_pipeline_set_state")
+
+
+def _host_view(x):
+    if isinstance(x, np.ndarray):
+        return x
+    return x.numpy()      # CPU torch tensor (pinned or not) shares memory with numpy
+
+
+_rt = None
+
+
+def _cudart():
+    global _rt
+    if _rt is None:
+        import torch, glob, os
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+            glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + \
+            glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+        _rt = C.CDLL(cands[0])
+    return _rt

@@ -1,0 +1,79 @@
+"""Deterministic synthetic FM-broadcast IQ streams (8-bit interleaved I,Q).
+
+Recipe of SURVEY.md §8(d): per stream s with base seed S, rng = PCG64(S+s);
+left/right tones in [300, 5000] Hz with amplitudes in [0.2, 0.5]; multiplex
+m = 0.45(L+R) + 0.1 sin(wp t + phi) + 0.45 (L-R) sin(2(wp t + phi)), wp = 2 pi 19 kHz;
+FM with 75 kHz deviation; additive N(0, 0.01^2) noise on I and Q;
+u8 = clip(round(100 x + 128), 0, 255).  The format is what the reference reads
+on stdin (rtl_sdr output, src/iofunc.cpp:113-120).
+
+Not on the hot path: this only feeds tests and the benchmark.
+"""
+import numpy as np
+
+RF_FS = {0: 2.4e6, 1: 1.44e6, 2: 2.4e6, 3: 1.92e6}  # reference src/project.cpp:180,192,204,216
+
+
+def stream_params(seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return dict(fL=rng.uniform(300, 5000), fR=rng.uniform(300, 5000),
+                aL=rng.uniform(0.2, 0.5), aR=rng.uniform(0.2, 0.5),
+                phi=rng.uniform(0, 2 * np.pi), noise_seed=int(rng.integers(0, 2**31)))
+
+
+def make_stream(mode, n_pairs, seed, rds=False):
+    """One stream: uint8[2*n_pairs], interleaved I0 Q0 I1 Q1 ..."""
+    fs = RF_FS[mode]
+    p = stream_params(seed)
+    t = np.arange(n_pairs, dtype=np.float64) / fs
+    L = p["aL"] * np.sin(2 * np.pi * p["fL"] * t)
+    R = p["aR"] * np.sin(2 * np.pi * p["fR"] * t)
+    wp = 2 * np.pi * 19e3 * t + p["phi"]
+    m = 0.45 * (L + R) + 0.1 * np.sin(wp) + 0.45 * (L - R) * np.sin(2 * wp)
+    if rds:
+        rng_b = np.random.Generator(np.random.PCG64(seed + 7919))
+        nbits = int(np.ceil(t[-1] * 1187.5)) + 2
+        bits = rng_b.integers(0, 2, nbits) * 2 - 1
+        sym = np.floor(t * 2375.0).astype(np.int64)          # Manchester: two half-symbols per bit
+        d = bits[sym // 2] * np.where(sym % 2 == 0, 1.0, -1.0)
+        m = m + 0.05 * d * np.cos(3 * wp)
+    phase = 2 * np.pi * 75e3 * np.cumsum(m) / fs
+    rng_n = np.random.Generator(np.random.PCG64(p["noise_seed"]))
+    noise = rng_n.normal(0.0, 0.01, size=(2, n_pairs))
+    out = np.empty(2 * n_pairs, np.uint8)
+    out[0::2] = np.clip(np.rint(100 * (np.cos(phase) + noise[0]) + 128), 0, 255).astype(np.uint8)
+    out[1::2] = np.clip(np.rint(100 * (np.sin(phase) + noise[1]) + 128), 0, 255).astype(np.uint8)
+    return out
+
+
+def make_batch(mode, n_streams, n_pairs, base_seed=65, rds=False):
+    """uint8[n_streams, 2*n_pairs]; stream s uses seed base_seed + s."""
+    return np.stack([make_stream(mode, n_pairs, base_seed + s, rds) for s in range(n_streams)])
+
+
+def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chunk_streams=16):
+    """Same signal model generated on the GPU with torch (benchmark input only:
+    the random draws differ from make_batch, the statistics do not)."""
+    import torch
+    fs = RF_FS[mode]
+    out = torch.empty((n_streams, 2 * n_pairs), dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    t = torch.arange(n_pairs, dtype=torch.float64, device=device) / fs
+    for s0 in range(0, n_streams, chunk_streams):
+        s1 = min(n_streams, s0 + chunk_streams)
+        ps = [stream_params(base_seed + s) for s in range(s0, s1)]
+        col = lambda k: torch.tensor([p[k] for p in ps], dtype=torch.float64, device=device)[:, None]
+        L = col("aL") * torch.sin(2 * np.pi * col("fL") * t)
+        R = col("aR") * torch.sin(2 * np.pi * col("fR") * t)
+        wp = 2 * np.pi * 19e3 * t + col("phi")
+        m = 0.45 * (L + R) + 0.1 * torch.sin(wp) + 0.45 * (L - R) * torch.sin(2 * wp)
+        del L, R, wp
+        phase = (2 * np.pi * 75e3 / fs) * torch.cumsum(m, dim=1)
+        del m
+        g.manual_seed(base_seed * 1000003 + s0)
+        for ch, fn in ((0, torch.cos), (1, torch.sin)):
+            x = fn(phase).to(torch.float32)
+            x += 0.01 * torch.randn(x.shape, generator=g, device=device, dtype=torch.float32)
+            out[s0:s1, ch::2] = torch.clamp(torch.round(100 * x + 128), 0, 255).to(torch.uint8)
+        del phase
+    return out

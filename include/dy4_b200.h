@@ -1,0 +1,161 @@
+/*
+ * dy4_b200.h — C ABI of libdy4b200.so: the B200 (sm_100a) implementation of the
+ * 3DY4 FM receiver's data-parallel hot path.
+ *
+ * The reference has no FFI: its "operator interface" for this path is the set
+ * of free C++ functions in /root/reference/include/filter.h:17-34, called only
+ * from src/project.cpp (frontend :72-93, backend :95-134, main :262-273,:310).
+ * This header is what a binding of that interface binds to.  Two tiers:
+ *
+ *  (1) Compatibility tier — one entry point per filter.h prototype, plain host
+ *      pointers and sizes, same argument meaning, state updated in place.  The
+ *      C++ shim csrc/filter_shim.cpp re-exports them under the reference's own
+ *      C++ signatures so project.cpp links against this library unchanged
+ *      (INTEGRATION.md).  Each call copies host->device, runs a CUDA kernel and
+ *      copies back: correct and drop-in, not fast.
+ *
+ *  (2) Throughput tier — a batched receiver ("pipeline") over n_streams
+ *      independent streams laid out [stream][time], state resident on the
+ *      device, fused sm_100a kernels.  This replaces the reference's block loop
+ *      (project.cpp:289-318), its stdin reader (iofunc.cpp:113-120) and its
+ *      threadSafeQ hand-off (threadSafeQ.cpp:18-55).
+ *
+ * All functions return 0 on success or a negative dy4 error code; the text of
+ * the last error on the calling thread is available from dy4_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with DY4_ERR_CUDA.
+ */
+#ifndef DY4_B200_H
+#define DY4_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DY4_OK 0
+#define DY4_ERR_ARG (-1)      /* invalid argument (mode, sizes, alignment, NULL) */
+#define DY4_ERR_CUDA (-2)     /* CUDA runtime error, see dy4_last_error()        */
+#define DY4_ERR_NOMEM (-3)
+
+const char* dy4_last_error(void);
+int dy4_version(void);
+
+/* ---- mode table: reference src/project.cpp:178-238 ----------------------- */
+typedef struct {
+    float rf_Fs;           /* IQ pairs per second in                          */
+    int   rf_decim;        /* front-end decimation                            */
+    float if_Fs;           /* IF rate ("audio_Fs" in the reference)           */
+    int   audio_decim;     /* D of the audio resampler                        */
+    int   audio_upsample;  /* U of the audio resampler                        */
+    int   audio_taps;      /* 101 * U                                         */
+    int   block_size;      /* bytes (interleaved uint8 I,Q) per block         */
+    int   if_per_block;    /* IF samples per block                            */
+    int   audio_per_block; /* audio samples per block and channel             */
+} dy4_mode_params_t;
+
+int dy4_mode_params(int mode, dy4_mode_params_t* out);
+
+/* ---- tap design (host side, one-time) ------------------------------------ */
+/* filter.h:17 impulseResponseLPF(Fs, Fc, num_taps, h, upFactor); h has num_taps floats */
+int dy4_lpf_taps(float Fs, float Fc, unsigned short num_taps, int up_factor, float* h);
+/* filter.h:27 impulseResponseBPF(Fs, Fb, Fe, num_taps, h, upFactor) */
+int dy4_bpf_taps(float Fs, float Fb, float Fe, unsigned short num_taps, int up_factor, float* h);
+
+/* ---- compatibility tier: host pointers, one stream ----------------------- */
+/* iofunc.cpp:117-119: out[k] = (raw[k]-128)/128 */
+int dy4_iq_to_float(const uint8_t* raw, size_t n, float* out);
+/* filter.h:18 convolveFIR: y has nx+nh-1 floats */
+int dy4_convolve_fir(float* y, const float* x, size_t nx, const float* h, size_t nh);
+/* filter.h:19 blockConvolveFIR: y has nx floats; state (nstate floats) is replaced by the tail of x */
+int dy4_block_fir(float* y, const float* x, size_t nx, const float* h, size_t nh, float* state, size_t nstate);
+/* filter.h:25 downsampleBlockConvolveFIR: y has nx/factor floats */
+int dy4_decim_fir(int factor, float* y, const float* x, size_t nx, const float* h, size_t nh, float* state, size_t nstate);
+/* filter.h:26 resampleBlockConvolveFIR: y has (nx/down)*up floats; *ny receives that count */
+int dy4_resample_fir(int up, int down, float* y, size_t* ny, const float* x, size_t nx, const float* h, size_t nh, float* state, size_t nstate);
+/* filter.h:20 fmDemodArctan */
+int dy4_fm_demod(const float* I, const float* Q, size_t n, float* prev_I, float* prev_Q, float* fm_demod);
+/* filter.h:29 fmPLL; the six float& of the reference in its argument order */
+int dy4_pll(const float* pll_in, size_t n, float freq, float Fs, float nco_scale, float phase_adjust, float norm_bandwidth,
+            float* nco_out, float* feedbackI, float* feedbackQ, float* integrator, float* phaseEst, float* trigOffset, float* nco_state);
+/* filter.h:22-23 downsample / upsample */
+int dy4_downsample(const float* data, size_t n, size_t factor, float* out, size_t* n_out);
+int dy4_upsample(const float* data, size_t n, size_t factor, float* out, size_t* n_out);
+/* filter.h:30 delayBlock */
+int dy4_delay_block(const float* in, size_t n, float* state, size_t nstate, float* out);
+/* filter.h:31-33: multiply carries the reference's gain of 2 (filter.cpp:264) */
+int dy4_pointwise_multiply(const float* a, size_t na, const float* b, size_t nb, float* out, size_t* n_out);
+int dy4_pointwise_add(const float* a, const float* b, size_t n, float* out);
+int dy4_pointwise_subtract(const float* a, const float* b, size_t n, float* out);
+/* filter.h:34 interleave: out has nl+nr floats */
+int dy4_interleave(const float* left, size_t nl, const float* right, size_t nr, float* out);
+
+/* ---- throughput tier: batched receiver ----------------------------------- */
+typedef struct dy4_pipeline dy4_pipeline_t;
+
+#define DY4_FLAG_EXACT_AUDIO 1u   /* also run the stages the PLL never sees (stereo-band BPF, resamplers)
+                                     with unfused multiply-add: every output is then bit-identical to
+                                     the reference instead of within ~1e-7 (default: fused where safe) */
+
+/* Create a receiver for `n_streams` independent streams in `mode` (0..3), mono (stereo=0)
+ * or stereo (stereo=1), on CUDA device `device`.  All carried state starts as in
+ * project.cpp:240-255 (zero history, PLL at feedbackI=1, nco_state=1). */
+int dy4_pipeline_create(int mode, int stereo, int n_streams, int device, unsigned flags, dy4_pipeline_t** out);
+int dy4_pipeline_destroy(dy4_pipeline_t* p);
+/* back to the initial state (start of a new set of streams) */
+int dy4_pipeline_reset(dy4_pipeline_t* p);
+
+/*
+ * Process `n_blocks` whole blocks of every stream.  DEVICE pointers.
+ *   d_iq        uint8 [n_streams][row_stride_bytes], interleaved I,Q; the first
+ *               n_blocks*block_size bytes of each row are consumed.  Rows and the
+ *               base must be 16-byte aligned.
+ *   d_pcm       int16 [n_streams][n_blocks*audio_per_block*channels]     or NULL
+ *   d_audio     float, same shape (stereo: interleaved L,R)              or NULL
+ *   d_if        float [n_streams][n_blocks*if_per_block]                 or NULL
+ *   stream      a cudaStream_t (as void*), NULL = the default stream
+ * Successive calls continue the same streams (state is carried on the device),
+ * exactly as successive blocks do in the reference.  Asynchronous on `stream`.
+ */
+int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stride_bytes, int n_blocks,
+                         int16_t* d_pcm, float* d_audio, float* d_if, void* stream);
+
+/*
+ * Same, HOST pointers (pinned memory recommended): input is cut into chunks of
+ * blocks, copied host->device on a copy stream into double-buffered staging
+ * while the previous chunk computes, and PCM/audio come back device->host on a
+ * third stream — the replacement for the reference's stdin reader + queue.
+ * Synchronous: returns when all outputs are in host memory.
+ */
+int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
+                              int16_t* h_pcm, float* h_audio, int chunk_blocks);
+
+/* Diagnostics (valid after a stereo process call): device pointers to the
+ * last sub-chunk's pilot and NCO rows, their stride in floats and length. */
+int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pilot, const float** d_nco, size_t* stride, int* n_if);
+
+/* Per-kernel timing with CUDA events on the launch stream.  enable!=0 turns it on.
+ * get: ms[] and launches[] have DY4_NUM_KERNELS entries, accumulated since the last reset. */
+#define DY4_NUM_KERNELS 5
+#define DY4_K_FRONTEND 0
+#define DY4_K_BPF 1
+#define DY4_K_PLL 2
+#define DY4_K_AUDIO 3
+#define DY4_K_TAILS 4
+int dy4_pipeline_profile(dy4_pipeline_t* p, int enable);
+int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long* launches, int reset);
+/* total kernels launched by this library in this process */
+long long dy4_launch_count(void);
+
+/* Checkpoint of the carried per-stream state (what project.cpp:25-53 holds in its structs):
+ * dy4_pipeline_state_size gives the byte count, get/set copy it device<->host. */
+size_t dy4_pipeline_state_size(const dy4_pipeline_t* p);
+int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf);
+int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DY4_B200_H */

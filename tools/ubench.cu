@@ -1,0 +1,194 @@
+// Instruction-throughput / latency microbenchmarks for B200 (sm_100a).
+// Purpose: measure the FP32 issue ceilings the FIR kernels are judged against
+// (scalar FFMA, unfused FMUL+FADD, packed f32x2 forms) and the FP64 / libm
+// latencies that bound the per-stream PLL recurrence.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench tools/ubench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+constexpr int ITER = 4096;
+constexpr int NCH = 16;
+
+__global__ void k_ffma(float* out, float a, float b) {
+    float acc[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 3 distinct register sources per FFMA (x*h + acc) as in a FIR
+__global__ void k_ffma3(float* out, float a, float b) {
+    float acc[NCH], x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = threadIdx.x + i; x[i] = a * i + threadIdx.x; }
+    float h0 = a, h1 = b;
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fmaf(x[i], h0, acc[i]);
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fmaf(x[(i + 1) % NCH], h1, acc[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_fmul_fadd(float* out, float a, float b) {
+    float acc[NCH], x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = threadIdx.x + i; x[i] = a * i + threadIdx.x; }
+    float h0 = a, h1 = b;
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x[i], h0));
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x[(i + 1) % NCH], h1));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+__global__ void k_ffma2(float* out, float a, float b) {
+    unsigned long long acc[NCH], x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = pk(threadIdx.x + i, i); x[i] = pk(a * i, threadIdx.x); }
+    unsigned long long h0 = pk(a, a), h1 = pk(b, b);
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = ffma2(x[i], h0, acc[i]);
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = ffma2(x[(i + 1) % NCH], h1, acc[i]);
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s ^= acc[i];
+    ((unsigned long long*)out)[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_fmul2_fadd2(float* out, float a, float b) {
+    unsigned long long acc[NCH], x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = pk(threadIdx.x + i, i); x[i] = pk(a * i, threadIdx.x); }
+    unsigned long long h0 = pk(a, a), h1 = pk(b, b);
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fadd2(acc[i], fmul2(x[i], h0));
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fadd2(acc[i], fmul2(x[(i + 1) % NCH], h1));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s ^= acc[i];
+    ((unsigned long long*)out)[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void k_dfma(double* out, double a, double b) {
+    double acc[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < ITER / 4; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- latency chains: one warp, one dependent chain, clock64 ----
+template <int OP>
+__global__ void k_lat(double* out, long long* cyc, double seed, int n) {
+    double v = seed;
+    float f = (float)seed;
+    long long t0 = clock64();
+    for (int i = 0; i < n; i++) {
+        if (OP == 0) v = fma(v, 1.0000001, 1e-9);                         // DFMA
+        if (OP == 1) f = fmaf(f, 1.0000001f, 1e-9f);                       // FFMA
+        if (OP == 2) v = atan2(v, 1.5) + 0.7;                              // double atan2
+        if (OP == 3) { double s, c; sincos(v, &s, &c); v = s + c + 1.3; }  // sincos small arg
+        if (OP == 4) { double s, c; sincos(v, &s, &c); v = s + c + 4.0e5; } // sincos large arg (> 105615)
+        if (OP == 5) { f = (float)((double)f * 1.0000001 + 1e-9); }        // F2F round trip + DFMA
+        if (OP == 6) v = 1.0 / (v + 2.0);                                  // double divide
+        if (OP == 7) v = cos(v) + 1.3;                                     // cos small
+        if (OP == 8) v = cos(v) + 4.0e5;                                   // cos large
+        if (OP == 9) f = __fdividef(1.0f, f + 2.0f);                        // fast float div
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = v + f;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+
+template <typename K, typename T>
+void run_tput(const char* name, K kern, T* buf, double ops_per_thread, int flops_per_op) {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int blocks = p.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; w++) kern<<<blocks, threads>>>(buf, 1.0001f, 0.5f);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        CK(cudaEventRecord(e0));
+        kern<<<blocks, threads>>>(buf, 1.0001f, 0.5f);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+    }
+    double ops = ops_per_thread * blocks * threads;
+    printf("%-16s %8.3f ms  %8.2f Ginstr(thread)/s  %8.2f TFLOP/s  (%.1f lane-ops/ns/SM)\n", name, best,
+           ops / best * 1e-6, ops * flops_per_op / best * 1e-9, ops / best * 1e-6 / p.multiProcessorCount);
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("device %s SMs %d clock %d kHz smem/SM %zu\n", p.name, p.multiProcessorCount, clk, p.sharedMemPerMultiprocessor);
+    float* buf; CK(cudaMalloc(&buf, 64 << 20));
+    double n = (double)ITER * NCH;
+    run_tput("ffma(imm-ish)", k_ffma, buf, n, 2);
+    run_tput("ffma 3reg", k_ffma3, buf, n, 2);
+    run_tput("fmul+fadd", k_fmul_fadd, buf, n, 2);       // counts MACs (2 instr each)
+    run_tput("ffma2 packed", k_ffma2, buf, n, 4);          // one instr = 2 MAC
+    run_tput("fmul2+fadd2", k_fmul2_fadd2, buf, n, 4);    // 2 instr = 2 MAC
+    run_tput("dfma", k_dfma, (double*)buf, n / 4, 2);
+
+    long long* cyc; CK(cudaMallocManaged(&cyc, 8));
+    const char* names[] = {"DFMA", "FFMA", "atan2(double)", "sincos small", "sincos large", "F2F+DFMA+F2F", "ddiv", "cos small", "cos large", "fdividef"};
+    int nrep = 2000;
+#define LAT(OP) { k_lat<OP><<<1, 32>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); k_lat<OP><<<1, 32>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); printf("lat %-16s %8.1f cycles/iter\n", names[OP], (double)*cyc / nrep); }
+    LAT(0) LAT(1) LAT(2) LAT(3) LAT(4) LAT(5) LAT(6) LAT(7) LAT(8) LAT(9)
+    return 0;
+}
