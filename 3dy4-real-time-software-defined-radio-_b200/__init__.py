@@ -20,6 +20,7 @@ from .modes import mode_params, ModeParams  # noqa: F401
 from .pipeline import Pipeline, launch_count  # noqa: F401
 from . import filterh  # noqa: F401
 from . import synth  # noqa: F401
+from . import shard  # noqa: F401
 
 PACKAGE_DIR = _os.path.dirname(_os.path.abspath(__file__))
 __all__ = ["lib", "Dy4Error", "Pipeline", "mode_params", "ModeParams", "filterh", "synth", "launch_count", "build_library"]

@@ -65,7 +65,9 @@ class Pipeline:
         if stream is None:
             stream = torch.cuda.current_stream(dev)
         ptr = lambda k: C.c_void_p(out[k].data_ptr()) if k in out else None
-        check(lib.dy4_pipeline_process(self._h, C.c_void_p(iq.data_ptr()), iq.stride(0), int(n_blocks),
+        # a single row may carry any stride (numpy/torch leave it arbitrary for size-1 dims)
+        row_stride = iq.stride(0) if self.n_streams > 1 else (n_blocks * p.block_size + 15) // 16 * 16
+        check(lib.dy4_pipeline_process(self._h, C.c_void_p(iq.data_ptr()), row_stride, int(n_blocks),
                                        ptr("pcm"), ptr("audio"), ptr("if"), C.c_void_p(stream.cuda_stream)),
               "dy4_pipeline_process")
         return out
@@ -86,7 +88,8 @@ class Pipeline:
         if "audio" in want and "audio" not in out:
             out["audio"] = np.empty((self.n_streams, na), np.float32)
         hp = lambda k: C.c_void_p(_host_view(out[k]).ctypes.data) if k in out else None
-        check(lib.dy4_pipeline_process_host(self._h, C.c_void_p(a.ctypes.data), a.strides[0], int(n_blocks),
+        row_stride = a.strides[0] if self.n_streams > 1 else n_blocks * p.block_size
+        check(lib.dy4_pipeline_process_host(self._h, C.c_void_p(a.ctypes.data), row_stride, int(n_blocks),
                                             hp("pcm"), hp("audio"), int(chunk_blocks)), "dy4_pipeline_process_host")
         return out
 

@@ -1,0 +1,77 @@
+"""Multi-GPU sharding of the stream batch: one process per GPU, streams partitioned by index.
+
+The path has no cross-stream dependency (every stream owns its filter history and PLL state,
+reference src/project.cpp:240-255), so there is NO data-path collective: rank g of G runs its
+own Pipeline on streams [g*N/G, (g+1)*N/G).  torch.distributed is used only for the barrier,
+the max-over-ranks timing and an optional host-side gather of the int16 audio to rank 0."""
+import os
+
+
+def stream_range(n_streams, world_size, rank):
+    """Contiguous, balanced slice of the batch owned by `rank` (first n_streams % world_size ranks get one extra)."""
+    assert 0 <= rank < world_size and n_streams >= 0
+    base, extra = divmod(n_streams, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def dist_env():
+    """(rank, local_rank, world_size) from the torchrun environment; (0, 0, 1) when launched directly."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_process_group(backend=None):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29512")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value, device="cpu"):
+    """max of a python float over all ranks (identity when not distributed)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device="cpu"):
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_rows_to_rank0(rows, n_streams):
+    """Host-side gather of per-rank output rows (CPU tensor [n_local, L]) into [n_streams, L] on rank 0.
+    Not on the timed path; returns None on other ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return rows
+    world, rank = dist.get_world_size(), dist.get_rank()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(rows, parts, dst=0)
+    if rank != 0:
+        return None
+    out = torch.cat(parts, dim=0)
+    assert out.shape[0] == n_streams
+    return out

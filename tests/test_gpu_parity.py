@@ -1,0 +1,266 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the golden fixtures minted
+from the reference and against the CPU checker (the reference replay oracle/_ref when it was built,
+else the C restatement) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): IF and float audio relative L2 <= 1e-5, int16 PCM within
+1 LSB.  What is actually asserted is stronger wherever the design makes it so: IF, pilot and NCO
+are BIT-EXACT always (they feed the PLL, which is chaotic in the last bit), and with
+exact_audio=True audio and PCM are bit-exact too."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden, bits, rel_l2
+
+pytestmark = pytest.mark.gpu
+MODES = [0, 1, 2, 3]
+TOL_L2 = 1e-5
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_gpu(dy4, mode, stereo, iq, exact_audio=False, want=("pcm", "audio", "if"), host=False, **kw):
+    import torch
+    iq = np.atleast_2d(iq)
+    p = dy4.Pipeline(mode, stereo, iq.shape[0], exact_audio=exact_audio)
+    try:
+        if host:
+            out = p.process_host(iq, want=[w for w in want if w != "if"], **kw)
+            return {k: np.asarray(v) for k, v in out.items()}, None
+        out = p.process(torch.from_numpy(iq).cuda(), want=want)
+        torch.cuda.synchronize()
+        dbg = [t.cpu().numpy() for t in p.debug_pilot_nco()] if stereo else None
+        return {k: v.cpu().numpy() for k, v in out.items()}, dbg
+    finally:
+        p.close()
+
+
+# ---------------------------------------------------------------- golden fixtures (the reference's own outputs)
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_stereo(dy4, mode):
+    g = golden("mode%d_stereo.npz" % mode)
+    out, (pilot, nco) = run_gpu(dy4, mode, 1, g["iq"], exact_audio=True)
+    assert np.array_equal(bits(out["if"][0]), bits(g["if"]))
+    assert np.array_equal(bits(pilot[0]), bits(g["pilot"]))
+    assert np.array_equal(bits(nco[0]), bits(g["nco"]))
+    assert np.array_equal(bits(out["audio"][0]), bits(g["audio"]))
+    assert np.array_equal(out["pcm"][0], g["pcm"])
+    out, _ = run_gpu(dy4, mode, 1, g["iq"], exact_audio=False)            # default (fused where the PLL cannot see it)
+    assert np.array_equal(bits(out["if"][0]), bits(g["if"]))
+    assert rel_l2(out["audio"][0], g["audio"]) <= TOL_L2
+    assert np.abs(out["pcm"][0].astype(np.int32) - g["pcm"]).max() <= 1
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_mono(dy4, mode):
+    iq = golden("mode%d_stereo.npz" % mode)["iq"]
+    g = golden("mode%d_mono.npz" % mode)
+    out, _ = run_gpu(dy4, mode, 0, iq, exact_audio=True)
+    assert np.array_equal(bits(out["audio"][0]), bits(g["audio"])) and np.array_equal(out["pcm"][0], g["pcm"])
+    out, _ = run_gpu(dy4, mode, 0, iq)
+    assert rel_l2(out["audio"][0], g["audio"]) <= TOL_L2
+    assert np.abs(out["pcm"][0].astype(np.int32) - g["pcm"]).max() <= 1
+
+
+def test_golden_long_stream_pll_chaos(dy4):
+    g = golden("mode0_stereo_long.npz")
+    m = dy4.mode_params(0)
+    iq = dy4.synth.make_stream(0, int(g["n_blocks"]) * m.block_size // 2, int(g["seed"]))
+    assert sha(iq) == str(g["iq_sha256"])
+    out, (pilot, nco) = run_gpu(dy4, 0, 1, iq, exact_audio=True)
+    assert sha(out["if"][0]) == str(g["if_sha256"])
+    assert sha(pilot[0]) == str(g["pilot_sha256"])
+    assert sha(nco[0]) == str(g["nco_sha256"])
+    assert np.array_equal(bits(out["audio"][0]), bits(g["audio"])) and np.array_equal(out["pcm"][0], g["pcm"])
+
+
+# ---------------------------------------------------------------- live checker on seeded batches
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("stereo", [0, 1])
+def test_batch_against_checker(dy4, checker, mode, stereo):
+    m = dy4.mode_params(mode)
+    S, nb = 5, 7
+    iq = dy4.synth.make_batch(mode, S, nb * m.block_size // 2, base_seed=200 + 10 * mode)
+    out, dbg = run_gpu(dy4, mode, stereo, iq)
+    oute, _ = run_gpu(dy4, mode, stereo, iq, exact_audio=True)
+    for s in range(S):
+        ref = checker.pipeline(mode, stereo, iq[s])
+        assert np.array_equal(bits(out["if"][s]), bits(ref["if"]))
+        assert rel_l2(out["audio"][s], ref["audio"]) <= TOL_L2
+        assert np.abs(out["pcm"][s].astype(np.int32) - ref["pcm"]).max() <= 1
+        assert np.array_equal(bits(oute["audio"][s]), bits(ref["audio"])) and np.array_equal(oute["pcm"][s], ref["pcm"])
+        if stereo:
+            assert np.array_equal(bits(dbg[0][s]), bits(ref["pilot"])) and np.array_equal(bits(dbg[1][s]), bits(ref["nco"]))
+
+
+def test_two_second_stream(dy4, checker):
+    """~2 s of mode 0 stereo (94 blocks, 481k IF samples): deep inside the regime where one differing
+    rounding anywhere upstream of the PLL would change the audio at the 1e-3 level."""
+    m = dy4.mode_params(0)
+    iq = dy4.synth.make_batch(0, 2, 94 * m.block_size // 2, base_seed=500)
+    out, (pilot, nco) = run_gpu(dy4, 0, 1, iq)
+    for s in range(2):
+        ref = checker.pipeline(0, 1, iq[s])
+        assert np.array_equal(bits(nco[s]), bits(ref["nco"]))
+        assert rel_l2(out["audio"][s], ref["audio"]) <= TOL_L2
+        assert np.abs(out["pcm"][s].astype(np.int32) - ref["pcm"]).max() <= 1
+
+
+# ---------------------------------------------------------------- chunking, host path, state
+def test_chunking_and_subchunking_do_not_change_results(dy4, monkeypatch):
+    import torch
+    m = dy4.mode_params(2)
+    iq = dy4.synth.make_batch(2, 3, 9 * m.block_size // 2, base_seed=31)
+    one, _ = run_gpu(dy4, 2, 1, iq, exact_audio=True)
+    d = torch.from_numpy(iq).cuda()
+    p = dy4.Pipeline(2, 1, 3, exact_audio=True)
+    parts = [p.process(d[:, a * m.block_size:b * m.block_size], want=("pcm", "audio", "if")) for a, b in ((0, 1), (1, 2), (2, 6), (6, 9))]
+    for k in one:
+        assert np.array_equal(torch.cat([x[k] for x in parts], 1).cpu().numpy(), one[k]), k
+    p.close()
+    monkeypatch.setenv("DY4_SUBCHUNK_BLOCKS", "2")           # force the internal time sub-chunking
+    sub, _ = run_gpu(dy4, 2, 1, iq, exact_audio=True)
+    for k in one:
+        assert np.array_equal(sub[k], one[k]), k
+
+
+@pytest.mark.parametrize("mode,stereo", [(0, 1), (1, 0), (3, 1)])
+def test_host_path_equals_device_path(dy4, mode, stereo):
+    import torch
+    m = dy4.mode_params(mode)
+    iq = dy4.synth.make_batch(mode, 4, 7 * m.block_size // 2, base_seed=77)
+    dev, _ = run_gpu(dy4, mode, stereo, iq)
+    host, _ = run_gpu(dy4, mode, stereo, iq, host=True, chunk_blocks=2)
+    assert np.array_equal(host["pcm"], dev["pcm"]) and np.array_equal(bits(host["audio"]), bits(dev["audio"]))
+    pinned = torch.from_numpy(iq).pin_memory()
+    host2, _ = run_gpu(dy4, mode, stereo, pinned.numpy(), host=True)     # default chunking, pinned input
+    assert np.array_equal(host2["pcm"], dev["pcm"])
+
+
+def test_checkpoint_restore(dy4):
+    import torch
+    m = dy4.mode_params(0)
+    iq = dy4.synth.make_batch(0, 2, 6 * m.block_size // 2, base_seed=5)
+    d = torch.from_numpy(iq).cuda()
+    p = dy4.Pipeline(0, 1, 2)
+    full = p.process(d, want=("pcm",))["pcm"].cpu().numpy()
+    p.reset()
+    p.process(d[:, :3 * m.block_size], want=("pcm",))
+    torch.cuda.synchronize()
+    ckpt = p.get_state()
+    p.close()
+    q = dy4.Pipeline(0, 1, 2)
+    q.set_state(ckpt)
+    rest = q.process(d[:, 3 * m.block_size:], want=("pcm",))["pcm"].cpu().numpy()
+    assert np.array_equal(rest, full[:, full.shape[1] // 2:])
+    q.close()
+
+
+def test_ragged_and_empty_inputs(dy4):
+    import torch
+    m = dy4.mode_params(0)
+    iq = dy4.synth.make_batch(0, 2, 2 * m.block_size // 2 + 1234, base_seed=9)   # trailing partial block
+    p = dy4.Pipeline(0, 0, 2)
+    d = torch.zeros((2, 3 * m.block_size), dtype=torch.uint8, device="cuda")
+    d[:, :iq.shape[1]] = torch.from_numpy(iq).cuda()
+    out = p.process(d[:, :iq.shape[1] // 16 * 16], want=("pcm",))                 # n_blocks = floor(bytes/block): 2
+    assert out["pcm"].shape == (2, 2 * m.audio_per_block)
+    p.reset()
+    assert p.process(d, n_blocks=0, want=())== {}
+    with pytest.raises(dy4.Dy4Error):
+        p.process(d[:, 1:], n_blocks=1, want=("pcm",))                           # misaligned rows are refused
+    p.close()
+
+
+def test_silence(dy4):
+    m = dy4.mode_params(1)
+    iq = np.full((2, 2 * m.block_size), 128, np.uint8)
+    out, _ = run_gpu(dy4, 1, 1, iq)
+    assert not out["if"].any() and not out["pcm"].any()
+
+
+# ---------------------------------------------------------------- filter.h compatibility tier, per op
+def test_filterh_ops_against_checker(dy4, checker):
+    fh = dy4.filterh
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(7000).astype(np.float32)
+    for nh in (101, 37, 1):
+        h = rng.standard_normal(nh).astype(np.float32)
+        ns = max(nh - 1, 1)
+        sa, sb = rng.standard_normal(ns).astype(np.float32), None
+        sb = sa.copy()
+        for blk in (x[:3000], x[3000:7000]):
+            assert np.array_equal(bits(fh.blockConvolveFIR(blk, h, sa)), bits(checker.block_fir(blk, h, sb)))
+            assert np.array_equal(sa, sb)
+        sa = np.zeros(ns, np.float32); sb = sa.copy()
+        for blk in (x[:3000], x[3000:7000]):
+            assert np.array_equal(bits(fh.downsampleBlockConvolveFIR(10, blk, h, sa)), bits(checker.decim_fir(10, blk, h, sb)))
+            assert np.array_equal(sa, sb)
+    hh = rng.standard_normal(101 * 147).astype(np.float32)
+    sa = np.zeros(100, np.float32); sb = sa.copy()
+    for blk in (x[:1600], x[1600:6400]):
+        assert np.array_equal(bits(fh.resampleBlockConvolveFIR(147, 800, blk, hh, sa)), bits(checker.resample_fir(147, 800, blk, hh, sb)))
+        assert np.array_equal(sa, sb)
+    I, Q = x[:3000].copy(), x[3000:6000].copy()
+    I[7] = Q[7] = 0.0
+    pb = [0.5, -0.25]
+    got, pi, pq = fh.fmDemodArctan(I, Q, 0.5, -0.25)
+    assert np.array_equal(bits(got), bits(checker.fm_demod(I, Q, pb))) and [pi, pq] == pb
+    pil = (0.1 * np.sin(2 * np.pi * 19e3 / 240e3 * np.arange(40000) + 1.0)).astype(np.float32)
+    pil[50] = 0.0
+    for scale, adj, bw in ((2.0, 0.0, 0.01), (0.5, 0.3, 0.001)):
+        sa = np.array([1, 0, 0, 0, 0, 1], np.float32); sb = sa.copy()
+        for a in (0, 20000):
+            assert np.array_equal(bits(fh.fmPLL(pil[a:a + 20000], 19e3, 240e3, scale, adj, bw, sa)),
+                                  bits(checker.pll(pil[a:a + 20000], 19e3, 240e3, scale, adj, bw, sb)))
+            assert np.array_equal(bits(sa), bits(sb))
+    sa = np.arange(50, dtype=np.float32); sb = sa.copy()
+    assert np.array_equal(fh.delayBlock(x[:600], sa), checker.delay_block(x[:600], sb)) and np.array_equal(sa, sb)
+    raw = rng.integers(0, 256, 5000, dtype=np.uint8)
+    assert np.array_equal(bits(fh.iqToFloat(raw)), bits(checker.iq_to_float(raw)))
+    a, b = x[:1000], x[1000:1900]
+    assert np.array_equal(fh.pointwiseMultiply(a, b), (a[:900] * b * np.float32(2)))
+    assert np.array_equal(fh.pointwiseAdd(a, x[2000:3000]), a + x[2000:3000])
+    assert np.array_equal(fh.pointwiseSubtract(a, x[2000:3000]), a - x[2000:3000])
+    il = fh.interleave(a, x[2000:3000])
+    assert np.array_equal(il[0::2], a) and np.array_equal(il[1::2], x[2000:3000])
+    assert np.array_equal(fh.downsample(a, 7), a[::7])
+    up = fh.upsample(a[:100], 3)
+    assert np.array_equal(up[::3], a[:100]) and not up[1::3].any() and not up[2::3].any()
+    full = fh.convolveFIR(a, x[5000:5101])
+    ref = checker.block_fir(np.concatenate([a, np.zeros(100, np.float32)]), x[5000:5101], np.zeros(100, np.float32))
+    assert np.array_equal(bits(full), bits(ref))
+
+
+# ---------------------------------------------------------------- BASELINE-size properties
+def test_config2_size_batch_independence_and_sampled_parity(dy4, checker):
+    """configs[1]: mode 0 stereo, 256 streams.  Streams are independent, so (a) a stream's output does not
+    depend on its slot or its neighbours, (b) a sample of streams equals the CPU checker."""
+    import torch
+    m = dy4.mode_params(0)
+    S, nb = 256, 6
+    base = dy4.synth.make_batch(0, 8, nb * m.block_size // 2, base_seed=65)
+    idx = np.arange(S) % 8
+    iq = base[idx]
+    out, _ = run_gpu(dy4, 0, 1, iq, want=("pcm", "audio"))
+    for s in range(8, S):
+        assert np.array_equal(out["pcm"][s], out["pcm"][idx[s]])
+    for s in (0, 3, 7):
+        ref = checker.pipeline(0, 1, base[s])
+        assert rel_l2(out["audio"][s], ref["audio"]) <= TOL_L2
+        assert np.abs(out["pcm"][s].astype(np.int32) - ref["pcm"]).max() <= 1
+
+
+def test_linearity_of_fir_stages_on_device(dy4):
+    """Size-independent property: the compat-tier FIR is linear within float rounding."""
+    fh = dy4.filterh
+    rng = np.random.default_rng(8)
+    x, y = rng.standard_normal(20000).astype(np.float32), rng.standard_normal(20000).astype(np.float32)
+    h = fh.impulseResponseLPF(2.4e6, 100e3, 101)
+    z = lambda: np.zeros(100, np.float32)
+    a = fh.downsampleBlockConvolveFIR(10, x, h, z()) + fh.downsampleBlockConvolveFIR(10, y, h, z())
+    b = fh.downsampleBlockConvolveFIR(10, x + y, h, z())
+    assert rel_l2(a, b) < 1e-6
