@@ -27,6 +27,8 @@ struct Dy4BpfArgs {
 
 struct Dy4PllArgs {
     const float* in; long long in_stride;       // pilot
+    float* theta; long long theta_stride;       // scratch: trigArg after each sample (the NCO row is derived from it)
+    float* nco0;                                // scratch [n_streams]: NCO value that opens this launch's row
     float* nco; long long nco_stride;
     float* state;                               // [n_streams][8]: fbI fbQ integ phase trigOffset nco_state pad pad
     int n, n_streams;
