@@ -152,14 +152,14 @@ extern "C" int dy4_pll(const float* pll_in, size_t n, float freq, float Fs, floa
 {
     if (!pll_in || !nco_out || !feedbackI || !feedbackQ || !integrator || !phaseEst || !trigOffset || !nco_state || !n) return DY4_ERR_ARG;
     Arena& a = t_arena;
-    int rc = a.reserve(3 * al(n * 4) + 2 * al(64));
+    int rc = a.reserve(2 * al(n * 4) + 2 * al(n * 8) + 2 * al(64));
     if (rc) return rc;
-    float* d_in = a.take<float>(n); float* d_nco = a.take<float>(n); float* d_th = a.take<float>(n); float* d_st = a.take<float>(8); float* d_n0 = a.take<float>(1);
+    float* d_in = a.take<float>(n); float* d_nco = a.take<float>(n); double* d_th = a.take<double>(n); double* d_inv = a.take<double>(n); float* d_st = a.take<float>(8); float* d_n0 = a.take<float>(1);
     float st[8] = {*feedbackI, *feedbackQ, *integrator, *phaseEst, *trigOffset, *nco_state, 0.f, 0.f};
     CU(cudaMemcpyAsync(d_in, pll_in, n * 4, cudaMemcpyHostToDevice, a.st));
     CU(cudaMemcpyAsync(d_st, st, sizeof(st), cudaMemcpyHostToDevice, a.st));
     Dy4PllArgs pa;
-    pa.in = d_in; pa.in_stride = (long long)n; pa.nco = d_nco; pa.nco_stride = (long long)n; pa.theta = d_th; pa.theta_stride = (long long)n; pa.nco0 = d_n0; pa.state = d_st;
+    pa.in = d_in; pa.in_stride = (long long)n; pa.nco = d_nco; pa.nco_stride = (long long)n; pa.theta = d_th; pa.inv = d_inv; pa.wide_stride = (long long)n; pa.nco0 = d_n0; pa.state = d_st;
     pa.n = (int)n; pa.n_streams = 1; pa.freq = freq; pa.Fs = Fs; pa.ncoScale = nco_scale; pa.phaseAdjust = phase_adjust; pa.normBandwidth = norm_bandwidth;
     CU(dy4_launch_pll(pa, a.st));
     CU(cudaMemcpyAsync(nco_out, d_nco, n * 4, cudaMemcpyDeviceToHost, a.st));

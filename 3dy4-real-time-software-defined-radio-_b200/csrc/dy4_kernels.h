@@ -27,7 +27,7 @@ struct Dy4BpfArgs {
 
 struct Dy4PllArgs {
     const float* in; long long in_stride;       // pilot
-    float* theta; long long theta_stride;       // scratch: trigArg after each sample (the NCO row is derived from it)
+    double* inv; double* theta; long long wide_stride;  // scratch rows of doubles: 1/x per input sample; trigArg after each sample
     float* nco0;                                // scratch [n_streams]: NCO value that opens this launch's row
     float* nco; long long nco_stride;
     float* state;                               // [n_streams][8]: fbI fbQ integ phase trigOffset nco_state pad pad

@@ -48,7 +48,8 @@ struct dy4_pipeline {
     // carried state
     uint8_t* iq_tail = nullptr; float* if_tail = nullptr; float* mix_tail = nullptr; float* pll_state = nullptr;
     // workspace for one sub-chunk
-    float *ws_if = nullptr, *ws_pilot = nullptr, *ws_sband = nullptr, *ws_nco = nullptr, *ws_theta = nullptr, *ws_nco0 = nullptr;
+    float *ws_if = nullptr, *ws_pilot = nullptr, *ws_sband = nullptr, *ws_nco = nullptr, *ws_nco0 = nullptr;
+    double *ws_theta = nullptr, *ws_inv = nullptr;
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0;
     // host-facing staging
     uint8_t* d_stage[2] = {nullptr, nullptr}; int16_t* d_pcm_stage[2] = {nullptr, nullptr}; float* d_audio_stage[2] = {nullptr, nullptr};
@@ -119,15 +120,15 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
 {
     size_t budget = 3ull << 30;
     if (const char* e = std::getenv("DY4_WS_BYTES")) budget = std::strtoull(e, nullptr, 10);
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 5 : 1);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 8 : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
     if (const char* e = std::getenv("DY4_SUBCHUNK_BLOCKS")) blocks = std::max(1, atoi(e));
     if (p->ws_blocks >= blocks) return DY4_OK;
     if (p->ws_blocks > 0) {
         CU(cudaDeviceSynchronize());
-        cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta);
-        p->ws_if = p->ws_pilot = p->ws_sband = p->ws_nco = p->ws_theta = nullptr;
+        cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta); cudaFree(p->ws_inv);
+        p->ws_if = p->ws_pilot = p->ws_sband = p->ws_nco = nullptr; p->ws_theta = p->ws_inv = nullptr;
         p->ws_blocks = 0;
     }
     p->ws_stride = (size_t)blocks * p->mp.if_per_block;
@@ -137,7 +138,8 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         CU(cudaMalloc(&p->ws_pilot, bytes));
         CU(cudaMalloc(&p->ws_sband, bytes));
         CU(cudaMalloc(&p->ws_nco, bytes));
-        CU(cudaMalloc(&p->ws_theta, bytes));
+        CU(cudaMalloc(&p->ws_theta, 2 * bytes));
+        CU(cudaMalloc(&p->ws_inv, 2 * bytes));
         if (!p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, (size_t)p->n_streams * sizeof(float)));
     }
     p->ws_blocks = blocks;
@@ -179,7 +181,7 @@ int run_subchunk(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int nb
 
         Dy4PllArgs pa;
         pa.in = p->ws_pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = p->ws_nco; pa.nco_stride = (long long)p->ws_stride;
-        pa.theta = p->ws_theta; pa.theta_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0;
+        pa.theta = p->ws_theta; pa.inv = p->ws_inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0;
         pa.state = p->pll_state; pa.n = n_if; pa.n_streams = p->n_streams;
         pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
         { Timer t(p, DY4_K_PLL, st); CU(dy4_launch_pll(pa, st)); }
@@ -286,7 +288,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     for (auto e : p->pool) cudaEventDestroy(e);
     cudaFree(p->d_rf_taps); cudaFree(p->d_taps_poly);
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
-    cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta); cudaFree(p->ws_nco0);
+    cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta); cudaFree(p->ws_inv); cudaFree(p->ws_nco0);
     for (int i = 0; i < 2; i++) { cudaFree(p->d_stage[i]); cudaFree(p->d_pcm_stage[i]); cudaFree(p->d_audio_stage[i]); }
     if (p->streams_ready) {
         cudaStreamDestroy(p->s_compute); cudaStreamDestroy(p->s_h2d); cudaStreamDestroy(p->s_d2h);

@@ -24,102 +24,155 @@
 #include "dy4_internal.h"
 #include "dy4_pllmath.h"
 
+#include <cstdlib>
+#include <string>
+
 namespace {
 
 struct PllConst { double w; float Kp, Ki, ncoScale, phaseAdjust; };
 
-struct PllRegs { float fbI, fbQ, integ, phase, trigOffset; };
+// float state of the reference (filter.cpp:174 signature) plus the binade tracker for trigArg's rounding
+struct PllRegs { float fbI, fbQ, integ, phase; double trigOffset; double lim, lim2, magic; };   // trigOffset: float VALUE kept in a double
 
-// Everything after the phase detector: loop filter, phase accumulator, NCO (filter.cpp:206-222).
-// `o` receives sin/cos of the new trigArg together with its reduction, for the next detector call.
 __device__ __forceinline__ float nco_value(float trigArg, float ncoScale, float phaseAdjust)
 {
     const float narg = __fadd_rn(__fmul_rn(trigArg, ncoScale), phaseAdjust);   // float, as filter.cpp:219/:221
     dy4_nco_t on;
-    dy4_sincos_nco((double)narg, &on);
+    dy4_sincos_nco((double)narg, 0, &on);
     return __double2float_rn(on.c);
 }
 
-// returns the new trigArg (the NCO output is a pure function of it and is evaluated by k_nco)
-__device__ __forceinline__ float pll_advance(float eD, PllRegs& s, const PllConst& c, dy4_nco_t& o)
+// Everything after the phase detector: loop filter, phase accumulator, NCO phase (filter.cpp:206-217).
+// Returns the new trigArg as a double holding a float value (the NCO output is a pure function of it and
+// is evaluated by k_nco).  `o` receives sin/cos of it and the reference angle for the next detector call.
+template <int GRID, bool SELB>
+__device__ __forceinline__ double pll_advance(float eD, PllRegs& s, const PllConst& c, dy4_nco_t& o, bool next_neg)
 {
     s.integ = __fadd_rn(s.integ, __fmul_rn(c.Ki, eD));                         // :207
     s.phase = __fadd_rn(s.phase, __fadd_rn(__fmul_rn(c.Kp, eD), s.integ));     // :210
-    s.trigOffset = __fadd_rn(s.trigOffset, 1.0f);                              // :213
-    const float trigArg = __double2float_rn(__dadd_rn(__dmul_rn(c.w, (double)s.trigOffset), (double)s.phase)); // :214
-    dy4_sincos_nco((double)trigArg, &o);
+    s.trigOffset = fmin(s.trigOffset + 1.0, 16777216.0);                       // :213 float counter: exact below 2^24, sticks there (16777217 rounds back)
+    const double arg = __dadd_rn(__dmul_rn(c.w, s.trigOffset), (double)s.phase);            // :214, in double
+    // :214 narrows to float.  Inside the tracked binade [lim, 2 lim) that is an add/subtract of a magic
+    // constant on the double pipe (ties to even, same grid) instead of two conversions.
+    // GRID_SAFE: the caller has shown that arg stays inside the binade for this step, no check needed.
+    double th;
+    if (GRID == 0) th = (double)__double2float_rn(arg);
+    else th = dy4_round_to_float_grid(arg, s.magic);
+    if (GRID == 1 && !(arg >= s.lim && arg < s.lim2)) {                        // binade changed (24 times per stream) or start-up
+        th = (double)__double2float_rn(arg);
+        const int hi = __double2hiint(th);
+        if (hi >= 0x38100000 && hi < 0x47e00000) {                             // positive, comfortably inside float's normal range
+            s.lim = __hiloint2double(hi & 0x7ff00000, 0);
+            s.lim2 = s.lim + s.lim;
+            s.magic = s.lim * 805306368.0;                                     // 1.5 * 2^29
+        } else { s.lim = 0.0; s.lim2 = 0.0; s.magic = 0.0; }
+    }
+    dy4_sincos_nco_v(th, next_neg, &o, SELB);
     s.fbI = __double2float_rn(o.c);                                            // :216
     s.fbQ = __double2float_rn(o.s);                                            // :217
-    return trigArg;
+    return th;
 }
 
-// One PLL step with the libm phase detector: used for the first sample of a launch (the carried
-// feedbackI/Q come from the caller) and for inputs the fast detector does not cover (0, denormal, inf, NaN).
-__device__ __noinline__ float detector_libm(float x, const PllRegs& s)
+// The libm phase detector: used for the first sample of a launch (the carried feedbackI/Q come from the
+// caller) and for inputs the fast detector does not cover (0, denormal, inf, NaN).
+__device__ __noinline__ float detector_libm(float x, float fbI, float fbQ)
 {
-    const float eI = __fmul_rn((x == 0.0f ? 1.0f : x), s.fbI);                 // filter.cpp:192
-    const float eQ = __fmul_rn(x, -s.fbQ);                                     // :193
+    const float eI = __fmul_rn((x == 0.0f ? 1.0f : x), fbI);                   // filter.cpp:192
+    const float eQ = __fmul_rn(x, -fbQ);                                       // :193
     return __double2float_rn(atan2((double)eQ, (double)eI));                   // :200
 }
 
-__device__ __forceinline__ float pll_step(float x, double inv_x, PllRegs& s, const PllConst& c, dy4_nco_t& o, bool have_o)
+__device__ __forceinline__ bool fast_ok(float x) { const float ax = fabsf(x); return ax > 1e-20f && ax < 1e20f; }
+
+// Fast step: x is a normal, finite, non-zero float and `o` describes the current feedbackI/Q.  Straight-line code.
+template <int GRID, bool SELB>
+__device__ __forceinline__ double pll_step_fast(float x, double inv_x, float x_next, PllRegs& s, const PllConst& c, dy4_nco_t& o)
 {
-    float eD;
-    const float ax = fabsf(x);
-    if (have_o && ax > 1e-20f && ax < 1e20f) {
-        const float eI = __fmul_rn(x, s.fbI);
-        const float eQ = __fmul_rn(x, -s.fbQ);
-        eD = __double2float_rn(dy4_detector_atan2((double)eQ, (double)eI, x < 0.0f ? 1.0 : 0.0, &o, inv_x));
-    } else {
-        eD = detector_libm(x, s);
-    }
-    return pll_advance(eD, s, c, o);
+    const float eI = __fmul_rn(x, s.fbI);                                      // filter.cpp:192 (x != 0)
+    const float eQ = __fmul_rn(x, -s.fbQ);                                     // :193
+    const float eD = __double2float_rn(dy4_detector_atan2((double)eQ, (double)eI, &o, inv_x));  // :200
+    return pll_advance<GRID, SELB>(eD, s, c, o, x_next < 0.0f);
 }
 
+// `o_matches_x`: o.base_* was prepared for the sign of this x (true after any step that was given x as x_next)
+template <bool SELB>
+__device__ __forceinline__ double pll_step_any(float x, float x_next, PllRegs& s, const PllConst& c, dy4_nco_t& o, bool o_valid)
+{
+    if (o_valid && fast_ok(x)) return pll_step_fast<1, SELB>(x, dy4_recip(x), x_next, s, c, o);
+    return pll_advance<1, SELB>(detector_libm(x, s.fbI, s.fbQ), s, c, o, x_next < 0.0f);
+}
+
+template <int GRID, bool SELB>
 __global__ void __launch_bounds__(32)
-k_pll(const float* __restrict__ in, long long in_stride, float* __restrict__ theta, long long theta_stride,
+k_pll(const float* __restrict__ in, long long in_stride, const double* __restrict__ inv, double* __restrict__ theta, long long wide_stride,
       float* __restrict__ nco0, float* __restrict__ state, int n, int n_streams, PllConst c)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     float* st = state + (long long)s * 8;
-    PllRegs r = {st[0], st[1], st[2], st[3], st[4]};
+    PllRegs r = {st[0], st[1], st[2], st[3], (double)st[4], 0.0, 0.0, 0.0};
     nco0[s] = st[5];                             // nco_state opens this launch's NCO row (filter.cpp:184)
     const float* x = in + (long long)s * in_stride;
-    float* y = theta + (long long)s * theta_stride;
+    const double* ix = inv + (long long)s * wide_stride;      // 1/x per sample from k_pll_prep, 0 where the fast detector does not apply
+    double* y = theta + (long long)s * wide_stride;
     dy4_nco_t o;
-    o.c = 1.0; o.s = 0.0; o.rho_hi = 0.0; o.rho_lo = 0.0; o.n = 0;
-    bool have_o = false;
-    float last = 0.0f;
-    const int n4 = n & ~3;
-    float4 v = n4 > 0 ? *reinterpret_cast<const float4*>(x) : make_float4(0, 0, 0, 0);
-    for (int k = 0; k < n4; k += 4) {
+    o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
+    if (n <= 0) return;
+    // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
+    double th = pll_advance<1, SELB>(detector_libm(x[0], r.fbI, r.fbQ), r, c, o, n > 1 && x[1] < 0.0f);
+    y[0] = th;
+    int k = 1;
+    for (; k < n && (k & 3); k++) { th = pll_step_any<SELB>(x[k], k + 1 < n ? x[k + 1] : 0.0f, r, c, o, true); y[k] = th; }
+    // two groups of four samples (and their reciprocals) are kept in registers ahead of the recurrence (the step
+    // that closes a group needs the sign of the next group's first sample), so no load is ever waited on
+    const float4 z4 = make_float4(0, 0, 0, 0);
+    const double2 zd = make_double2(0, 0);
+    float4 v = k + 4 <= n ? *reinterpret_cast<const float4*>(x + k) : z4;
+    double2 ia = k + 4 <= n ? *reinterpret_cast<const double2*>(ix + k) : zd, ib = k + 4 <= n ? *reinterpret_cast<const double2*>(ix + k + 2) : zd;
+    float4 v2 = k + 8 <= n ? *reinterpret_cast<const float4*>(x + k + 4) : z4;
+    double2 ia2 = k + 8 <= n ? *reinterpret_cast<const double2*>(ix + k + 4) : zd, ib2 = k + 8 <= n ? *reinterpret_cast<const double2*>(ix + k + 6) : zd;
+    for (; k + 4 <= n; k += 4) {
         const float4 cur = v;
-        if (k + 4 < n4) v = *reinterpret_cast<const float4*>(x + k + 4);
-        // reciprocals of the inputs: known ahead of the recurrence, so off its critical path
-        const double i0 = dy4_recip(cur.x), i1 = dy4_recip(cur.y), i2 = dy4_recip(cur.z), i3 = dy4_recip(cur.w);
-        float4 out;
-        out.x = pll_step(cur.x, i0, r, c, o, have_o);
-        have_o = true;
-        out.y = pll_step(cur.y, i1, r, c, o, true);
-        out.z = pll_step(cur.z, i2, r, c, o, true);
-        out.w = pll_step(cur.w, i3, r, c, o, true);
-        last = out.w;
-        *reinterpret_cast<float4*>(y + k) = out;
+        const double2 ca = ia, cb = ib;
+        v = v2; ia = ia2; ib = ib2;
+        if (k + 12 <= n) {
+            v2 = *reinterpret_cast<const float4*>(x + k + 8);
+            ia2 = *reinterpret_cast<const double2*>(ix + k + 8);
+            ib2 = *reinterpret_cast<const double2*>(ix + k + 10);
+        }
+        float nx = v.x;                                                       // the sample after this group
+        if (k + 8 > n) nx = (k + 4 < n) ? x[k + 4] : 0.0f;
+        // Per step the phase argument moves by w + (Kp*eD + integ): |Kp*eD| <= 0.0267*pi and the integrator drifts by
+        // < 1.2e-3 per step, so with |integ| < 0.1 four steps move it by at most 4*(w+0.2) and at least 4*min(0,w-0.2).
+        // If that range stays inside the tracked binade the narrowing to float needs no per-step check.
+        const double up4 = 4.0 * (c.w + 0.2), dn4 = fmin(0.0, 4.0 * (c.w - 0.2)) + fmin(0.0, c.w - 0.2);
+        const bool grid_safe = GRID != 2 || ((th + dn4 >= r.lim) && (th + up4 < r.lim2) && (fabsf(r.integ) < 0.1f) && (c.Kp <= 0.0267f));
+        const bool fast4 = (ca.x != 0.0) && (ca.y != 0.0) && (cb.x != 0.0) && (cb.y != 0.0);
+        double t0, t1, t2, t3;
+        if (fast4 && grid_safe) {
+            t0 = pll_step_fast<GRID, SELB>(cur.x, ca.x, cur.y, r, c, o);
+            t1 = pll_step_fast<GRID, SELB>(cur.y, ca.y, cur.z, r, c, o);
+            t2 = pll_step_fast<GRID, SELB>(cur.z, cb.x, cur.w, r, c, o);
+            t3 = pll_step_fast<GRID, SELB>(cur.w, cb.y, nx, r, c, o);
+        } else {
+            t0 = pll_step_any<SELB>(cur.x, cur.y, r, c, o, true);
+            t1 = pll_step_any<SELB>(cur.y, cur.z, r, c, o, true);
+            t2 = pll_step_any<SELB>(cur.z, cur.w, r, c, o, true);
+            t3 = pll_step_any<SELB>(cur.w, nx, r, c, o, true);
+        }
+        th = t3;
+        *reinterpret_cast<double2*>(y + k) = make_double2(t0, t1);
+        *reinterpret_cast<double2*>(y + k + 2) = make_double2(t2, t3);
     }
-    for (int k = n4; k < n; k++) {
-        last = pll_step(x[k], dy4_recip(x[k]), r, c, o, have_o);
-        y[k] = last;
-        have_o = true;
-    }
-    st[0] = r.fbI; st[1] = r.fbQ; st[2] = r.integ; st[3] = r.phase; st[4] = r.trigOffset;
-    st[5] = nco_value(last, c.ncoScale, c.phaseAdjust);      // nco_state for the next launch (filter.cpp:218-219)
+    for (; k < n; k++) { th = pll_step_any<SELB>(x[k], k + 1 < n ? x[k + 1] : 0.0f, r, c, o, true); y[k] = th; }
+    st[0] = r.fbI; st[1] = r.fbQ; st[2] = r.integ; st[3] = r.phase; st[4] = (float)r.trigOffset;
+    st[5] = nco_value((float)th, c.ncoScale, c.phaseAdjust);      // nco_state for the next launch (filter.cpp:218-219)
 }
 
 // NCO row from the phase row: nco[0] = carried nco_state, nco[k] = cos(trigArg[k-1]*ncoScale + phaseAdjust)
 // (filter.cpp:184,219-221).  Not part of the recurrence, so it runs as a plain data-parallel pass.
 __global__ void __launch_bounds__(256)
-k_nco(const float* __restrict__ theta, long long theta_stride, const float* __restrict__ nco0,
+k_nco(const double* __restrict__ theta, long long theta_stride, const float* __restrict__ nco0,
       float* __restrict__ nco, long long nco_stride, int n, float ncoScale, float phaseAdjust)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,8 +180,20 @@ k_nco(const float* __restrict__ theta, long long theta_stride, const float* __re
     if (k >= n) return;
     float v;
     if (k == 0) v = nco0[s];
-    else v = nco_value(__ldg(theta + (long long)s * theta_stride + k - 1), ncoScale, phaseAdjust);
+    else v = nco_value((float)__ldg(theta + (long long)s * theta_stride + k - 1), ncoScale, phaseAdjust);
     nco[(long long)s * nco_stride + k] = v;
+}
+
+// Reciprocal of every PLL input sample, in double (dy4_recip: exact-rounded float reciprocal + one Newton step).
+// The detector divides by the input sample; the inputs are known before the recurrence runs, so this is a plain
+// data-parallel pre-pass.  0 marks samples the fast detector does not cover (0, denormal, huge, inf, NaN).
+__global__ void __launch_bounds__(256)
+k_pll_prep(const float* __restrict__ in, long long in_stride, double* __restrict__ inv, long long inv_stride, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float x = __ldg(in + (long long)blockIdx.y * in_stride + k);
+    inv[(long long)blockIdx.y * inv_stride + k] = fast_ok(x) ? dy4_recip(x) : 0.0;
 }
 
 }  // namespace
@@ -145,13 +210,25 @@ cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
     c.w = 2 * 3.14159265358979323846 * (double)ratio;           // (2*PI)*(freq/Fs), left to right in double
     c.ncoScale = a.ncoScale;
     c.phaseAdjust = a.phaseAdjust;
-    const int threads = 32;
-    k_pll<<<(a.n_streams + threads - 1) / threads, threads, 0, st>>>(a.in, a.in_stride, a.theta, a.theta_stride, a.nco0, a.state, a.n, a.n_streams, c);
+    static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
+    {
+        dim3 gp((a.n + 255) / 256, a.n_streams);
+        k_pll_prep<<<gp, 256, 0, st>>>(a.in, a.in_stride, a.inv, a.wide_stride, a.n);
+        g_dy4_launches++;
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return e0;
+    }
+    // DY4_PLL_NARROW=f2f selects the plain double->float->double narrowing of trigArg instead of the
+    // magic-constant rounding inside a tracked binade (A/B knob; results are identical, see tests).
+    static const bool f2f = std::getenv("DY4_PLL_NARROW") && std::string(std::getenv("DY4_PLL_NARROW")) == "f2f";
+    const dim3 g((a.n_streams + threads - 1) / threads);
+    if (f2f) k_pll<0, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
+    else k_pll<2, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
     g_dy4_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid((a.n + 255) / 256, a.n_streams);
-    k_nco<<<grid, 256, 0, st>>>(a.theta, a.theta_stride, a.nco0, a.nco, a.nco_stride, a.n, a.ncoScale, a.phaseAdjust);
+    k_nco<<<grid, 256, 0, st>>>(a.theta, a.wide_stride, a.nco0, a.nco, a.nco_stride, a.n, a.ncoScale, a.phaseAdjust);
     g_dy4_launches++;
     return cudaGetLastError();
 }

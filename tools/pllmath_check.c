@@ -41,7 +41,7 @@ int main(int argc, char** argv)
         for (long i = 0; i < n; i++) {
             float xf = (float)(urand() * (i & 1 ? 8.3e6 : 2000.0));
             if (i % 7 == 0) xf = (float)(urand() * 3.0);
-            dy4_nco_t o; dy4_sincos_nco((double)xf, &o);
+            dy4_nco_t o; dy4_sincos_nco((double)xf, 0, &o);
             double rs = sin((double)xf), rc = cos((double)xf);
             if ((float)o.s != (float)rs) bad_s++;
             if ((float)o.c != (float)rc) bad_c++;
@@ -58,38 +58,44 @@ int main(int argc, char** argv)
         int ns = atoi(argv[2]); long n = atol(argv[3]);
         float Kp = 0.01f * 2.666f, Ki = 0.01f * 0.01f * 3.555f;
         float ratio = 19e3f / 240e3f; double w = 2 * 3.14159265358979323846 * (double)ratio;
-        long total_mis = 0, streams_bad = 0, det_mis = 0, sc_mis = 0;
+        long total_mis = 0, streams_bad = 0, det_mis = 0, sc_mis = 0, grid_mis = 0;
         for (int s = 0; s < ns; s++) {
             regs_t a = {1, 0, 0, 0, 0}, b = {1, 0, 0, 0, 0};
-            dy4_nco_t o; dy4_sincos_nco(0.0, &o);
+            dy4_nco_t o; float xn = 0; int have_o = 0;
             double ph0 = urand() * 6.28, amp = 0.02 + 0.1 * urand(), df = 19e3 * (1 + 2e-5 * (urand() - 0.5));
             long first_bad = -1;
+            xn = (float)(amp * sin(ph0) + 0.003 * (urand() - 0.5));
             for (long k = 0; k < n; k++) {
-                float x = (float)(amp * sin(2 * 3.14159265358979323846 * df / 240e3 * k + ph0) + 0.003 * (urand() - 0.5));
+                float x = xn;
+                xn = (float)(amp * sin(2 * 3.14159265358979323846 * df / 240e3 * (k + 1) + ph0) + 0.003 * (urand() - 0.5));
                 step_ref(x, &a, w, Kp, Ki, 2.0f, 0.0f);
                 /* fast path, same float ops around the custom double math */
                 float eI = (x == 0 ? 1 : x) * b.fbI;
                 float eQ = x * (-1 * b.fbQ);
                 float eD;
-                if (fabsf(x) > 1e-20f && fabsf(x) < 1e20f) {
+                if (have_o && fabsf(x) > 1e-20f && fabsf(x) < 1e20f) {
                     double inv_x = dy4_recip(x);
-                    eD = (float)dy4_detector_atan2((double)eQ, (double)eI, x < 0 ? 1.0 : 0.0, &o, inv_x);
+                    eD = (float)dy4_detector_atan2((double)eQ, (double)eI, &o, inv_x);
                     float eDr = (float)atan2((double)eQ, (double)eI);
                     if (eD != eDr) det_mis++;
                 } else eD = (float)atan2((double)eQ, (double)eI);
                 float t0 = Ki * eD; b.integ = b.integ + t0;
                 float t1 = Kp * eD; float t2 = t1 + b.integ; b.phase = b.phase + t2;
                 b.trigOffset = b.trigOffset + 1.0f;
-                float trigArg = (float)(w * (double)b.trigOffset + (double)b.phase);
-                dy4_sincos_nco((double)trigArg, &o);
+                double argd = w * (double)b.trigOffset + (double)b.phase;
+                float trigArg = (float)argd;
+                /* the magic-number rounding the device uses inside a binade must agree with the float conversion */
+                if (argd >= 1.0) { int ex; frexp(argd, &ex); double lim = ldexp(1.0, ex - 1); double mg = 1.5 * lim * 536870912.0;
+                    if (dy4_round_to_float_grid(argd, mg) != (double)trigArg) grid_mis++; }
+                dy4_sincos_nco((double)trigArg, xn < 0, &o); have_o = 1;
                 b.fbI = (float)o.c; b.fbQ = (float)o.s;
                 if (b.fbI != (float)cos((double)trigArg) || b.fbQ != (float)sin((double)trigArg)) sc_mis++;
                 if (first_bad < 0 && (a.fbI != b.fbI || a.fbQ != b.fbQ || a.phase != b.phase || a.integ != b.integ)) first_bad = k;
             }
             if (first_bad >= 0) { streams_bad++; total_mis++; printf("  stream %d diverged at sample %ld\n", s, first_bad); }
         }
-        printf("pll: %d streams x %ld samples: %ld diverged; per-call float mismatches: detector %ld, sincos %ld (of %ld calls each)\n",
-               ns, n, streams_bad, det_mis, sc_mis, (long)ns * n);
+        printf("pll: %d streams x %ld samples: %ld diverged; per-call float mismatches: detector %ld, sincos %ld, grid-rounding %ld (of %ld calls each)\n",
+               ns, n, streams_bad, det_mis, sc_mis, grid_mis, (long)ns * n);
         return 0;
     }
     fprintf(stderr, "usage: %s sincos N | pll STREAMS SAMPLES\n", argv[0]);
