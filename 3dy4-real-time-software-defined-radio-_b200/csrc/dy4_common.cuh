@@ -64,4 +64,37 @@ __device__ __forceinline__ void pair_decim_fir(const u64* __restrict__ w, const 
     }
 }
 
+// Same FIR over a window stored as bf16 pairs (one 32-bit word per (I,Q) sample: I in the low half, Q in the high
+// half).  The front end's samples are k/128 with |k| <= 128 — exact in bf16 — so halving the shared-memory
+// footprint (more resident CTAs to hide the staging loads) costs two ALU-pipe instructions per loaded sample and
+// no rounding.  Four pad words per D*R keep 128-bit loads of neighbouring threads (stride D*R+4 words = 4*odd)
+// on distinct banks.  C0 must be a multiple of 4.
+template <int D, int R, bool EXACT, int C0>
+__device__ __forceinline__ void pair_decim_fir_bf16(const uint32_t* __restrict__ w, const u64* __restrict__ hh, u64 nz, u64 (&acc)[R])
+{
+    constexpr int CH = D * R;
+    constexpr int QMAX = D * (R - 1) + (DY4_NTAPS - 1);
+    static_assert(C0 % 4 == 0 && CH % 4 == 0, "window groups must not straddle a pad");
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int g = QMAX / 4; g >= 0; g--) {
+        const int p = C0 + 4 * g;
+        const uint4 v = *reinterpret_cast<const uint4*>(w + p + 4 * (p / CH));
+        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            const int q = 4 * g + j;
+            if (q > QMAX) continue;
+            const u64 x = pk2(__uint_as_float(ws[j] << 16), __uint_as_float(ws[j] & 0xffff0000u));
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int k = D * r + (DY4_NTAPS - 1) - q;
+                if (k >= 0 && k < DY4_NTAPS) acc[r] = tap2<EXACT>(acc[r], x, hh[k], nz);
+            }
+        }
+    }
+}
+
+__host__ __device__ constexpr int dy4_padded_words_bf16(int D, int R, int NT) { return (D * R + 4) * NT + 256; }
 __host__ __device__ constexpr int dy4_padded_pairs(int D, int R, int NT) { return (D * R + 2) * NT + 128; }

@@ -23,63 +23,73 @@ namespace {
 __constant__ TapPairs c_rf2[4];   // (h,h) pairs of the RF low-pass, per mode
 
 template <int D, int R, int NT, bool EXACT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 k_frontend(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* __restrict__ iq_tail,
            float* __restrict__ if_out, long long if_stride, int n_if,
            const float* __restrict__ taps_g, u64 nz, int mode)
 {
-    extern __shared__ __align__(16) float2 sm[];
+    extern __shared__ __align__(16) uint32_t sm[];   // one word per IQ sample: bf16(I) | bf16(Q) << 16 (exact for k/128)
     __shared__ float2 s_last[NT];
     constexpr int T = NT * R;               // IF samples per tile
-    constexpr int CH = D * R;               // input pairs per thread chunk
-    constexpr int HALO = DY4_IQ_TAIL / 2;   // 112 pairs of history in front of the tile
+    constexpr int CH = D * R;               // input samples per thread chunk
+    constexpr int HALO = DY4_IQ_TAIL / 2;   // 112 samples of history in front of the tile
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * T;
     const uint8_t* row = iq + (long long)blockIdx.y * row_stride;
     const uint8_t* tail = iq_tail + (long long)blockIdx.y * DY4_IQ_TAIL;
     const long long row_bytes = 2LL * D * n_if;
 
-    // ---- stage: 4 bytes (2 IQ pairs) per thread per step -> one 16-byte shared store -------------
-    // tile-relative byte 0 is absolute byte 2*D*m0 - 224; a 4-byte unit never straddles byte 0.
-    constexpr int UNITS = (2 * D * T + DY4_IQ_TAIL) / 4;
+    // ---- stage: 8 bytes (4 IQ samples) per thread per step -> one 16-byte shared store -------------
+    // tile-relative byte 0 is absolute byte 2*D*m0 - 224; an 8-byte unit never straddles byte 0.
+    // Branch-free so that the unrolled loads are all in flight together: the address is always valid (history
+    // bytes come from the tail buffer, bytes past the end of the row are re-read from its last unit and masked).
+    constexpr int UNITS = (2 * D * T + DY4_IQ_TAIL) / 8;
     const long long b0 = 2LL * D * m0 - DY4_IQ_TAIL;
-#pragma unroll 4
+    const long long last_unit = row_bytes - 8;
+#pragma unroll 5
     for (int u = tid; u < UNITS; u += NT) {
-        const long long b = b0 + 4LL * u;
-        uint32_t w;
-        if (b < 0) w = *reinterpret_cast<const uint32_t*>(tail + DY4_IQ_TAIL + b);
-        else if (b < row_bytes) w = __ldg(reinterpret_cast<const uint32_t*>(row + b));
-        else w = 0x80808080u;
-        // (b-128)/128 exactly: 0x4B0000bb is 2^23+b; (2^23+b)*2^-7 - 65537 = (b-128)/128, no rounding anywhere
-        float4 f;
-        f.x = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)), 0.0078125f, -65537.0f);
-        f.y = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)), 0.0078125f, -65537.0f);
-        f.z = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)), 0.0078125f, -65537.0f);
-        f.w = fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)), 0.0078125f, -65537.0f);
-        const int p = 2 * u;
-        *reinterpret_cast<float4*>(&sm[p + 2 * (p / CH)]) = f;
+        const long long b = b0 + 8LL * u;
+        const uint8_t* src = b < 0 ? tail + (DY4_IQ_TAIL + b) : row + (b < last_unit ? b : last_unit);
+        uint2 w = __ldg(reinterpret_cast<const uint2*>(src));
+        if (b > last_unit) w = make_uint2(0x80808080u, 0x80808080u);
+        // (b-128)/128 exactly: 0x4B0000bb is 2^23+b; (2^23+b)*2^-7 - 65537 = (b-128)/128, no rounding anywhere;
+        // the result has at most 8 significant bits, so its top 16 bits are the exact bf16
+        uint4 o;
+        const uint32_t i0 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7440)), 0.0078125f, -65537.0f));
+        const uint32_t q0 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7441)), 0.0078125f, -65537.0f));
+        const uint32_t i1 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7442)), 0.0078125f, -65537.0f));
+        const uint32_t q1 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7443)), 0.0078125f, -65537.0f));
+        const uint32_t i2 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7440)), 0.0078125f, -65537.0f));
+        const uint32_t q2 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7441)), 0.0078125f, -65537.0f));
+        const uint32_t i3 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7442)), 0.0078125f, -65537.0f));
+        const uint32_t q3 = __float_as_uint(fmaf(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7443)), 0.0078125f, -65537.0f));
+        o.x = __byte_perm(i0, q0, 0x7632); o.y = __byte_perm(i1, q1, 0x7632);
+        o.z = __byte_perm(i2, q2, 0x7632); o.w = __byte_perm(i3, q3, 0x7632);
+        const int p = 4 * u;
+        *reinterpret_cast<uint4*>(&sm[p + 4 * (p / CH)]) = o;
     }
     __syncthreads();
 
     // ---- FIR: R consecutive (I,Q) outputs per thread -------------------------------------------------
     u64 acc[R];
-    const u64* w = reinterpret_cast<const u64*>(sm) + (CH + 2) * tid;
-    pair_decim_fir<D, R, EXACT, HALO - (DY4_NTAPS - 1)>(w, reinterpret_cast<const u64*>(c_rf2[mode].t), nz, acc);
+    const u64* hh = reinterpret_cast<const u64*>(c_rf2[mode].t);
+    pair_decim_fir_bf16<D, R, EXACT, HALO - (DY4_NTAPS - 1)>(sm + (CH + 4) * tid, hh, nz, acc);
 
     // ---- the sample before the tile (for the discriminator's first difference) ---------------------
+    // One extra output, m0-1, on thread 0: same taps from the constant bank, same ascending order, window
+    // offsets known at compile time (logical sample HALO - D - k).
     float pI, pQ;
     upk2(acc[R - 1], pI, pQ);
     s_last[tid] = make_float2(pI, pQ);
     if (tid == 0) {
-        float aI = 0.f, aQ = 0.f;
+        u64 a0 = 0ull;
+#pragma unroll
         for (int k = 0; k < DY4_NTAPS; k++) {
             const int p = HALO - D - k;
-            const float2 x = sm[p + 2 * (p / CH)];
-            const float h = taps_g[k];
-            if (EXACT) { aI = __fadd_rn(aI, __fmul_rn(h, x.x)); aQ = __fadd_rn(aQ, __fmul_rn(h, x.y)); }
-            else { aI = fmaf(h, x.x, aI); aQ = fmaf(h, x.y, aQ); }
+            const uint32_t wv = sm[p + 4 * (p / CH)];
+            a0 = tap2<EXACT>(a0, pk2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xffff0000u)), hh[k], nz);
         }
-        pI = aI; pQ = aQ;
+        upk2(a0, pI, pQ);
     }
     __syncthreads();
     if (tid > 0) { const float2 l = s_last[tid - 1]; pI = l.x; pQ = l.y; }
@@ -110,7 +120,7 @@ template <int D, int R, int NT, bool EXACT>
 cudaError_t launch(const Dy4FrontendArgs& a, cudaStream_t st)
 {
     constexpr int T = NT * R;
-    const size_t smem = sizeof(float2) * dy4_padded_pairs(D, R, NT);
+    const size_t smem = sizeof(uint32_t) * dy4_padded_words_bf16(D, R, NT);
     auto kern = k_frontend<D, R, NT, EXACT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

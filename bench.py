@@ -34,6 +34,9 @@ BLOCKS_PER_STREAM = 47           # 47 x 21.33 ms = 1.003 s per stream
 METRIC = "aggregate_iq_msamples_per_s_stereo_fm"
 UNIT = "Msamples/s"
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45: SMs x lanes x 2 flop x max SM clock
+# DRAM traffic of k_frontend from the `ncu --set full` capture summarised in profiles/r1_ncu_frontend.md:
+# (209.83 + 30.51) MB for 256 streams x 8 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
+NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (209.832448e6 + 30.508544e6) / (256 * 8 * 51200)
 
 
 def measured_peaks():
@@ -113,7 +116,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region (NVML, 20 Hz)."""
+    """SM clock and throttle reasons DURING the timed region (NVML, ~100 Hz)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -138,7 +141,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.01)
         except Exception as e:      # NVML missing: report that, do not fail the bench
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
@@ -236,6 +239,9 @@ def run_gpu_arm(args):
     torch.cuda.synchronize(dev)
     e2e_ms = shard.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
     e2e_value = world * pairs_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
+    pipe.reset()                                     # same starting state as the e2e pass, then compare the two paths
+    pipe.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
+    torch.cuda.synchronize(dev)
     pcm_matches = bool(torch.equal(h_pcm.to(dev), out["pcm"]))
 
     if rank != 0:
@@ -274,7 +280,10 @@ def run_gpu_arm(args):
         "note": "bit-exact (unfused multiply then add) costs 2 FP32 instructions per MAC: the issue-limited ceiling of this kernel is frac 0.5",
         "issue_frac": round(2 * fe["fp32_TFLOPs"] / FP32_PEAK_TFLOPS_NOMINAL, 4),
         "hbm": {"achieved": fe["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(fe["GBps"] / hbm_peak, 4), "peak_source": hbm_src},
-        "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"], "traffic": None,
+        "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"],
+        "algorithmic_bytes": int(alg["frontend"]["bytes"] * pairs_per_step),
+        "traffic": int(NCU_FRONTEND_DRAM_BYTES_PER_PAIR * pairs_per_step),
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r1_ncu_frontend.md, scaled to this launch",
     }
     pll = kernels.get("pll")
     pll_info = None
@@ -288,10 +297,10 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, kind, pairs, dt = cpu_throughput(2 * cores, 24, cores)
+        v, kind, pairs, dt = cpu_throughput(8 * cores, BLOCKS_PER_STREAM, cores)
         cpu = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "%d streams x 24 blocks (0.51 s of signal each), one reference pipeline per stream on %d worker processes, %.1f s wall"
-                         % (2 * cores, cores, dt)}
+               "sample": "%d of the workload's streams x %d blocks (%.2f s of signal each), one reference pipeline per stream on %d worker "
+                         "processes, %.1f s wall (%.0f core-seconds)" % (8 * cores, BLOCKS_PER_STREAM, BLOCKS_PER_STREAM * 0.021333, cores, dt, dt * cores)}
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -264,3 +264,24 @@ def test_linearity_of_fir_stages_on_device(dy4):
     a = fh.downsampleBlockConvolveFIR(10, x, h, z()) + fh.downsampleBlockConvolveFIR(10, y, h, z())
     b = fh.downsampleBlockConvolveFIR(10, x + y, h, z())
     assert rel_l2(a, b) < 1e-6
+
+
+# ---------------------------------------------------------------- the reference's own project.cpp over this library
+@pytest.mark.parametrize("mode,stereo", [(0, 1), (2, 1), (1, 0)])
+def test_reference_project_binary_linked_against_this_library(dy4, mode, stereo):
+    """oracle/_ref/project_b200 = the reference's UNMODIFIED project.cpp/iofunc.cpp objects linked against
+    libdy4b200.so instead of the reference's filter.o.  Fed the golden input on stdin it must
+    write the golden PCM: every filter.h call it makes runs through the filter.h shim and the CUDA kernels."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "project_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/project_b200 not built (needs /root/reference at build time)")
+    iq = golden("mode%d_stereo.npz" % mode)["iq"]
+    want = golden("mode%d_%s.npz" % (mode, "stereo" if stereo else "mono"))["pcm"]
+    before = dy4.launch_count()
+    p = subprocess.run([exe, str(mode), "stereo" if stereo else "mono"], input=iq.tobytes(), capture_output=True, timeout=300)
+    assert p.returncode == 1, p.stderr[-500:]                      # the reference exits 1 at end of input
+    got = np.frombuffer(p.stdout, np.int16)
+    assert got.size == want.size
+    assert np.array_equal(got, want)                               # compat tier is unfused everywhere: bit-exact PCM
