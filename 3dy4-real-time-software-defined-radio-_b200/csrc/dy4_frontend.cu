@@ -18,6 +18,10 @@
 #include "dy4_kernels.h"
 #include "dy4_internal.h"
 
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
 namespace {
 
 __constant__ TapPairs c_rf2[4];   // (h,h) pairs of the RF low-pass, per mode
@@ -116,6 +120,221 @@ k_frontend(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA-staged persistent variant (default).  The tile's raw bytes (history + 2*D*T bytes, 20.7 KB for D=10) are
+// brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP in SASS) that completes on
+// an mbarrier; two buffers, so the copy for tile i+2 is issued as soon as tile i has been filtered and lands
+// while tile i+1 is being filtered.  No staging pass at all: the FIR reads the packed uint8 pairs straight from
+// shared memory with 128-bit loads (8 IQ samples each) and unpacks in registers — two byte-permutes build the
+// floats 2^23+b, one packed add removes 2^23+128 — while the 1/128 of (b-128)/128 is folded into the taps (a power
+// of two: products and roundings are unchanged).  Each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (stream-major tile order), grid = SMs x resident CTAs.
+// Variants measured on a B200 and not kept: three stages with mbarrier-only hand-offs between
+// warps (register-capped, spills), one tile per CTA with per-output tap tables (constant-cache thrash).
+// ------------------------------------------------------------------------------------------------------------
+__constant__ TapPairs c_rf2s[4];   // (h/128, h/128) pairs of the RF low-pass, per mode
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// (I,Q) of the IQ sample held in the 16-bit half `h` (0 or 1) of word w, as exact integers b-128 in a packed pair
+__device__ __forceinline__ u64 unpack_iq(uint32_t w, int h, u64 neg_bias)
+{
+    const float fi = __uint_as_float(__byte_perm(w, 0x4B000000u, h ? 0x7442 : 0x7440));   // 2^23 + I byte
+    const float fq = __uint_as_float(__byte_perm(w, 0x4B000000u, h ? 0x7443 : 0x7441));   // 2^23 + Q byte
+    return fadd2(pk2(fi, fq), neg_bias);                                                  // - (2^23 + 128): exact
+}
+
+template <int D, int R, int NT, bool EXACT>
+__global__ void __launch_bounds__(NT, 3)
+k_frontend_tma(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* __restrict__ iq_tail,
+               float* __restrict__ if_out, long long if_stride, int n_if, u64 nz, int mode,
+               int tiles_per_stream, int n_tiles)
+{
+    constexpr int T = NT * R;                          // IF samples per tile
+    constexpr int NW = NT / 32;
+    constexpr int CH = D * R;                          // input samples per thread
+    constexpr int HALO = DY4_IQ_TAIL / 2;              // 112 samples of history in front of the tile
+    constexpr int TILE_BYTES = 2 * D * T + DY4_IQ_TAIL;
+    constexpr int BUF_BYTES = (TILE_BYTES + 64 + 127) / 128 * 128;   // +64: the last thread's final 16-byte load runs past the tile
+    constexpr int QMAX = D * (R - 1) + (DY4_NTAPS - 1);
+    constexpr int C0 = HALO - (DY4_NTAPS - 1);         // 12: first window sample of thread 0
+    constexpr int CA = C0 & ~7;                        // window start aligned down to a 16-byte group (8 samples)
+    constexpr int NG = (C0 - CA + QMAX) / 8 + 1;       // 16-byte groups per thread window
+    static_assert(TILE_BYTES % 16 == 0 && (2 * CH) % 16 == 0, "bulk copies and window loads are 16-byte granular");
+    extern __shared__ __align__(128) uint8_t smraw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ float2 s_last[NT];
+    __shared__ float2 s_prev;
+    const int tid = threadIdx.x;
+    const long long row_bytes = 2LL * D * n_if;
+    const u64* hh = reinterpret_cast<const u64*>(c_rf2s[mode].t);
+    const u64 neg_bias = pk2(-8388736.0f, -8388736.0f);
+
+    auto issue = [&](int t, int b) {                   // thread 0: start the bulk copy of tile t into buffer b
+        const int s = t / tiles_per_stream, m0 = (t - s * tiles_per_stream) * T;
+        const uint8_t* row = iq + (long long)s * row_stride;
+        uint8_t* dst = smraw + b * BUF_BYTES;
+        const long long start = 2LL * D * m0 - DY4_IQ_TAIL;
+        const long long begin = start < 0 ? 0 : start;
+        long long len = (start + TILE_BYTES) - begin;
+        if (begin + len > row_bytes) len = row_bytes - begin;
+        if (len < 0) len = 0;
+        const uint32_t head = start < 0 ? (uint32_t)DY4_IQ_TAIL : 0u;   // first tile of the chunk: history from the carried tail
+        mbar_expect_tx(&mbar[b], head + (uint32_t)len);
+        if (head) bulk_g2s(dst, iq_tail + (long long)s * DY4_IQ_TAIL, head, &mbar[b]);
+        if (len > 0) bulk_g2s(dst + head, row + begin, (uint32_t)len, &mbar[b]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (tid == 0) {
+        if (first < n_tiles) issue(first, 0);
+        if (first + stride < n_tiles) issue(first + stride, 1);
+    }
+
+    int it = 0;
+    for (int t = first; t < n_tiles; t += stride, it++) {
+        const int b = it & 1;
+        const int s = t / tiles_per_stream, m0 = (t - s * tiles_per_stream) * T;
+        mbar_wait(&mbar[b], (it >> 1) & 1);
+        const uint8_t* buf = smraw + b * BUF_BYTES;
+
+        // ---- FIR: R consecutive (I,Q) outputs per thread; window index descends so taps ascend ------------
+        u64 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0ull;
+        const uint4* win = reinterpret_cast<const uint4*>(buf + 2 * (CH * tid + CA));
+#pragma unroll
+        for (int g = NG - 1; g >= 0; g--) {
+            const uint4 v = win[g];
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 7; j >= 0; j--) {
+                const int q = 8 * g + j - (C0 - CA);
+                if (q < 0 || q > QMAX) continue;
+                const u64 x = unpack_iq(ws[j >> 1], j & 1, neg_bias);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int k = D * r + (DY4_NTAPS - 1) - q;
+                    if (k >= 0 && k < DY4_NTAPS) acc[r] = tap2<EXACT>(acc[r], x, hh[k], nz);
+                }
+            }
+        }
+
+        // ---- the output before the tile (m0-1), for the discriminator's first difference: 101 extra taps on one
+        // lane; the warp that pays rotates with the tile so no scheduler is always the slow one.
+        float pI, pQ;
+        upk2(acc[R - 1], pI, pQ);
+        s_last[tid] = make_float2(pI, pQ);
+        if (tid == 32 * (it % NW)) {
+            u64 a0 = 0ull;
+            const uint4* w0 = reinterpret_cast<const uint4*>(buf);
+            constexpr int PMAX = HALO - D;                     // tap k reads sample PMAX - k
+#pragma unroll
+            for (int g = PMAX / 8; g >= 0; g--) {
+                const uint4 v = w0[g];
+                const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    const int k = PMAX - (8 * g + j);
+                    if (k >= 0 && k < DY4_NTAPS) a0 = tap2<EXACT>(a0, unpack_iq(ws[j >> 1], j & 1, neg_bias), hh[k], nz);
+                }
+            }
+            float eI, eQ;
+            upk2(a0, eI, eQ);
+            s_prev = make_float2(eI, eQ);
+        }
+        __syncthreads();                                       // edge values visible; every read of buffer b is done
+        if (tid == 0 && t + 2 * stride < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + 2 * stride, b);
+        }
+        { const float2 l = tid > 0 ? s_last[tid - 1] : s_prev; pI = l.x; pQ = l.y; }
+
+        // ---- discriminator, reference arithmetic: double sum of squares narrowed to float, float rest ---
+        float out[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float I, Q;
+            upk2(acc[r], I, Q);
+            const float den = __double2float_rn(fma((double)I, (double)I, (double)Q * (double)Q));
+            const float num = __fsub_rn(__fmul_rn(I, __fsub_rn(Q, pQ)), __fmul_rn(Q, __fsub_rn(I, pI)));
+            out[r] = (den == 0.0f) ? 0.0f : __fdiv_rn(num, den);
+            pI = I; pQ = Q;
+        }
+        float* dst = if_out + (long long)s * if_stride + m0 + tid * R;
+        const int left = n_if - (m0 + tid * R);
+        if (left >= R) {
+#pragma unroll
+            for (int r = 0; r < R; r += 4) *reinterpret_cast<float4*>(dst + r) = make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) if (r < left) dst[r] = out[r];
+        }
+        __syncthreads();                                       // the edge slots are rewritten by the next tile
+    }
+}
+
+template <int D, int R, int NT, bool EXACT>
+cudaError_t launch_tma(const Dy4FrontendArgs& a, cudaStream_t st)
+{
+    constexpr int T = NT * R;
+    constexpr int TILE_BYTES = 2 * D * T + DY4_IQ_TAIL;
+    constexpr int BUF_BYTES = (TILE_BYTES + 64 + 127) / 128 * 128;
+    const size_t smem = 2 * BUF_BYTES;
+    auto kern = k_frontend_tma<D, R, NT, EXACT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int tiles_per_stream = (a.n_if + T - 1) / T;
+    const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
+    if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)sms * ctas_per_sm);
+    kern<<<grid, NT, smem, st>>>(a.iq, a.row_stride, a.iq_tail, a.if_out, a.if_stride, a.n_if, a.neg_zero2, a.mode,
+                                 tiles_per_stream, (int)n_tiles);
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
+
 template <int D, int R, int NT, bool EXACT>
 cudaError_t launch(const Dy4FrontendArgs& a, cudaStream_t st)
 {
@@ -135,9 +354,20 @@ cudaError_t launch(const Dy4FrontendArgs& a, cudaStream_t st)
 cudaError_t dy4_launch_frontend(const Dy4FrontendArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
-    if (a.rf_decim == 10) return launch<10, 8, 128, true>(a, st);
-    if (a.rf_decim == 5) return launch<5, 8, 128, true>(a, st);
+    // DY4_FRONTEND=staged selects the earlier converted-to-bf16 staging kernel (A/B knob; identical results)
+    static const bool staged = std::getenv("DY4_FRONTEND") && std::string(std::getenv("DY4_FRONTEND")) == "staged";
+    if (a.rf_decim == 10) return staged ? launch<10, 8, 128, true>(a, st) : launch_tma<10, 8, 128, true>(a, st);
+    if (a.rf_decim == 5) return staged ? launch<5, 8, 128, true>(a, st) : launch_tma<5, 8, 128, true>(a, st);
     return cudaErrorInvalidValue;
 }
 
-cudaError_t dy4_upload_taps_frontend(const TapPairs* rf4) { return cudaMemcpyToSymbol(c_rf2, rf4, sizeof(TapPairs) * 4); }
+cudaError_t dy4_upload_taps_frontend(const TapPairs* rf4)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_rf2, rf4, sizeof(TapPairs) * 4);
+    if (e != cudaSuccess) return e;
+    static TapPairs scaled[4];
+    for (int m = 0; m < 4; m++)
+        for (int k = 0; k < DY4_NTAPS + 3; k++)
+            scaled[m].t[k] = make_float2(rf4[m].t[k].x * 0.0078125f, rf4[m].t[k].y * 0.0078125f);   // exact: power of two
+    return cudaMemcpyToSymbol(c_rf2s, scaled, sizeof(TapPairs) * 4);
+}

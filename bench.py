@@ -35,8 +35,8 @@ METRIC = "aggregate_iq_msamples_per_s_stereo_fm"
 UNIT = "Msamples/s"
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45: SMs x lanes x 2 flop x max SM clock
 # DRAM traffic of k_frontend from the `ncu --set full` capture summarised in profiles/r1_ncu_frontend.md:
-# (209.83 + 30.51) MB for 256 streams x 8 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
-NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (209.832448e6 + 30.508544e6) / (256 * 8 * 51200)
+# (209.88 + 28.41) MB for 256 streams x 8 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
+NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (209.879296e6 + 28.413440e6) / (256 * 8 * 51200)
 
 
 def measured_peaks():
@@ -244,6 +244,10 @@ def run_gpu_arm(args):
     torch.cuda.synchronize(dev)
     pcm_matches = bool(torch.equal(h_pcm.to(dev), out["pcm"]))
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 
@@ -273,7 +277,7 @@ def run_gpu_arm(args):
         }
     fe = kernels["frontend"]
     roofline = {
-        "kernel": "k_frontend (uint8 IQ -> 101-tap decimating FIR on I,Q -> FM discriminator)",
+        "kernel": "k_frontend_tma (TMA-staged uint8 IQ -> 101-tap decimating FIR on I,Q -> FM discriminator)",
         "bound": "fp32", "achieved": fe["fp32_TFLOPs"], "peak": round(FP32_PEAK_TFLOPS_NOMINAL, 2), "unit": "TFLOP/s",
         "frac": round(fe["fp32_TFLOPs"] / FP32_PEAK_TFLOPS_NOMINAL, 4),
         "peak_source": "148 SMs x 128 FP32 lanes x 2 x 1.965 GHz; tools/ubench measures 71.6 TFLOP/s FFMA on this pool",
