@@ -56,8 +56,8 @@ k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __
     constexpr int HALO = 112;
     constexpr int DELAY = DY4_NTAPS / 2;            // project.cpp:251: mono_delay_state has num_taps/2 = 50 entries
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * T;
-    const int s = blockIdx.y;
+    const int m0 = blockIdx.y * T;
+    const int s = blockIdx.x;                       // streams on grid.x (no 65535 limit), tiles on grid.y
     const float* row = if_in + (long long)s * if_stride;
     const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
     const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
@@ -160,8 +160,8 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
     float* s_ifd = sm_f;                 // delayed IF over the tile's span
     float* s_mix = sm_f + span_max;      // mixed signal over the same span
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * NT;
-    const int s = blockIdx.y;
+    const int m0 = blockIdx.y * NT;
+    const int s = blockIdx.x;
     const float* row = if_in + (long long)s * if_stride;
     const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
     const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
@@ -214,7 +214,7 @@ cudaError_t launch_u1(const Dy4AudioArgs& a, cudaStream_t st)
     auto kern = k_audio_u1<D, R, NT, EXACT, STEREO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((a.n_audio + T - 1) / T, a.n_streams);
+    dim3 grid(a.n_streams, (a.n_audio + T - 1) / T);
     kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride,
                                  a.pcm, a.pcm_stride, a.n_if, a.n_audio, a.neg_zero2, a.mode);
     g_dy4_launches++;
@@ -235,7 +235,7 @@ cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
     constexpr int NT = 128;
     const int span_max = (int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 3;
     const size_t smem = sizeof(float) * 2 * span_max;
-    dim3 grid((a.n_audio + NT - 1) / NT, a.n_streams);
+    dim3 grid(a.n_streams, (a.n_audio + NT - 1) / NT);
     k_audio_poly<NT, EXACT, STEREO><<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
                                                             a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
                                                             a.up, a.down, a.taps_poly, a.up_pad, span_max);

@@ -28,9 +28,9 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     constexpr int NP = T + HALO;                    // logical (x,x) pairs per tile
     __shared__ __align__(16) float2 sm[NP + 2 * (NP / R) + 8];
     const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * T;
-    const float* row = if_in + (long long)blockIdx.y * if_stride;
-    const float* tail = if_tail + (long long)blockIdx.y * DY4_IF_TAIL;
+    const int n0 = blockIdx.y * T;                    // streams on grid.x (no 65535 limit), tiles on grid.y
+    const float* row = if_in + (long long)blockIdx.x * if_stride;
+    const float* tail = if_tail + (long long)blockIdx.x * DY4_IF_TAIL;
 
     // stage 4 samples per step as 4 duplicated pairs; logical pair p <-> sample n0 - HALO + p
     for (int u = tid; u < NP / 4; u += NT) {
@@ -67,7 +67,7 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     float op[R], os[R];
 #pragma unroll
     for (int r = 0; r < R; r++) upk2(acc[r], op[r], os[r]);
-    const long long o = (long long)blockIdx.y * out_stride + n0 + tid * R;
+    const long long o = (long long)blockIdx.x * out_stride + n0 + tid * R;
     const int left = n_if - (n0 + tid * R);
     if (left >= R) {
 #pragma unroll
@@ -87,7 +87,7 @@ cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     constexpr int R = 8, NT = 128;
-    dim3 grid((a.n_if + NT * R - 1) / (NT * R), a.n_streams);
+    dim3 grid(a.n_streams, (a.n_if + NT * R - 1) / (NT * R));
     k_twin_bpf<R, NT, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
     g_dy4_launches++;
     return cudaGetLastError();

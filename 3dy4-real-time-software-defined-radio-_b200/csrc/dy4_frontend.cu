@@ -38,9 +38,9 @@ k_frontend(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* 
     constexpr int CH = D * R;               // input samples per thread chunk
     constexpr int HALO = DY4_IQ_TAIL / 2;   // 112 samples of history in front of the tile
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * T;
-    const uint8_t* row = iq + (long long)blockIdx.y * row_stride;
-    const uint8_t* tail = iq_tail + (long long)blockIdx.y * DY4_IQ_TAIL;
+    const int m0 = blockIdx.y * T;                    // streams on grid.x (no 65535 limit), tiles on grid.y
+    const uint8_t* row = iq + (long long)blockIdx.x * row_stride;
+    const uint8_t* tail = iq_tail + (long long)blockIdx.x * DY4_IQ_TAIL;
     const long long row_bytes = 2LL * D * n_if;
 
     // ---- stage: 8 bytes (4 IQ samples) per thread per step -> one 16-byte shared store -------------
@@ -109,7 +109,7 @@ k_frontend(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* 
         out[r] = (den == 0.0f) ? 0.0f : __fdiv_rn(num, den);
         pI = I; pQ = Q;
     }
-    float* dst = if_out + (long long)blockIdx.y * if_stride + m0 + tid * R;
+    float* dst = if_out + (long long)blockIdx.x * if_stride + m0 + tid * R;
     const int left = n_if - (m0 + tid * R);
     if (left >= R) {
 #pragma unroll
@@ -343,7 +343,7 @@ cudaError_t launch(const Dy4FrontendArgs& a, cudaStream_t st)
     auto kern = k_frontend<D, R, NT, EXACT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((a.n_if + T - 1) / T, a.n_streams);
+    dim3 grid(a.n_streams, (a.n_if + T - 1) / T);
     kern<<<grid, NT, smem, st>>>(a.iq, a.row_stride, a.iq_tail, a.if_out, a.if_stride, a.n_if, a.taps_g, a.neg_zero2, a.mode);
     g_dy4_launches++;
     return cudaGetLastError();

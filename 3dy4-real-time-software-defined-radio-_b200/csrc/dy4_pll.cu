@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(256)
 k_nco(const double* __restrict__ theta, long long theta_stride, const float* __restrict__ nco0,
       float* __restrict__ nco, long long nco_stride, int n, float ncoScale, float phaseAdjust)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x;                       // streams on grid.x (no 65535 limit)
     if (k >= n) return;
     float v;
     if (k == 0) v = nco0[s];
@@ -190,10 +190,10 @@ k_nco(const double* __restrict__ theta, long long theta_stride, const float* __r
 __global__ void __launch_bounds__(256)
 k_pll_prep(const float* __restrict__ in, long long in_stride, double* __restrict__ inv, long long inv_stride, int n)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const float x = __ldg(in + (long long)blockIdx.y * in_stride + k);
-    inv[(long long)blockIdx.y * inv_stride + k] = fast_ok(x) ? dy4_recip(x) : 0.0;
+    const float x = __ldg(in + (long long)blockIdx.x * in_stride + k);
+    inv[(long long)blockIdx.x * inv_stride + k] = fast_ok(x) ? dy4_recip(x) : 0.0;
 }
 
 }  // namespace
@@ -212,7 +212,7 @@ cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
     c.phaseAdjust = a.phaseAdjust;
     static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
     {
-        dim3 gp((a.n + 255) / 256, a.n_streams);
+        dim3 gp(a.n_streams, (a.n + 255) / 256);
         k_pll_prep<<<gp, 256, 0, st>>>(a.in, a.in_stride, a.inv, a.wide_stride, a.n);
         g_dy4_launches++;
         cudaError_t e0 = cudaGetLastError();
@@ -227,7 +227,7 @@ cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
     g_dy4_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 grid((a.n + 255) / 256, a.n_streams);
+    dim3 grid(a.n_streams, (a.n + 255) / 256);
     k_nco<<<grid, 256, 0, st>>>(a.theta, a.wide_stride, a.nco0, a.nco, a.nco_stride, a.n, a.ncoScale, a.phaseAdjust);
     g_dy4_launches++;
     return cudaGetLastError();

@@ -152,12 +152,11 @@ class ClockSampler(threading.Thread):
 
 def workload_config():
     return {
-        "workload": "BASELINE configs[1]: mode 0 stereo FM (2.4 MS/s 8-bit IQ -> 240 kS/s IF -> 48 kS/s L/R PCM), "
-                    "%d independent synthetic streams per GPU x %d blocks (%.3f s of signal per stream)"
-                    % (STREAMS_PER_GPU, BLOCKS_PER_STREAM, BLOCKS_PER_STREAM * 51200 / 2.4e6),
+        "workload": "%smode %d stereo FM (8-bit IQ -> IF -> L/R int16 PCM), %d independent synthetic streams per GPU x %d blocks"
+                    % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU) == (0, 256) else "", MODE, STREAMS_PER_GPU, BLOCKS_PER_STREAM),
         "mode": MODE, "stereo": True, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
-        "input_bytes_per_gpu": STREAMS_PER_GPU * BLOCKS_PER_STREAM * 102400,
-        "l2": "inputs (1.23 GB per GPU) are larger than the 126 MB L2; no flush needed",
+        "input_bytes_per_gpu": STREAMS_PER_GPU * BLOCKS_PER_STREAM * {0: 102400, 1: 81920, 2: 160000, 3: 128000}[MODE],
+        "l2": "inputs are larger than the 126 MB L2 (see input_bytes_per_gpu); no flush needed",
         "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32, f64 libm in the PLL); "
                       "audio resamplers fused f32 (PCM within 1 LSB)",
         "parallelism": "streams partitioned across GPUs, one process per GPU, no collective on the data path",
@@ -184,10 +183,12 @@ def run_gpu_arm(args):
     n_if, n_audio = nb * m.if_per_block, nb * m.audio_per_block
 
     # synthetic input, generated on the GPU; stream s of the whole job uses seed 65+s
-    d_iq = dy4_b200.synth.make_batch_torch(MODE, S, nb * m.block_size // 2, base_seed=65 + lo, device=dev)
+    d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev)
+    if S > 512:                                      # very large batches: tile 512 distinct streams (generation time, not a kernel matter)
+        d_iq = d_iq.repeat((S + 511) // 512, 1)[:S].contiguous()
     pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank)
     out = {"pcm": torch.empty((S, n_audio * 2), dtype=torch.int16, device=dev)}
-    max_steps_between_resets = max(1, int(55.0 / (nb * 51200 / 2.4e6)))   # float PLL sample counter saturates at 2^24 (~69.9 s)
+    max_steps_between_resets = max(1, int(55.0 / (nb * (m.block_size / 2) / m.rf_Fs)))   # float PLL sample counter saturates at 2^24 (~69.9 s)
 
     def step(i):
         if i % max_steps_between_resets == 0:
@@ -256,11 +257,13 @@ def run_gpu_arm(args):
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
     # algorithmic bytes / MACs per IQ pair, SURVEY.md §8(d) and DESIGN.md §5
+    rd = float(m.rf_decim)                           # IQ pairs per IF sample
+    ad = rd * m.audio_decim / m.audio_upsample       # IQ pairs per audio sample
     alg = {
-        "frontend": {"bytes": 2.0 + 0.4, "mac": 2 * 101 / 10.0},
-        "twin_bpf": {"bytes": 0.4 + 0.8, "mac": 2 * 101 / 10.0},
-        "pll": {"bytes": 0.8, "mac": 0.0},
-        "audio": {"bytes": 1.2 + 0.08, "mac": 2 * 101 / 50.0},
+        "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
+        "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
+        "pll": {"bytes": 8 / rd, "mac": 0.0},
+        "audio": {"bytes": 12 / rd + 4 / ad, "mac": 2 * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
     }
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -323,6 +326,7 @@ def run_gpu_arm(args):
 
 
 def main():
+    global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -330,7 +334,11 @@ def main():
     ap.add_argument("--impl", default="dy4", choices=["dy4", "reference"])
     ap.add_argument("--chunk-blocks", type=int, default=0, help="blocks per H2D chunk in the e2e leg (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: BASELINE configs[1], 256)")
+    ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STREAM, help="blocks per stream per step (default 47 = 1.003 s)")
+    ap.add_argument("--mode", type=int, default=MODE, help="receiver mode 0..3 (default 0)")
     args = ap.parse_args()
+    STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE = args.streams, args.blocks, args.mode
     args.warmup = max(args.warmup, 3) if args.impl == "dy4" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)

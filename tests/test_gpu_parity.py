@@ -285,3 +285,21 @@ def test_reference_project_binary_linked_against_this_library(dy4, mode, stereo)
     got = np.frombuffer(p.stdout, np.int16)
     assert got.size == want.size
     assert np.array_equal(got, want)                               # compat tier is unfused everywhere: bit-exact PCM
+
+
+def test_more_than_65535_streams(dy4, checker):
+    """config 5's upper end: 66 000 streams in one batch (streams ride on grid.x, which has no 65 535 limit)."""
+    import torch
+    m = dy4.mode_params(1)
+    S, nb = 66000, 1
+    base = dy4.synth.make_batch(1, 8, nb * m.block_size // 2, base_seed=42)
+    iq = torch.from_numpy(base).cuda().repeat(S // 8, 1).contiguous()
+    p = dy4.Pipeline(1, 1, S)
+    out = p.process(iq, want=("pcm",))["pcm"]
+    torch.cuda.synchronize()
+    first = out[:8]
+    assert bool((out.view(S // 8, 8, -1) == first.unsqueeze(0)).all())
+    for s in (0, 5):
+        ref = checker.pipeline(1, 1, base[s])
+        assert np.abs(first[s].cpu().numpy().astype(np.int32) - ref["pcm"]).max() <= 1
+    p.close()
