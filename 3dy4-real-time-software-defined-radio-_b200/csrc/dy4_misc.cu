@@ -21,15 +21,15 @@ namespace {
 __global__ void k_tails(Dy4TailArgs a)
 {
     const int s = blockIdx.x, t = threadIdx.x;
-    if (a.iq_tail) {
+    if (a.iq_tail && a.iq) {
         const uint8_t* row = a.iq + (long long)s * a.row_stride + a.row_bytes - DY4_IQ_TAIL;
         if (t < DY4_IQ_TAIL) a.iq_tail[(long long)s * DY4_IQ_TAIL + t] = row[t];
     }
-    if (a.if_tail) {
+    if (a.if_tail && a.if_in) {
         const float* row = a.if_in + (long long)s * a.if_stride + a.n_if - DY4_IF_TAIL;
         if (t < DY4_IF_TAIL) a.if_tail[(long long)s * DY4_IF_TAIL + t] = row[t];
     }
-    if (a.mix_tail) {
+    if (a.mix_tail && a.nco) {
         const long long o = (long long)s * a.bb_stride + a.n_if - DY4_MIX_TAIL;
         if (t < DY4_MIX_TAIL) a.mix_tail[(long long)s * DY4_MIX_TAIL + t] = __fmul_rn(__fmul_rn(a.nco[o + t], a.sband[o + t]), 2.0f);
     }

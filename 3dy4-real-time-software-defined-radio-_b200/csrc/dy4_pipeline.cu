@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -45,17 +46,22 @@ struct dy4_pipeline {
     float* d_rf_taps = nullptr;
     float* d_taps_poly = nullptr;
     int up_pad = 0;
-    // carried state
+    // carried state.  if_tail is a ring of three slots: sub-chunk c reads slot c%3 and leaves slot (c+1)%3 for its
+    // successor, so the front end of c+1 / c+2 can run (under the PLL of c) before the audio kernel of c has read its slot.
     uint8_t* iq_tail = nullptr; float* if_tail = nullptr; float* mix_tail = nullptr; float* pll_state = nullptr;
-    // workspace for one sub-chunk
-    float *ws_if = nullptr, *ws_pilot = nullptr, *ws_sband = nullptr, *ws_nco = nullptr, *ws_nco0 = nullptr;
-    double *ws_theta = nullptr, *ws_inv = nullptr;
-    size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0;
+    long long seq = 0;                               // sub-chunks processed so far: selects the if_tail slot
+    // workspace: two sets, sub-chunk c uses set c&1
+    struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; };
+    WorkSet ws[2];
+    float* ws_nco0 = nullptr;
+    size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
+    cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
+    cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
     // host-facing staging
-    uint8_t* d_stage[2] = {nullptr, nullptr}; int16_t* d_pcm_stage[2] = {nullptr, nullptr}; float* d_audio_stage[2] = {nullptr, nullptr};
+    uint8_t* d_stage = nullptr; int16_t* d_pcm_stage = nullptr; float* d_audio_stage = nullptr;
     int stage_blocks = 0; bool stage_audio = false;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+    std::vector<cudaEvent_t> ev_up, ev_done;          // one pair per sub-chunk of a window
     bool streams_ready = false;
     // profiling
     bool prof = false;
@@ -105,7 +111,8 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
 {
     const size_t S = (size_t)p->n_streams;
     CU(cudaMemsetAsync(p->iq_tail, 128, S * DY4_IQ_TAIL, st));            // byte 128 = 0.0f: zero RF history (project.cpp:242-243)
-    CU(cudaMemsetAsync(p->if_tail, 0, S * DY4_IF_TAIL * sizeof(float), st));
+    CU(cudaMemsetAsync(p->if_tail, 0, 3 * S * DY4_IF_TAIL * sizeof(float), st));
+    p->seq = 0;
     CU(cudaMemsetAsync(p->mix_tail, 0, S * DY4_MIX_TAIL * sizeof(float), st));
     std::vector<float> h(S * 8, 0.0f);
     for (size_t s = 0; s < S; s++) { h[s * 8 + 0] = 1.0f; h[s * 8 + 5] = 1.0f; }   // PLLState, project.cpp:46-53
@@ -114,33 +121,53 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     return DY4_OK;
 }
 
-// IF / pilot / stereo-band / NCO rows for one sub-chunk.  Sized to the job, capped by a byte budget
-// (DY4_WS_BYTES, default 3 GiB); longer jobs are cut into sub-chunks, the tails carry the state across.
+// IF / pilot / stereo-band / NCO rows (and the PLL's double rows) for one sub-chunk, two sets.  A stereo job is cut
+// into sub-chunks (plan_subchunks) so that the FIR kernels of sub-chunk c+1 run beside the serial PLL of sub-chunk c;
+// the whole thing is capped by a byte budget (DY4_WS_BYTES, default 3 GiB).  DY4_FLAG_DEBUG_ROWS keeps the job in one
+// sub-chunk so that dy4_pipeline_debug_buffers() sees whole rows.
 int ensure_workspace(dy4_pipeline* p, int n_blocks)
 {
     size_t budget = 3ull << 30;
     if (const char* e = std::getenv("DY4_WS_BYTES")) budget = std::strtoull(e, nullptr, 10);
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 8 : 1);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 16 : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
+    const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
+    int nsub = 3;                                      // largest sub-chunk = a third of the job (see plan_subchunks)
+    if (const char* e = std::getenv("DY4_SUBCHUNKS")) nsub = std::max(1, atoi(e));
+    if (p->stereo && !whole && n_blocks >= 8) blocks = std::min(blocks, (n_blocks + nsub - 1) / nsub);
     if (const char* e = std::getenv("DY4_SUBCHUNK_BLOCKS")) blocks = std::max(1, atoi(e));
-    if (p->ws_blocks >= blocks) return DY4_OK;
+    if (whole) blocks = std::max(blocks, n_blocks);
+    if (p->ws_blocks >= blocks && (p->ws_blocks == blocks || whole || n_blocks < 8 || !p->stereo)) return DY4_OK;
     if (p->ws_blocks > 0) {
         CU(cudaDeviceSynchronize());
-        cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta); cudaFree(p->ws_inv);
-        p->ws_if = p->ws_pilot = p->ws_sband = p->ws_nco = nullptr; p->ws_theta = p->ws_inv = nullptr;
+        for (auto& w : p->ws) {
+            cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv);
+            w = dy4_pipeline::WorkSet();
+        }
         p->ws_blocks = 0;
     }
     p->ws_stride = (size_t)blocks * p->mp.if_per_block;
     const size_t bytes = (size_t)p->n_streams * p->ws_stride * sizeof(float);
-    CU(cudaMalloc(&p->ws_if, bytes));
-    if (p->stereo) {
-        CU(cudaMalloc(&p->ws_pilot, bytes));
-        CU(cudaMalloc(&p->ws_sband, bytes));
-        CU(cudaMalloc(&p->ws_nco, bytes));
-        CU(cudaMalloc(&p->ws_theta, 2 * bytes));
-        CU(cudaMalloc(&p->ws_inv, 2 * bytes));
-        if (!p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, (size_t)p->n_streams * sizeof(float)));
+    for (int i = 0; i < (p->stereo ? 2 : 1); i++) {
+        auto& w = p->ws[i];
+        CU(cudaMalloc(&w.w_if, bytes));
+        if (p->stereo) {
+            CU(cudaMalloc(&w.pilot, bytes));
+            CU(cudaMalloc(&w.sband, bytes));
+            CU(cudaMalloc(&w.nco, bytes));
+            CU(cudaMalloc(&w.theta, 2 * bytes));
+            CU(cudaMalloc(&w.inv, 2 * bytes));
+        }
+    }
+    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, (size_t)p->n_streams * sizeof(float)));
+    if (p->stereo && !p->s_pll) {
+        CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&p->ev_bpf[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_pll[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     }
     p->ws_blocks = blocks;
     return DY4_OK;
@@ -158,72 +185,159 @@ struct Timer {
     ~Timer() { if (p->prof) { cudaEventRecord(e1, st); p->recs.push_back({k, e0, e1}); } }
 };
 
-int run_subchunk(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int nb,
-                 int16_t* d_pcm, size_t pcm_stride, float* d_audio, size_t audio_stride,
-                 float* d_if, size_t if_out_stride, cudaStream_t st)
+struct SubChunk {                        // one sub-chunk of the job: where its input and outputs live
+    const uint8_t* iq; int nb;
+    int16_t* pcm; float* audio; float* d_if;
+    int set; float* if_tail_in; float* if_tail_out;
+};
+
+float* if_tail_slot(dy4_pipeline* p, long long seq) { return p->if_tail + (size_t)(seq % 3) * p->n_streams * DY4_IF_TAIL; }
+
+// front half on the main stream: uint8 IQ -> IF -> (pilot, stereo band); leaves the IQ and IF history for the successor
+int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_out_stride, cudaStream_t st)
 {
     const dy4_mode_params_t& m = p->mp;
-    const int n_if = nb * m.if_per_block, n_audio = nb * m.audio_per_block;
-    const bool exact_audio = (p->flags & DY4_FLAG_EXACT_AUDIO) != 0;
-
+    const int n_if = c.nb * m.if_per_block;
+    auto& w = p->ws[c.set];
     Dy4FrontendArgs fa;
-    fa.iq = d_iq; fa.row_stride = (long long)row_stride; fa.iq_tail = p->iq_tail;
-    fa.if_out = p->ws_if; fa.if_stride = (long long)p->ws_stride; fa.n_if = n_if; fa.n_streams = p->n_streams;
+    fa.iq = c.iq; fa.row_stride = (long long)row_stride; fa.iq_tail = p->iq_tail;
+    fa.if_out = w.w_if; fa.if_stride = (long long)p->ws_stride; fa.n_if = n_if; fa.n_streams = p->n_streams;
     fa.rf_decim = m.rf_decim; fa.exact = 1; fa.taps_g = p->d_rf_taps; fa.mode = p->mode; fa.neg_zero2 = kNegZero2;
     { Timer t(p, DY4_K_FRONTEND, st); CU(dy4_launch_frontend(fa, st)); }
-
+    if (c.d_if) CU(cudaMemcpy2DAsync(c.d_if, if_out_stride * sizeof(float), w.w_if, p->ws_stride * sizeof(float),
+                                     (size_t)n_if * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+    Dy4TailArgs ta{};
+    ta.iq = c.iq; ta.row_stride = (long long)row_stride; ta.row_bytes = (long long)c.nb * m.block_size; ta.iq_tail = p->iq_tail;
+    ta.if_in = w.w_if; ta.if_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.if_tail = c.if_tail_out;
+    ta.mix_tail = nullptr; ta.n_streams = p->n_streams;
+    { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
     if (p->stereo) {
         Dy4BpfArgs ba;
-        ba.if_in = p->ws_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = p->if_tail;
-        ba.pilot = p->ws_pilot; ba.sband = p->ws_sband; ba.out_stride = (long long)p->ws_stride;
+        ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
+        ba.pilot = w.pilot; ba.sband = w.sband; ba.out_stride = (long long)p->ws_stride;
         ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.neg_zero2 = kNegZero2;
         { Timer t(p, DY4_K_BPF, st); CU(dy4_launch_bpf(ba, st)); }
-
-        Dy4PllArgs pa;
-        pa.in = p->ws_pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = p->ws_nco; pa.nco_stride = (long long)p->ws_stride;
-        pa.theta = p->ws_theta; pa.inv = p->ws_inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0;
-        pa.state = p->pll_state; pa.n = n_if; pa.n_streams = p->n_streams;
-        pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
-        { Timer t(p, DY4_K_PLL, st); CU(dy4_launch_pll(pa, st)); }
     }
-
-    Dy4AudioArgs aa;
-    aa.if_in = p->ws_if; aa.if_stride = (long long)p->ws_stride; aa.if_tail = p->if_tail;
-    aa.nco = p->ws_nco; aa.sband = p->ws_sband; aa.bb_stride = (long long)p->ws_stride; aa.mix_tail = p->mix_tail;
-    aa.audio = d_audio; aa.audio_stride = (long long)audio_stride; aa.pcm = d_pcm; aa.pcm_stride = (long long)pcm_stride;
-    aa.n_if = n_if; aa.n_audio = n_audio; aa.n_streams = p->n_streams; aa.stereo = p->stereo;
-    aa.up = m.audio_upsample; aa.down = m.audio_decim; aa.exact = exact_audio ? 1 : 0;
-    aa.mode = p->mode; aa.taps_poly = p->d_taps_poly; aa.up_pad = p->up_pad; aa.neg_zero2 = kNegZero2;
-    if (d_audio || d_pcm) { Timer t(p, DY4_K_AUDIO, st); CU(dy4_launch_audio(aa, st)); }
-
-    if (d_if) CU(cudaMemcpy2DAsync(d_if, if_out_stride * sizeof(float), p->ws_if, p->ws_stride * sizeof(float),
-                                   (size_t)n_if * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
-
-    Dy4TailArgs ta;
-    ta.iq = d_iq; ta.row_stride = (long long)row_stride; ta.row_bytes = (long long)nb * m.block_size; ta.iq_tail = p->iq_tail;
-    ta.if_in = p->ws_if; ta.if_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.if_tail = p->if_tail;
-    ta.nco = p->ws_nco; ta.sband = p->ws_sband; ta.bb_stride = (long long)p->ws_stride; ta.mix_tail = p->stereo ? p->mix_tail : nullptr;
-    ta.n_streams = p->n_streams;
-    { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
-    p->last_n_if = n_if;
     return DY4_OK;
+}
+
+// the serial part, on its own stream: pilot -> NCO row
+int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
+{
+    const dy4_mode_params_t& m = p->mp;
+    auto& w = p->ws[c.set];
+    Dy4PllArgs pa;
+    pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
+    pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0;
+    pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
+    pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
+    { Timer t(p, DY4_K_PLL, st); CU(dy4_launch_pll(pa, st)); }
+    return DY4_OK;
+}
+
+// back half on the main stream: IF, NCO, stereo band -> audio / PCM; leaves the mixed-signal history
+int run_back(dy4_pipeline* p, const SubChunk& c, size_t pcm_stride, size_t audio_stride, cudaStream_t st)
+{
+    const dy4_mode_params_t& m = p->mp;
+    const int n_if = c.nb * m.if_per_block, n_audio = c.nb * m.audio_per_block;
+    auto& w = p->ws[c.set];
+    Dy4AudioArgs aa;
+    aa.if_in = w.w_if; aa.if_stride = (long long)p->ws_stride; aa.if_tail = c.if_tail_in;
+    aa.nco = w.nco; aa.sband = w.sband; aa.bb_stride = (long long)p->ws_stride; aa.mix_tail = p->mix_tail;
+    aa.audio = c.audio; aa.audio_stride = (long long)audio_stride; aa.pcm = c.pcm; aa.pcm_stride = (long long)pcm_stride;
+    aa.n_if = n_if; aa.n_audio = n_audio; aa.n_streams = p->n_streams; aa.stereo = p->stereo;
+    aa.up = m.audio_upsample; aa.down = m.audio_decim; aa.exact = (p->flags & DY4_FLAG_EXACT_AUDIO) ? 1 : 0;
+    aa.mode = p->mode; aa.taps_poly = p->d_taps_poly; aa.up_pad = p->up_pad; aa.neg_zero2 = kNegZero2;
+    if (c.audio || c.pcm) { Timer t(p, DY4_K_AUDIO, st); CU(dy4_launch_audio(aa, st)); }
+    if (p->stereo) {
+        Dy4TailArgs ta{};
+        ta.nco = w.nco; ta.sband = w.sband; ta.bb_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.mix_tail = p->mix_tail;
+        ta.n_streams = p->n_streams;
+        { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
+    }
+    p->last_n_if = n_if; p->last_set = c.set;
+    return DY4_OK;
+}
+
+// Optional per-sub-chunk hooks of the host-facing path: wait for that sub-chunk's upload before its front half,
+// start the download of its PCM after its back half.  Arguments: first block and number of blocks of the sub-chunk.
+struct Hooks { std::function<int(int, int, int)> before_front, after_back; };   // (index, first block, blocks)
+
+// The sub-chunks of a stereo job grow geometrically — 1, 2, 4, ... blocks up to the workspace size, then that size —
+// so that (a) only one block's FIR work and, on the host path, one block's upload precede the first PLL launch, and
+// every later upload (PCIe moves a block ~2x faster than the PLL consumes it) lands before it is needed, while
+// (b) most of the job runs in large launches (front-end wave balance, few PLL launches).  Mono: uniform sub-chunks.
+std::vector<std::pair<int, int>> plan_subchunks(int n_blocks, int sb, bool geometric)
+{
+    std::vector<std::pair<int, int>> v;
+    int b = 0;
+    if (geometric && n_blocks >= 8)
+        for (int g = 1; g < sb && b + g < n_blocks; g *= 2) { v.push_back({b, g}); b += g; }
+    for (; b < n_blocks; b += sb) v.push_back({b, std::min(sb, n_blocks - b)});
+    return v;
 }
 
 int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int n_blocks,
                    int16_t* d_pcm, float* d_audio, float* d_if, cudaStream_t st,
-                   size_t pcm_stride, size_t audio_stride, size_t if_stride)
+                   size_t pcm_stride, size_t audio_stride, size_t if_stride, const Hooks* hooks = nullptr)
 {
     const dy4_mode_params_t& m = p->mp;
     const int ch = p->stereo ? 2 : 1;
     int rc = ensure_workspace(p, n_blocks);
     if (rc) return rc;
-    for (int b = 0; b < n_blocks; b += p->ws_blocks) {
-        const int nb = std::min(p->ws_blocks, n_blocks - b);
-        rc = run_subchunk(p, d_iq + (size_t)b * m.block_size, row_stride, nb,
-                          d_pcm ? d_pcm + (size_t)b * m.audio_per_block * ch : nullptr, pcm_stride,
-                          d_audio ? d_audio + (size_t)b * m.audio_per_block * ch : nullptr, audio_stride,
-                          d_if ? d_if + (size_t)b * m.if_per_block : nullptr, if_stride, st);
-        if (rc) return rc;
+    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+    auto sub = [&](int b, int nb, long long seq) {
+        SubChunk c;
+        c.nb = nb;
+        c.iq = d_iq + (size_t)b * m.block_size;
+        c.pcm = d_pcm ? d_pcm + (size_t)b * m.audio_per_block * ch : nullptr;
+        c.audio = d_audio ? d_audio + (size_t)b * m.audio_per_block * ch : nullptr;
+        c.d_if = d_if ? d_if + (size_t)b * m.if_per_block : nullptr;
+        c.set = p->stereo ? (int)(seq & 1) : 0;
+        c.if_tail_in = if_tail_slot(p, seq);
+        c.if_tail_out = if_tail_slot(p, seq + 1);
+        return c;
+    };
+    if (!p->stereo) {                                  // mono: no serial stage, one stream
+        for (size_t i = 0; i < plan.size(); i++, p->seq++) {
+            const int b = plan[i].first;
+            const SubChunk c = sub(b, plan[i].second, p->seq);
+            if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
+            if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
+            if ((rc = run_back(p, c, pcm_stride, audio_stride, st))) return rc;
+            if (hooks && (rc = hooks->after_back((int)i, b, c.nb))) return rc;
+        }
+        return DY4_OK;
+    }
+    // stereo: software pipeline.  main stream:  front(0) | front(1) back(0) | front(2) back(1) | ... | back(last)
+    //                             PLL stream:            pll(0)         | pll(1)          | ...
+    // front(c+1) is queued before back(c), so it runs while pll(c) does; buffers of set c&1 are next written by
+    // front(c+2), which is queued after back(c) (their last reader), and back(c) has waited for pll(c).
+    CU(cudaEventRecord(p->ev_in, st));
+    CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
+    SubChunk prev{};
+    bool have_prev = false;
+    int prev_b = 0, prev_i = 0;
+    for (size_t i = 0; i < plan.size(); i++, p->seq++) {
+        const int b = plan[i].first;
+        const SubChunk c = sub(b, plan[i].second, p->seq);
+        if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
+        if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
+        CU(cudaEventRecord(p->ev_bpf[c.set], st));
+        CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
+        if ((rc = run_pll(p, c, p->s_pll))) return rc;
+        CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
+        if (have_prev) {
+            CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
+            if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
+            if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
+        }
+        prev = c; have_prev = true; prev_b = b; prev_i = (int)i;
+    }
+    if (have_prev) {
+        CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
+        if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
+        if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
     }
     return DY4_OK;
 }
@@ -262,7 +376,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
     }
     const size_t S = (size_t)n_streams;
     CU(cudaMalloc(&p->iq_tail, S * DY4_IQ_TAIL));
-    CU(cudaMalloc(&p->if_tail, S * DY4_IF_TAIL * sizeof(float)));
+    CU(cudaMalloc(&p->if_tail, 3 * S * DY4_IF_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->mix_tail, S * DY4_MIX_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->pll_state, S * 8 * sizeof(float)));
     int rc = init_state(p, nullptr);
@@ -288,12 +402,17 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     for (auto e : p->pool) cudaEventDestroy(e);
     cudaFree(p->d_rf_taps); cudaFree(p->d_taps_poly);
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
-    cudaFree(p->ws_if); cudaFree(p->ws_pilot); cudaFree(p->ws_sband); cudaFree(p->ws_nco); cudaFree(p->ws_theta); cudaFree(p->ws_inv); cudaFree(p->ws_nco0);
-    for (int i = 0; i < 2; i++) { cudaFree(p->d_stage[i]); cudaFree(p->d_pcm_stage[i]); cudaFree(p->d_audio_stage[i]); }
-    if (p->streams_ready) {
-        cudaStreamDestroy(p->s_compute); cudaStreamDestroy(p->s_h2d); cudaStreamDestroy(p->s_d2h);
-        for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_h2d[i]); cudaEventDestroy(p->ev_comp[i]); cudaEventDestroy(p->ev_d2h[i]); }
+    for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); }
+    cudaFree(p->ws_nco0);
+    if (p->s_pll) {
+        cudaStreamDestroy(p->s_pll);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); }
+        cudaEventDestroy(p->ev_in);
     }
+    cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);
+    for (auto e : p->ev_up) cudaEventDestroy(e);
+    for (auto e : p->ev_done) cudaEventDestroy(e);
+    if (p->streams_ready) { cudaStreamDestroy(p->s_compute); cudaStreamDestroy(p->s_h2d); cudaStreamDestroy(p->s_d2h); }
     delete p;
     return DY4_OK;
 }
@@ -325,69 +444,84 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     CU(cudaSetDevice(p->device));
     const int ch = p->stereo ? 2 : 1;
     const size_t S = (size_t)p->n_streams;
-    if (chunk_blocks <= 0) {
-        // default: ~64 MiB of input per chunk, at least one block, at most the job
-        const size_t per_block = S * m.block_size;
-        chunk_blocks = (int)std::max<size_t>(1, (64ull << 20) / per_block);
-    }
-    chunk_blocks = std::min(chunk_blocks, n_blocks);
+    // A "window" of blocks is resident in device staging at a time (DY4_STAGE_BYTES of input, default 4 GiB, or
+    // chunk_blocks if given).  Inside a window every sub-chunk has its own upload and download: all uploads are queued
+    // at once on the copy stream, the front half of sub-chunk c waits only for ITS bytes, and its PCM starts back to
+    // the host as soon as its back half is done — so the copies hide under the (PLL-bound) compute of the neighbours.
+    size_t budget = 4ull << 30;
+    if (const char* e = std::getenv("DY4_STAGE_BYTES")) budget = std::strtoull(e, nullptr, 10);
+    int window = chunk_blocks > 0 ? chunk_blocks : (int)std::max<size_t>(1, budget / (S * m.block_size));
+    window = std::min(window, n_blocks);
     if (!p->streams_ready) {
         CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            CU(cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
-        }
         p->streams_ready = true;
     }
-    if (p->stage_blocks < chunk_blocks || (h_audio && !p->stage_audio)) {
+    if (p->stage_blocks < window || (h_audio && !p->stage_audio)) {
         CU(cudaDeviceSynchronize());
-        for (int i = 0; i < 2; i++) {
-            cudaFree(p->d_stage[i]); cudaFree(p->d_pcm_stage[i]); cudaFree(p->d_audio_stage[i]);
-            p->d_stage[i] = nullptr; p->d_pcm_stage[i] = nullptr; p->d_audio_stage[i] = nullptr;
-            CU(cudaMalloc(&p->d_stage[i], S * chunk_blocks * m.block_size));
-            CU(cudaMalloc(&p->d_pcm_stage[i], S * chunk_blocks * m.audio_per_block * ch * sizeof(int16_t)));
-            if (h_audio) CU(cudaMalloc(&p->d_audio_stage[i], S * chunk_blocks * m.audio_per_block * ch * sizeof(float)));
-        }
-        p->stage_blocks = chunk_blocks;
+        cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);
+        p->d_stage = nullptr; p->d_pcm_stage = nullptr; p->d_audio_stage = nullptr;
+        CU(cudaMalloc(&p->d_stage, S * window * m.block_size));
+        CU(cudaMalloc(&p->d_pcm_stage, S * window * m.audio_per_block * ch * sizeof(int16_t)));
+        if (h_audio) CU(cudaMalloc(&p->d_audio_stage, S * window * m.audio_per_block * ch * sizeof(float)));
+        p->stage_blocks = window;
         p->stage_audio = h_audio != nullptr;
     }
-    const size_t total_audio = (size_t)n_blocks * m.audio_per_block * ch;   // per-stream row length of the host outputs
-    int c = 0;
-    for (int b = 0; b < n_blocks; b += chunk_blocks, c++) {
-        const int nb = std::min(chunk_blocks, n_blocks - b), buf = c & 1;
-        const size_t in_bytes = (size_t)nb * m.block_size, st_stride = (size_t)p->stage_blocks * m.block_size;
-        const size_t na = (size_t)nb * m.audio_per_block * ch, out_stride = (size_t)p->stage_blocks * m.audio_per_block * ch;
-        if (c >= 2) CU(cudaStreamWaitEvent(p->s_h2d, p->ev_comp[buf], 0));            // staging buffer free again
-        CU(cudaMemcpy2DAsync(p->d_stage[buf], st_stride, h_iq + (size_t)b * m.block_size, row_stride_bytes,
-                             in_bytes, S, cudaMemcpyHostToDevice, p->s_h2d));
-        CU(cudaEventRecord(p->ev_h2d[buf], p->s_h2d));
-        CU(cudaStreamWaitEvent(p->s_compute, p->ev_h2d[buf], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(p->s_compute, p->ev_d2h[buf], 0));         // output staging drained
-        int rc = process_device(p, p->d_stage[buf], st_stride, nb, h_pcm ? p->d_pcm_stage[buf] : nullptr,
-                                h_audio ? p->d_audio_stage[buf] : nullptr, nullptr, p->s_compute, out_stride, out_stride, 0);
+    const size_t st_stride = (size_t)p->stage_blocks * m.block_size;                     // staging row strides
+    const size_t out_stride = (size_t)p->stage_blocks * m.audio_per_block * ch;
+    const size_t total_audio = (size_t)n_blocks * m.audio_per_block * ch;                // host output row length
+
+    for (int w0 = 0; w0 < n_blocks; w0 += window) {
+        const int wn = std::min(window, n_blocks - w0);
+        int rc = ensure_workspace(p, wn);
         if (rc) return rc;
-        CU(cudaEventRecord(p->ev_comp[buf], p->s_compute));
-        CU(cudaStreamWaitEvent(p->s_d2h, p->ev_comp[buf], 0));
-        if (h_pcm) CU(cudaMemcpy2DAsync(h_pcm + (size_t)b * m.audio_per_block * ch, total_audio * sizeof(int16_t), p->d_pcm_stage[buf],
-                                        out_stride * sizeof(int16_t), na * sizeof(int16_t), S, cudaMemcpyDeviceToHost, p->s_d2h));
-        if (h_audio) CU(cudaMemcpy2DAsync(h_audio + (size_t)b * m.audio_per_block * ch, total_audio * sizeof(float), p->d_audio_stage[buf],
-                                          out_stride * sizeof(float), na * sizeof(float), S, cudaMemcpyDeviceToHost, p->s_d2h));
-        CU(cudaEventRecord(p->ev_d2h[buf], p->s_d2h));
+        const auto plan = plan_subchunks(wn, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+        const int nsub = (int)plan.size();
+        while ((int)p->ev_up.size() < nsub) {
+            cudaEvent_t a, d;
+            CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&d, cudaEventDisableTiming));
+            p->ev_up.push_back(a); p->ev_done.push_back(d);
+        }
+        for (int i = 0; i < nsub; i++) {                                                 // queue every upload of the window
+            const int b = plan[i].first, nb = plan[i].second;
+            CU(cudaMemcpy2DAsync(p->d_stage + (size_t)b * m.block_size, st_stride, h_iq + (size_t)(w0 + b) * m.block_size, row_stride_bytes,
+                                 (size_t)nb * m.block_size, S, cudaMemcpyHostToDevice, p->s_h2d));
+            CU(cudaEventRecord(p->ev_up[i], p->s_h2d));
+        }
+        Hooks hooks;
+        hooks.before_front = [&](int i, int, int) -> int {
+            CU(cudaStreamWaitEvent(p->s_compute, p->ev_up[i], 0));
+            return DY4_OK;
+        };
+        hooks.after_back = [&](int i, int b, int nb) -> int {
+            const size_t na = (size_t)nb * m.audio_per_block * ch, off = (size_t)b * m.audio_per_block * ch;
+            CU(cudaEventRecord(p->ev_done[i], p->s_compute));
+            CU(cudaStreamWaitEvent(p->s_d2h, p->ev_done[i], 0));
+            if (h_pcm) CU(cudaMemcpy2DAsync(h_pcm + (size_t)w0 * m.audio_per_block * ch + off, total_audio * sizeof(int16_t), p->d_pcm_stage + off,
+                                            out_stride * sizeof(int16_t), na * sizeof(int16_t), S, cudaMemcpyDeviceToHost, p->s_d2h));
+            if (h_audio) CU(cudaMemcpy2DAsync(h_audio + (size_t)w0 * m.audio_per_block * ch + off, total_audio * sizeof(float), p->d_audio_stage + off,
+                                              out_stride * sizeof(float), na * sizeof(float), S, cudaMemcpyDeviceToHost, p->s_d2h));
+            return DY4_OK;
+        };
+        rc = process_device(p, p->d_stage, st_stride, wn, h_pcm ? p->d_pcm_stage : nullptr, h_audio ? p->d_audio_stage : nullptr,
+                            nullptr, p->s_compute, out_stride, out_stride, 0, &hooks);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(p->s_h2d));                                             // the staging is reused by the next window
+        CU(cudaStreamSynchronize(p->s_compute));
+        CU(cudaStreamSynchronize(p->s_d2h));
     }
-    CU(cudaStreamSynchronize(p->s_h2d));
-    CU(cudaStreamSynchronize(p->s_compute));
-    CU(cudaStreamSynchronize(p->s_d2h));
     return DY4_OK;
 }
 
 extern "C" int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pilot, const float** d_nco, size_t* stride, int* n_if)
 {
-    if (!p || !p->stereo || !p->ws_pilot) { dy4_set_error("dy4_pipeline_debug_buffers: no stereo sub-chunk processed yet"); return DY4_ERR_ARG; }
-    if (d_pilot) *d_pilot = p->ws_pilot;
-    if (d_nco) *d_nco = p->ws_nco;
+    if (!p || !p->stereo || !p->ws[0].pilot) { dy4_set_error("dy4_pipeline_debug_buffers: no stereo sub-chunk processed yet"); return DY4_ERR_ARG; }
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    if (d_pilot) *d_pilot = p->ws[p->last_set].pilot;
+    if (d_nco) *d_nco = p->ws[p->last_set].nco;
     if (stride) *stride = p->ws_stride;
     if (n_if) *n_if = p->last_n_if;
     return DY4_OK;
@@ -436,7 +570,7 @@ extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
     const size_t S = (size_t)p->n_streams;
     char* o = (char*)host_buf;
     CU(cudaMemcpy(o, p->iq_tail, S * DY4_IQ_TAIL, cudaMemcpyDeviceToHost)); o += S * DY4_IQ_TAIL;
-    CU(cudaMemcpy(o, p->if_tail, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
+    CU(cudaMemcpy(o, if_tail_slot(p, p->seq), S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(o, p->mix_tail, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_MIX_TAIL * sizeof(float);
     CU(cudaMemcpy(o, p->pll_state, S * 8 * sizeof(float), cudaMemcpyDeviceToHost));
     return DY4_OK;
@@ -450,7 +584,7 @@ extern "C" int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf)
     const size_t S = (size_t)p->n_streams;
     const char* o = (const char*)host_buf;
     CU(cudaMemcpy(p->iq_tail, o, S * DY4_IQ_TAIL, cudaMemcpyHostToDevice)); o += S * DY4_IQ_TAIL;
-    CU(cudaMemcpy(p->if_tail, o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
+    CU(cudaMemcpy(if_tail_slot(p, p->seq), o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(p->mix_tail, o, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_MIX_TAIL * sizeof(float);
     CU(cudaMemcpy(p->pll_state, o, S * 8 * sizeof(float), cudaMemcpyHostToDevice));
     return DY4_OK;

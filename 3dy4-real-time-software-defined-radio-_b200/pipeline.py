@@ -12,6 +12,7 @@ from ._lib import lib, check
 from .modes import mode_params
 
 FLAG_EXACT_AUDIO = 1
+FLAG_DEBUG_ROWS = 2
 KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails")
 
 
@@ -21,13 +22,14 @@ def launch_count():
 
 
 class Pipeline:
-    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False):
+    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False, debug_rows=False):
         self.mode, self.stereo, self.n_streams, self.device = int(mode), bool(stereo), int(n_streams), int(device)
         self.params = mode_params(mode)
         self.channels = 2 if stereo else 1
         self._h = C.c_void_p()
         check(lib.dy4_pipeline_create(self.mode, int(self.stereo), self.n_streams, self.device,
-                                      FLAG_EXACT_AUDIO if exact_audio else 0, C.byref(self._h)), "dy4_pipeline_create")
+                                      (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0),
+                                      C.byref(self._h)), "dy4_pipeline_create")
 
     def close(self):
         if self._h:

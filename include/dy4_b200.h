@@ -99,6 +99,9 @@ typedef struct dy4_pipeline dy4_pipeline_t;
                                      with unfused multiply-add: every output is then bit-identical to
                                      the reference instead of within ~1e-7 (default: fused where safe) */
 
+#define DY4_FLAG_DEBUG_ROWS 2u    /* keep each process call in ONE sub-chunk so that dy4_pipeline_debug_buffers() returns
+                                     whole pilot / NCO rows (diagnostics; disables the PLL/FIR overlap) */
+
 /* Create a receiver for `n_streams` independent streams in `mode` (0..3), mono (stereo=0)
  * or stereo (stereo=1), on CUDA device `device`.  All carried state starts as in
  * project.cpp:240-255 (zero history, PLL at feedbackI=1, nco_state=1). */
@@ -123,11 +126,13 @@ int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stri
                          int16_t* d_pcm, float* d_audio, float* d_if, void* stream);
 
 /*
- * Same, HOST pointers (pinned memory recommended): input is cut into chunks of
- * blocks, copied host->device on a copy stream into double-buffered staging
- * while the previous chunk computes, and PCM/audio come back device->host on a
- * third stream — the replacement for the reference's stdin reader + queue.
- * Synchronous: returns when all outputs are in host memory.
+ * Same, HOST pointers (pinned memory recommended): the input is uploaded in
+ * sub-chunks on a copy stream, each sub-chunk's kernels wait only for their own
+ * bytes, and each sub-chunk's PCM/audio goes back device->host on a third stream
+ * as soon as it exists — the replacement for the reference's stdin reader + queue.
+ * chunk_blocks > 0 caps the blocks resident in device staging at once (default:
+ * DY4_STAGE_BYTES of input, 4 GiB).  Synchronous: returns when all outputs are in
+ * host memory.
  */
 int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                               int16_t* h_pcm, float* h_audio, int chunk_blocks);

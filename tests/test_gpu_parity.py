@@ -25,7 +25,7 @@ def sha(a):
 def run_gpu(dy4, mode, stereo, iq, exact_audio=False, want=("pcm", "audio", "if"), host=False, **kw):
     import torch
     iq = np.atleast_2d(iq)
-    p = dy4.Pipeline(mode, stereo, iq.shape[0], exact_audio=exact_audio)
+    p = dy4.Pipeline(mode, stereo, iq.shape[0], exact_audio=exact_audio, debug_rows=not host)
     try:
         if host:
             out = p.process_host(iq, want=[w for w in want if w != "if"], **kw)

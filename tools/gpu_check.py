@@ -17,7 +17,7 @@ for mode in range(4):
     d_iq = torch.from_numpy(iq).cuda()
     for stereo in (0, 1):
         for exact in (0, 1):
-            p = dy4_b200.Pipeline(mode, stereo, S, exact_audio=bool(exact))
+            p = dy4_b200.Pipeline(mode, stereo, S, exact_audio=bool(exact), debug_rows=True)
             t = time.time()
             out = p.process(d_iq, want=("pcm", "audio", "if"))
             torch.cuda.synchronize()
