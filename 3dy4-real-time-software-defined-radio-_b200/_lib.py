@@ -41,6 +41,8 @@ def _load():
         "dy4_mode_params": (i, [i, C.POINTER(ModeParamsC)]),
         "dy4_lpf_taps": (i, [f, f, us, i, vp]),
         "dy4_bpf_taps": (i, [f, f, f, us, i, vp]),
+        "dy4_firwin": (i, [i, C.c_double, C.c_double, i, vp]),
+        "dy4_rrc_taps": (i, [C.c_double, i, vp]),
         "dy4_iq_to_float": (i, [vp, sz, vp]),
         "dy4_convolve_fir": (i, [vp, vp, sz, vp, sz]),
         "dy4_block_fir": (i, [vp, vp, sz, vp, sz, vp, sz]),
@@ -60,6 +62,9 @@ def _load():
         "dy4_pipeline_reset": (i, [vp]),
         "dy4_pipeline_process": (i, [vp, vp, sz, i, vp, vp, vp, vp]),
         "dy4_pipeline_process_host": (i, [vp, vp, sz, i, vp, vp, i]),
+        "dy4_pipeline_rds_read": (i, [vp, vp, vp, sz, C.POINTER(i), vp]),
+        "dy4_pipeline_rds_bounds": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "dy4_pipeline_rds_drain": (i, [vp, vp, sz, vp, sz, vp, sz, vp]),
         "dy4_pipeline_debug_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), psz, C.POINTER(i)]),
         "dy4_pipeline_profile": (i, [vp, i]),
         "dy4_pipeline_profile_get": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]),

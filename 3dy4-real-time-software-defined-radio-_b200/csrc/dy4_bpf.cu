@@ -15,9 +15,9 @@
 
 namespace {
 
-__constant__ TapPairs c_bpf2[4];   // (pilot[k], stereo-band[k]) pairs, per mode
+__constant__ TapPairs c_bpf2[6];   // (pilot[k], stereo-band[k]) pairs per mode; [4],[5]: RDS band-pass and RDS carrier band-pass, (h,h)
 
-template <int R, int NT, bool EXACT>
+template <int R, int NT, bool EXACT, bool SQUARE>
 __global__ void __launch_bounds__(NT)
 k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
            float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if,
@@ -39,6 +39,7 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
         if (i < 0) v = *reinterpret_cast<const float4*>(tail + DY4_IF_TAIL + i);
         else if (i + 3 < n_if) v = __ldg(reinterpret_cast<const float4*>(row + i));
         else { v.x = i < n_if ? row[i] : 0.f; v.y = i + 1 < n_if ? row[i + 1] : 0.f; v.z = i + 2 < n_if ? row[i + 2] : 0.f; v.w = 0.f; }
+        if (SQUARE) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }     // RDS carrier recovery: the filter input is the squared signal
         const int p = 4 * u;
         float4* d = reinterpret_cast<float4*>(&sm[p + 2 * (p / R)]);
         d[0] = make_float4(v.x, v.x, v.y, v.y);
@@ -73,11 +74,11 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
 #pragma unroll
         for (int r = 0; r < R; r += 4) {
             *reinterpret_cast<float4*>(pilot + o + r) = make_float4(op[r], op[r + 1], op[r + 2], op[r + 3]);
-            *reinterpret_cast<float4*>(sband + o + r) = make_float4(os[r], os[r + 1], os[r + 2], os[r + 3]);
+            if (sband) *reinterpret_cast<float4*>(sband + o + r) = make_float4(os[r], os[r + 1], os[r + 2], os[r + 3]);
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = op[r]; sband[o + r] = os[r]; }
+        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = op[r]; if (sband) sband[o + r] = os[r]; }
     }
 }
 
@@ -88,9 +89,11 @@ cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     constexpr int R = 8, NT = 128;
     dim3 grid(a.n_streams, (a.n_if + NT * R - 1) / (NT * R));
-    k_twin_bpf<R, NT, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
+    if (a.variant == 0) k_twin_bpf<R, NT, true, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
+    else if (a.variant == 1) k_twin_bpf<R, NT, false, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
+    else k_twin_bpf<R, NT, false, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
     g_dy4_launches++;
     return cudaGetLastError();
 }
 
-cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf4) { return cudaMemcpyToSymbol(c_bpf2, bpf4, sizeof(TapPairs) * 4); }
+cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf6) { return cudaMemcpyToSymbol(c_bpf2, bpf6, sizeof(TapPairs) * 6); }

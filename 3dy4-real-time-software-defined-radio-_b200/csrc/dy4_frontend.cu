@@ -306,6 +306,209 @@ k_frontend_tma(const uint8_t* __restrict__ iq, long long row_stride, const uint8
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// v3: same staging (one bulk copy per tile, two buffers), three changes aimed at the FMA pipe's idle time:
+//  * every CTA walks a CONTIGUOUS range of tiles, so the discriminator's "sample before the tile" is simply the
+//    last output of the CTA's previous tile (kept in shared memory); the 101 extra taps on one lane are paid only at
+//    the start of a range or of a stream, and the second barrier per tile goes away (edge slots double-buffered);
+//  * the -0 addend of the unfused product lives in a VECTOR register (read back from shared memory), which leaves
+//    the uniform operand slot of FFMA2 to the taps: ptxas then streams them through uniform registers (LDCU)
+//    instead of parking them in ~100 vector registers, and more CTAs fit per SM;
+//  * UNPACK = 1 converts the bytes with I2F.S8 (byte select in the instruction, after one XOR 0x80808080 per
+//    word), which takes the bias subtraction off the FMA pipe.
+// ------------------------------------------------------------------------------------------------------------
+template <int UNPACK>
+__device__ __forceinline__ void unpack_word(uint32_t w, u64 neg_bias, u64& x0, u64& x1)
+{
+    if (UNPACK == 1) {
+        const uint32_t sgn = w ^ 0x80808080u;                                  // bytes become two's-complement b-128
+        x0 = pk2((float)(int8_t)(sgn & 0xffu), (float)(int8_t)((sgn >> 8) & 0xffu));
+        x1 = pk2((float)(int8_t)((sgn >> 16) & 0xffu), (float)(int8_t)(sgn >> 24));
+    } else {
+        x0 = unpack_iq(w, 0, neg_bias);
+        x1 = unpack_iq(w, 1, neg_bias);
+    }
+}
+
+template <int MODE, int D, int R, int NT, bool EXACT, int UNPACK, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_frontend_v3(const uint8_t* __restrict__ iq, long long row_stride, const uint8_t* __restrict__ iq_tail,
+              float* __restrict__ if_out, long long if_stride, int n_if, u64 nz,
+              int tiles_per_stream, int n_tiles)
+{
+    constexpr int T = NT * R;
+    constexpr int CH = D * R;
+    constexpr int HALO = DY4_IQ_TAIL / 2;
+    constexpr int TILE_BYTES = 2 * D * T + DY4_IQ_TAIL;
+    constexpr int BUF_BYTES = (TILE_BYTES + 64 + 127) / 128 * 128;
+    constexpr int QMAX = D * (R - 1) + (DY4_NTAPS - 1);
+    constexpr int C0 = HALO - (DY4_NTAPS - 1);
+    constexpr int CA = C0 & ~7;
+    constexpr int NG = (C0 - CA + QMAX) / 8 + 1;
+    static_assert(TILE_BYTES % 16 == 0 && (2 * CH) % 16 == 0, "bulk copies and window loads are 16-byte granular");
+    extern __shared__ __align__(128) uint8_t smraw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ float2 s_last[2][NT];
+    __shared__ u64 s_nz[NT];
+    const int tid = threadIdx.x;
+    const long long row_bytes = 2LL * D * n_if;
+    const u64* hh = reinterpret_cast<const u64*>(c_rf2s[MODE].t);    // compile-time constant-bank addresses
+    const u64 neg_bias = pk2(-8388736.0f, -8388736.0f);
+
+    auto issue = [&](int t, int b) {
+        const int s = t / tiles_per_stream, m0 = (t - s * tiles_per_stream) * T;
+        const uint8_t* row = iq + (long long)s * row_stride;
+        uint8_t* dst = smraw + b * BUF_BYTES;
+        const long long start = 2LL * D * m0 - DY4_IQ_TAIL;
+        const long long begin = start < 0 ? 0 : start;
+        long long len = (start + TILE_BYTES) - begin;
+        if (begin + len > row_bytes) len = row_bytes - begin;
+        if (len < 0) len = 0;
+        const uint32_t head = start < 0 ? (uint32_t)DY4_IQ_TAIL : 0u;
+        mbar_expect_tx(&mbar[b], head + (uint32_t)len);
+        if (head) bulk_g2s(dst, iq_tail + (long long)s * DY4_IQ_TAIL, head, &mbar[b]);
+        if (len > 0) bulk_g2s(dst + head, row + begin, (uint32_t)len, &mbar[b]);
+    };
+
+    const int t_begin = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    s_nz[tid] = nz;
+    __syncthreads();
+    if (tid == 0) {
+        if (t_begin < t_end) issue(t_begin, 0);
+        if (t_begin + 1 < t_end) issue(t_begin + 1, 1);
+    }
+    const u64 nzv = *reinterpret_cast<volatile u64*>(&s_nz[tid]);  // (-0,-0) in a vector register: see the header comment
+
+    int it = 0;
+    for (int t = t_begin; t < t_end; t++, it++) {
+        const int b = it & 1;
+        const int s = t / tiles_per_stream, m0 = (t - s * tiles_per_stream) * T;
+        mbar_wait(&mbar[b], (it >> 1) & 1);
+        const uint8_t* buf = smraw + b * BUF_BYTES;
+
+        u64 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0ull;
+        const uint4* win = reinterpret_cast<const uint4*>(buf + 2 * (CH * tid + CA));
+#pragma unroll
+        for (int g = NG - 1; g >= 0; g--) {
+            const uint4 v = win[g];
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int w = 3; w >= 0; w--) {
+                if (8 * g + 2 * w + 1 - (C0 - CA) < 0 || 8 * g + 2 * w - (C0 - CA) > QMAX) continue;
+                u64 xs[2];
+                unpack_word<UNPACK>(ws[w], neg_bias, xs[0], xs[1]);
+#pragma unroll
+                for (int h = 1; h >= 0; h--) {
+                    const int q = 8 * g + 2 * w + h - (C0 - CA);
+                    if (q < 0 || q > QMAX) continue;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int k = D * r + (DY4_NTAPS - 1) - q;
+                        if (k >= 0 && k < DY4_NTAPS) acc[r] = tap2<EXACT>(acc[r], xs[h], hh[k], nzv);
+                    }
+                }
+            }
+        }
+
+        float pI, pQ;
+        upk2(acc[R - 1], pI, pQ);
+        s_last[b][tid] = make_float2(pI, pQ);
+        const bool edge = it == 0 || m0 == 0;                  // no previous tile of this stream in this CTA
+        if (edge && tid == 0) {                                // output m0-1 from the history in front of the tile
+            u64 a0 = 0ull;
+            const uint4* w0 = reinterpret_cast<const uint4*>(buf);
+            constexpr int PMAX = HALO - D;
+#pragma unroll 1
+            for (int g = PMAX / 8; g >= 0; g--) {
+                const uint4 v = w0[g];
+                const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    const int k = PMAX - (8 * g + j);
+                    if (k >= 0 && k < DY4_NTAPS) a0 = tap2<EXACT>(a0, unpack_iq(ws[j >> 1], j & 1, neg_bias), hh[k], nzv);
+                }
+            }
+            upk2(a0, pI, pQ);
+        }
+        __syncthreads();                                       // edge slots visible; every read of buffer b is done
+        if (tid == 0 && t + 2 < t_end) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + 2, b);
+        }
+        if (tid > 0) { const float2 l = s_last[b][tid - 1]; pI = l.x; pQ = l.y; }
+        else if (!edge) { const float2 l = s_last[b ^ 1][NT - 1]; pI = l.x; pQ = l.y; }
+
+        float out[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float I, Q;
+            upk2(acc[r], I, Q);
+            const float den = __double2float_rn(fma((double)I, (double)I, (double)Q * (double)Q));
+            const float num = __fsub_rn(__fmul_rn(I, __fsub_rn(Q, pQ)), __fmul_rn(Q, __fsub_rn(I, pI)));
+            out[r] = (den == 0.0f) ? 0.0f : __fdiv_rn(num, den);
+            pI = I; pQ = Q;
+        }
+        float* dst = if_out + (long long)s * if_stride + m0 + tid * R;
+        const int left = n_if - (m0 + tid * R);
+        if (left >= R) {
+#pragma unroll
+            for (int r = 0; r < R; r += 4) *reinterpret_cast<float4*>(dst + r) = make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) if (r < left) dst[r] = out[r];
+        }
+    }
+}
+
+template <int MODE, int D, int R, int NT, bool EXACT, int UNPACK, int MINB>
+cudaError_t launch_v3(const Dy4FrontendArgs& a, cudaStream_t st)
+{
+    constexpr int T = NT * R;
+    constexpr int TILE_BYTES = 2 * D * T + DY4_IQ_TAIL;
+    constexpr int BUF_BYTES = (TILE_BYTES + 64 + 127) / 128 * 128;
+    const size_t smem = 2 * BUF_BYTES;
+    auto kern = k_frontend_v3<MODE, D, R, NT, EXACT, UNPACK, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int tiles_per_stream = (a.n_if + T - 1) / T;
+    const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
+    if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)sms * ctas_per_sm);
+    kern<<<grid, NT, smem, st>>>(a.iq, a.row_stride, a.iq_tail, a.if_out, a.if_stride, a.n_if, a.neg_zero2,
+                                 tiles_per_stream, (int)n_tiles);
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
+
+template <int UNPACK, int MINB>
+cudaError_t launch_v3_mode(const Dy4FrontendArgs& a, cudaStream_t st)
+{
+    switch (a.mode) {                                  // rf_decim follows the mode (project.cpp:178-238)
+    case 0: return launch_v3<0, 10, 8, 128, true, UNPACK, MINB>(a, st);
+    case 1: return launch_v3<1, 5, 8, 128, true, UNPACK, MINB>(a, st);
+    case 2: return launch_v3<2, 10, 8, 128, true, UNPACK, MINB>(a, st);
+    case 3: return launch_v3<3, 5, 8, 128, true, UNPACK, MINB>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int D, int R, int NT, bool EXACT>
 cudaError_t launch_tma(const Dy4FrontendArgs& a, cudaStream_t st)
 {
@@ -355,7 +558,10 @@ cudaError_t dy4_launch_frontend(const Dy4FrontendArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     // DY4_FRONTEND=staged selects the earlier converted-to-bf16 staging kernel (A/B knob; identical results)
-    static const bool staged = std::getenv("DY4_FRONTEND") && std::string(std::getenv("DY4_FRONTEND")) == "staged";
+    static const std::string which = std::getenv("DY4_FRONTEND") ? std::getenv("DY4_FRONTEND") : "";
+    static const bool staged = which == "staged";
+    if (which == "v3") return launch_v3_mode<0, 4>(a, st);
+    if (which == "v3i") return launch_v3_mode<1, 4>(a, st);
     if (a.rf_decim == 10) return staged ? launch<10, 8, 128, true>(a, st) : launch_tma<10, 8, 128, true>(a, st);
     if (a.rf_decim == 5) return staged ? launch<5, 8, 128, true>(a, st) : launch_tma<5, 8, 128, true>(a, st);
     return cudaErrorInvalidValue;

@@ -21,7 +21,8 @@ struct Dy4BpfArgs {
     const float* if_in; long long if_stride;    // IF samples of this chunk
     const float* if_tail;                       // [n_streams][DY4_IF_TAIL] IF samples preceding the chunk
     float* pilot; float* sband; long long out_stride;
-    int n_if, n_streams, mode;
+    int n_if, n_streams, mode;                  // mode 0..3: (pilot, stereo) table; 4, 5: RDS band-pass / carrier tables
+    int variant;                                // 0 exact pair; 1 fused; 2 fused on the SQUARED input.  sband may be NULL.
     unsigned long long neg_zero2;
 };
 
@@ -62,8 +63,48 @@ cudaError_t dy4_launch_audio(const Dy4AudioArgs& a, cudaStream_t st);
 cudaError_t dy4_launch_tails(const Dy4TailArgs& a, cudaStream_t st);
 // one-time (per device) upload of the four per-mode tap tables
 cudaError_t dy4_upload_taps_frontend(const TapPairs* rf4);
-cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf4);
+cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf6);
 cudaError_t dy4_upload_taps_audio(const TapPairs* audio4);
+
+// ---- RDS filtering front end (Python model only: model/fmMonoBlock.py:673-696) -------------------------------------
+struct Dy4RdsArgs {
+    const float* rds_f; long long stride;       // 54-60 kHz band-pass output of this chunk (IF rate)
+    const float* rds_tail;                      // [n_streams][DY4_IF_TAIL] of it before the chunk
+    const float* carrier;                       // 113.5-114.5 kHz band-pass of rds_f^2
+    double* theta; long long wide_stride;       // scratch: PLL phase argument after each sample
+    float* nco_i; float* nco_q;                 // scratch rows (stride)
+    double* pll_state;                          // [n_streams][8]: integ, phase, trigOffset, theta, ncoI_state, ncoQ_state
+    float* mix_tail;                            // [n_streams][2][DY4_MIX_TAIL]: mixed I / Q before the chunk
+    float* lp; long long lp_stride;             // scratch [n_streams][2][lp_stride]: resampler output I, Q of this chunk
+    float* lp_tail;                             // [n_streams][2][DY4_MIX_TAIL] of it before the chunk
+    float* out_i; float* out_q; long long out_stride;   // RRC-filtered I / Q (38 kS/s) of this chunk
+    const float* taps_poly; int up_pad;         // [101][up_pad] polyphase low-pass taps (gain up), up = 19
+    const float* taps_rrc;                      // 101 RRC taps
+    int n_if, n_streams;
+    long long if_abs;                           // absolute IF index of the chunk's first sample (resampler phase)
+    long long m_first; int n_out;               // absolute index of the first resampler output of this chunk and their count
+    double w, Kp, Ki, nco_scale, phase_adjust;
+    int up, down;
+};
+cudaError_t dy4_launch_rds_pll(const Dy4RdsArgs& a, cudaStream_t st);        // carrier -> theta -> nco_i / nco_q
+cudaError_t dy4_launch_rds_resample(const Dy4RdsArgs& a, cudaStream_t st);   // delay, mix, 19/120 resampler, RRC, tails
+
+// RDS back half (model/fmSupportLib.py:209-247, model/fmMonoBlock.py:78-284, 699-730): one thread per stream walks whole
+// model blocks of DY4_RDS_BLOCK in-phase RRC samples: symbol timing, Manchester + differential decoding, frame sync.
+constexpr int DY4_RDS_BLOCK = 3040;            // 16 samples/symbol x 190 symbols = 19 200 IF samples x 19/120
+constexpr int DY4_RDS_STATE_INTS = 16;
+struct Dy4RdsDecodeArgs {
+    const float* acc; long long acc_stride; int n_blocks;      // n_blocks whole model blocks at the start of every row
+    int* state;                                                // [n_streams][DY4_RDS_STATE_INTS]
+    int* counts;                                               // [n_streams][4]: symbols, bits, events written so far
+    int8_t* sym; long long sym_stride; int sym_cap;
+    int8_t* bits; long long bits_stride; int bits_cap;
+    int* events; long long ev_stride; int ev_cap;              // 4 ints per event: type (A,B,C,C',D = 0..4), bit position, false-positive flag, 16-bit word
+    int n_streams;
+};
+cudaError_t dy4_launch_rds_append(const float* rrc_i, long long rrc_stride, int n_new, float* acc, long long acc_stride,
+                                  int consumed, int left, int n_streams, cudaStream_t st);
+cudaError_t dy4_launch_rds_decode(const Dy4RdsDecodeArgs& a, cudaStream_t st);
 
 // Generic single-op kernels for the filter.h compatibility tier (any tap count, any factor).
 cudaError_t dy4_launch_generic_fir(const float* x_ext, int n_hist, int n_out, int step, const float* h, int nh, float* y, cudaStream_t st);

@@ -55,6 +55,18 @@ struct dy4_pipeline {
     WorkSet ws[2];
     float* ws_nco0 = nullptr;
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
+    // RDS filtering front end (DY4_FLAG_RDS): its own stream beside the stereo PLL
+    float *rds_f = nullptr, *rds_carrier = nullptr, *rds_nco_i = nullptr, *rds_nco_q = nullptr, *rds_lp = nullptr, *rds_out = nullptr;
+    double *rds_theta = nullptr, *rds_pll_state = nullptr;
+    float *rds_tail = nullptr, *rds_mix_tail = nullptr, *rds_lp_tail = nullptr, *d_rds_poly = nullptr, *d_rds_rrc = nullptr;
+    size_t rds_cap = 0; int rds_n_out = 0; long long if_abs = 0;
+    // RDS back half: accumulation rows of in-phase RRC samples, decoder state, growing output rows
+    float* rds_acc = nullptr; size_t rds_acc_cap = 0; int rds_left = 0, rds_consumed = 0;
+    int *rds_dec_state = nullptr, *rds_counts = nullptr, *rds_events = nullptr;
+    int8_t *rds_sym = nullptr, *rds_bits = nullptr;
+    size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0;
+    long long rds_blocks_since_drain = 0;
+    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr;
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
     // host-facing staging
@@ -83,7 +95,7 @@ int upload_tap_tables(int device)
     static std::vector<int> done;
     std::lock_guard<std::mutex> lk(mu);
     if (std::find(done.begin(), done.end(), device) != done.end()) return DY4_OK;
-    static TapPairs rf4[4], bpf4[4], audio4[4];
+    static TapPairs rf4[4], bpf4[6], audio4[4];
     std::memset(rf4, 0, sizeof(rf4)); std::memset(bpf4, 0, sizeof(bpf4)); std::memset(audio4, 0, sizeof(audio4));
     for (int mode = 0; mode < 4; mode++) {
         dy4_mode_params_t mp;
@@ -99,6 +111,14 @@ int upload_tap_tables(int device)
             bpf4[mode].t[k] = make_float2(pilot[k], sb[k]);
             audio4[mode].t[k] = make_float2(au[k], au[k]);
         }
+    }
+    {   // RDS band-pass filters of the Python model (fmMonoBlock.py:489-499), IF rate 240 kS/s, float32 copies of firwin's doubles
+        double h[DY4_NTAPS];
+        const double nyq = 240e3 / 2;
+        dy4_firwin(DY4_NTAPS, 54e3 / nyq, 60e3 / nyq, 0, h);
+        for (int k = 0; k < DY4_NTAPS; k++) bpf4[4].t[k] = make_float2((float)h[k], (float)h[k]);
+        dy4_firwin(DY4_NTAPS, 113.5e3 / nyq, 114.5e3 / nyq, 0, h);
+        for (int k = 0; k < DY4_NTAPS; k++) bpf4[5].t[k] = make_float2((float)h[k], (float)h[k]);
     }
     CU(dy4_upload_taps_frontend(rf4));
     CU(dy4_upload_taps_bpf(bpf4));
@@ -117,6 +137,20 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     std::vector<float> h(S * 8, 0.0f);
     for (size_t s = 0; s < S; s++) { h[s * 8 + 0] = 1.0f; h[s * 8 + 5] = 1.0f; }   // PLLState, project.cpp:46-53
     CU(cudaMemcpyAsync(p->pll_state, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    p->if_abs = 0; p->rds_n_out = 0;
+    if (p->flags & DY4_FLAG_RDS) {
+        CU(cudaMemsetAsync(p->rds_tail, 0, S * DY4_IF_TAIL * sizeof(float), st));
+        CU(cudaMemsetAsync(p->rds_mix_tail, 0, S * 2 * DY4_MIX_TAIL * sizeof(float), st));
+        CU(cudaMemsetAsync(p->rds_lp_tail, 0, S * 2 * DY4_MIX_TAIL * sizeof(float), st));
+        std::vector<double> d(S * 8, 0.0);
+        for (size_t s = 0; s < S; s++) { d[s * 8 + 4] = 1.0; d[s * 8 + 5] = 1.0; }   // ncoState = q_ncoState = 1.0 (fmMonoBlock.py:455,459)
+        CU(cudaMemcpyAsync(p->rds_pll_state, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        std::vector<int> ds(S * DY4_RDS_STATE_INTS, 0);
+        for (size_t s = 0; s < S; s++) { ds[s * DY4_RDS_STATE_INTS + 7] = 24; ds[s * DY4_RDS_STATE_INTS + 9] = -1; }   // window_index = 24, offsetState = '' (fmMonoBlock.py:580,592)
+        CU(cudaMemcpyAsync(p->rds_dec_state, ds.data(), ds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(p->rds_counts, 0, S * 4 * sizeof(int), st));
+        p->rds_left = 0; p->rds_consumed = 0; p->rds_blocks_since_drain = 0;
+    }
     CU(cudaStreamSynchronize(st));
     return DY4_OK;
 }
@@ -132,7 +166,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 16 : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
-    const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
+    const bool whole = (p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)) != 0;    // RDS branch: one sub-chunk per call (round 1)
     int nsub = 3;                                      // largest sub-chunk = a third of the job (see plan_subchunks)
     if (const char* e = std::getenv("DY4_SUBCHUNKS")) nsub = std::max(1, atoi(e));
     if (p->stereo && !whole && n_blocks >= 8) blocks = std::min(blocks, (n_blocks + nsub - 1) / nsub);
@@ -168,6 +202,20 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaEventCreateWithFlags(&p->ev_pll[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    }
+    if (p->flags & DY4_FLAG_RDS) {
+        cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta);
+        cudaFree(p->rds_lp); cudaFree(p->rds_out);
+        CU(cudaMalloc(&p->rds_f, bytes)); CU(cudaMalloc(&p->rds_carrier, bytes));
+        CU(cudaMalloc(&p->rds_nco_i, bytes)); CU(cudaMalloc(&p->rds_nco_q, bytes)); CU(cudaMalloc(&p->rds_theta, 2 * bytes));
+        p->rds_cap = (p->ws_stride * 19 + 119) / 120 + 4;
+        CU(cudaMalloc(&p->rds_lp, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
+        CU(cudaMalloc(&p->rds_out, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
+        if (!p->s_rds) {
+            CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
+        }
     }
     p->ws_blocks = blocks;
     return DY4_OK;
@@ -215,10 +263,89 @@ int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_o
         Dy4BpfArgs ba;
         ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
         ba.pilot = w.pilot; ba.sband = w.sband; ba.out_stride = (long long)p->ws_stride;
-        ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.neg_zero2 = kNegZero2;
+        ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.variant = 0; ba.neg_zero2 = kNegZero2;
         { Timer t(p, DY4_K_BPF, st); CU(dy4_launch_bpf(ba, st)); }
     }
     return DY4_OK;
+}
+
+// grow a [n_streams][cap] device array to at least `need` columns, keeping its contents (stream-ordered on st)
+template <typename T>
+int grow_rows(T*& buf, size_t& cap, size_t need, size_t n_streams, size_t elems, cudaStream_t st)
+{
+    if (need <= cap) return DY4_OK;
+    const size_t ncap = std::max(need, cap * 2);
+    T* nb = nullptr;
+    CU(cudaMalloc(&nb, n_streams * ncap * elems * sizeof(T)));
+    if (buf && cap) CU(cudaMemcpy2DAsync(nb, ncap * elems * sizeof(T), buf, cap * elems * sizeof(T), cap * elems * sizeof(T), n_streams, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(buf);
+    buf = nb; cap = ncap;
+    return DY4_OK;
+}
+
+// RDS back half on the samples of this call: append to the accumulation rows, decode every whole model block
+int run_rds_decode(dy4_pipeline* p, cudaStream_t st)
+{
+    const size_t S = (size_t)p->n_streams;
+    const int n_new = p->rds_n_out;
+    int rc;
+    if ((rc = grow_rows(p->rds_acc, p->rds_acc_cap, (size_t)p->rds_left + p->rds_consumed + n_new + 64, S, 1, st))) return rc;
+    CU(dy4_launch_rds_append(p->rds_out, 2LL * (long long)p->rds_cap, n_new, p->rds_acc, (long long)p->rds_acc_cap, p->rds_consumed, p->rds_left,
+                             p->n_streams, st));
+    const int total = p->rds_left + n_new;
+    const int nblk = total / DY4_RDS_BLOCK;
+    p->rds_consumed = nblk * DY4_RDS_BLOCK;
+    p->rds_left = total - p->rds_consumed;
+    if (nblk == 0) return DY4_OK;
+    p->rds_blocks_since_drain += nblk;
+    const size_t need_sym = (size_t)p->rds_blocks_since_drain * (DY4_RDS_BLOCK / 16), need_bits = (need_sym + 1) / 2 + 1;
+    if ((rc = grow_rows(p->rds_sym, p->rds_sym_cap, need_sym, S, 1, st))) return rc;
+    if ((rc = grow_rows(p->rds_bits, p->rds_bits_cap, need_bits, S, 1, st))) return rc;
+    if ((rc = grow_rows(p->rds_events, p->rds_ev_cap, need_bits, S, 4, st))) return rc;    // at most one event per window, one window per bit
+    Dy4RdsDecodeArgs da{};
+    da.acc = p->rds_acc; da.acc_stride = (long long)p->rds_acc_cap; da.n_blocks = nblk;
+    da.state = p->rds_dec_state; da.counts = p->rds_counts;
+    da.sym = p->rds_sym; da.sym_stride = (long long)p->rds_sym_cap; da.sym_cap = (int)p->rds_sym_cap;
+    da.bits = p->rds_bits; da.bits_stride = (long long)p->rds_bits_cap; da.bits_cap = (int)p->rds_bits_cap;
+    da.events = p->rds_events; da.ev_stride = (long long)p->rds_ev_cap; da.ev_cap = (int)p->rds_ev_cap;
+    da.n_streams = p->n_streams;
+    CU(dy4_launch_rds_decode(da, st));
+    return DY4_OK;
+}
+
+// RDS filtering front end of one sub-chunk on its own stream (fmMonoBlock.py:673-691), beside the stereo PLL
+int run_rds(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
+{
+    const dy4_mode_params_t& m = p->mp;
+    const int n_if = c.nb * m.if_per_block;
+    auto& w = p->ws[c.set];
+    Dy4BpfArgs ba;
+    ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
+    ba.pilot = p->rds_f; ba.sband = nullptr; ba.out_stride = (long long)p->ws_stride;
+    ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = 4; ba.variant = 1; ba.neg_zero2 = kNegZero2;
+    CU(dy4_launch_bpf(ba, st));                                   // RDS channel extraction, 54-60 kHz
+    ba.if_in = p->rds_f; ba.if_tail = p->rds_tail; ba.pilot = p->rds_carrier; ba.mode = 5; ba.variant = 2;
+    CU(dy4_launch_bpf(ba, st));                                   // squaring + 113.5-114.5 kHz carrier extraction
+    Dy4RdsArgs ra{};
+    ra.rds_f = p->rds_f; ra.stride = (long long)p->ws_stride; ra.rds_tail = p->rds_tail; ra.carrier = p->rds_carrier;
+    ra.theta = p->rds_theta; ra.wide_stride = (long long)p->ws_stride; ra.nco_i = p->rds_nco_i; ra.nco_q = p->rds_nco_q;
+    ra.pll_state = p->rds_pll_state; ra.mix_tail = p->rds_mix_tail; ra.lp = p->rds_lp; ra.lp_stride = (long long)p->rds_cap;
+    ra.lp_tail = p->rds_lp_tail; ra.out_i = p->rds_out; ra.out_q = p->rds_out + p->rds_cap; ra.out_stride = 2LL * (long long)p->rds_cap;
+    ra.taps_poly = p->d_rds_poly; ra.up_pad = 20; ra.taps_rrc = p->d_rds_rrc; ra.n_if = n_if; ra.n_streams = p->n_streams;
+    ra.if_abs = p->if_abs; ra.up = 19; ra.down = 120;
+    ra.m_first = (19 * p->if_abs + 119) / 120;
+    ra.n_out = (int)((19 * (p->if_abs + n_if) + 119) / 120 - ra.m_first);
+    const double bw = 0.001;                                      // fmMonoBlock.py:444-447
+    ra.w = 2 * 3.141592653589793 * (114e3 / 240e3); ra.Kp = bw * 2.666; ra.Ki = (bw * bw) * 3.555; ra.nco_scale = 0.5; ra.phase_adjust = 0.0;
+    CU(dy4_launch_rds_pll(ra, st));
+    CU(dy4_launch_rds_resample(ra, st));
+    Dy4TailArgs ta{};                                             // history of the band-pass output for the next call
+    ta.if_in = p->rds_f; ta.if_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.if_tail = p->rds_tail; ta.n_streams = p->n_streams;
+    CU(dy4_launch_tails(ta, st));
+    p->rds_n_out = ra.n_out;
+    p->if_abs += n_if;
+    return run_rds_decode(p, st);
 }
 
 // the serial part, on its own stream: pilot -> NCO row
@@ -285,7 +412,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     const int ch = p->stereo ? 2 : 1;
     int rc = ensure_workspace(p, n_blocks);
     if (rc) return rc;
-    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)));
     auto sub = [&](int b, int nb, long long seq) {
         SubChunk c;
         c.nb = nb;
@@ -324,6 +451,11 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
+        if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
+            CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
+            if ((rc = run_rds(p, c, p->s_rds))) return rc;
+            CU(cudaEventRecord(p->ev_rds, p->s_rds));
+        }
         CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
         if ((rc = run_pll(p, c, p->s_pll))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
@@ -339,6 +471,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
         if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
     }
+    if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
     return DY4_OK;
 }
 
@@ -375,6 +508,27 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
         CU(cudaMemcpy(p->d_taps_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     const size_t S = (size_t)n_streams;
+    if (flags & DY4_FLAG_RDS) {
+        if (mode != 0 || !stereo) { dy4_set_error("DY4_FLAG_RDS: the model defines the RDS path for mode 0 stereo only"); delete p; return DY4_ERR_ARG; }
+        const int U = 19, NT = DY4_NTAPS * U;                      // fmMonoBlock.py:61-67,514-515: 1919 taps, Fc 3 kHz, gain 19, scipy default window
+        std::vector<double> h(NT), r(DY4_NTAPS);
+        dy4_firwin(NT, 0.0, 3e3 / (240e3 * U / 2), 1, h.data());
+        std::vector<float> poly((size_t)DY4_NTAPS * 20, 0.0f), rrc(DY4_NTAPS);
+        for (int j = 0; j < DY4_NTAPS; j++)
+            for (int ph = 0; ph < U; ph++) poly[(size_t)j * 20 + ph] = (float)(h[(size_t)ph + (size_t)j * U] * U);
+        dy4_rrc_taps(38000.0, DY4_NTAPS, r.data());               // sps 16 * 2375 (fmMonoBlock.py:66-67,690)
+        for (int k = 0; k < DY4_NTAPS; k++) rrc[k] = (float)r[k];
+        CU(cudaMalloc(&p->d_rds_poly, poly.size() * sizeof(float)));
+        CU(cudaMemcpy(p->d_rds_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&p->d_rds_rrc, rrc.size() * sizeof(float)));
+        CU(cudaMemcpy(p->d_rds_rrc, rrc.data(), rrc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&p->rds_tail, S * DY4_IF_TAIL * sizeof(float)));
+        CU(cudaMalloc(&p->rds_mix_tail, S * 2 * DY4_MIX_TAIL * sizeof(float)));
+        CU(cudaMalloc(&p->rds_lp_tail, S * 2 * DY4_MIX_TAIL * sizeof(float)));
+        CU(cudaMalloc(&p->rds_pll_state, S * 8 * sizeof(double)));
+        CU(cudaMalloc(&p->rds_dec_state, S * DY4_RDS_STATE_INTS * sizeof(int)));
+        CU(cudaMalloc(&p->rds_counts, S * 4 * sizeof(int)));
+    }
     CU(cudaMalloc(&p->iq_tail, S * DY4_IQ_TAIL));
     CU(cudaMalloc(&p->if_tail, 3 * S * DY4_IF_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->mix_tail, S * DY4_MIX_TAIL * sizeof(float)));
@@ -401,6 +555,10 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     for (auto& r : p->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : p->pool) cudaEventDestroy(e);
     cudaFree(p->d_rf_taps); cudaFree(p->d_taps_poly);
+    cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
+    cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
+    cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
+    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); }
     cudaFree(p->ws_nco0);
@@ -476,7 +634,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
         const int wn = std::min(window, n_blocks - w0);
         int rc = ensure_workspace(p, wn);
         if (rc) return rc;
-        const auto plan = plan_subchunks(wn, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+        const auto plan = plan_subchunks(wn, p->ws_blocks, p->stereo && !(p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)));
         const int nsub = (int)plan.size();
         while ((int)p->ev_up.size() < nsub) {
             cudaEvent_t a, d;
@@ -524,6 +682,57 @@ extern "C" int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pil
     if (d_nco) *d_nco = p->ws[p->last_set].nco;
     if (stride) *stride = p->ws_stride;
     if (n_if) *n_if = p->last_n_if;
+    return DY4_OK;
+}
+
+extern "C" int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d_rrc_q, size_t row_stride, int* n_samples, void* stream)
+{
+    if (!p || !(p->flags & DY4_FLAG_RDS) || !n_samples) { dy4_set_error("dy4_pipeline_rds_read: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }
+    CU(cudaSetDevice(p->device));
+    *n_samples = p->rds_n_out;
+    if (p->rds_n_out <= 0) return DY4_OK;
+    if (row_stride < (size_t)p->rds_n_out) { dy4_set_error("dy4_pipeline_rds_read: row stride smaller than the sample count"); return DY4_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_rrc_i) CU(cudaMemcpy2DAsync(d_rrc_i, row_stride * sizeof(float), p->rds_out, 2 * p->rds_cap * sizeof(float),
+                                      (size_t)p->rds_n_out * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+    if (d_rrc_q) CU(cudaMemcpy2DAsync(d_rrc_q, row_stride * sizeof(float), p->rds_out + p->rds_cap, 2 * p->rds_cap * sizeof(float),
+                                      (size_t)p->rds_n_out * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+    return DY4_OK;
+}
+
+extern "C" int dy4_pipeline_rds_bounds(dy4_pipeline_t* p, int* max_symbols, int* max_bits, int* max_events)
+{
+    if (!p || !(p->flags & DY4_FLAG_RDS)) { dy4_set_error("dy4_pipeline_rds_bounds: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }
+    const long long ns = p->rds_blocks_since_drain * (DY4_RDS_BLOCK / 16);
+    if (max_symbols) *max_symbols = (int)ns;
+    if (max_bits) *max_bits = (int)((ns + 1) / 2 + 1);
+    if (max_events) *max_events = (int)((ns + 1) / 2 + 1);
+    return DY4_OK;
+}
+
+extern "C" int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size_t sym_stride, int8_t* h_bits, size_t bits_stride,
+                                      int32_t* h_events, size_t ev_stride, int32_t* h_counts)
+{
+    if (!p || !(p->flags & DY4_FLAG_RDS) || !h_counts) { dy4_set_error("dy4_pipeline_rds_drain: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->s_rds));
+    const size_t S = (size_t)p->n_streams;
+    int ms, mb, me;
+    dy4_pipeline_rds_bounds(p, &ms, &mb, &me);
+    if ((h_symbols && sym_stride < (size_t)ms) || (h_bits && bits_stride < (size_t)mb) || (h_events && ev_stride < (size_t)me)) {
+        dy4_set_error("dy4_pipeline_rds_drain: row strides smaller than dy4_pipeline_rds_bounds");
+        return DY4_ERR_ARG;
+    }
+    std::vector<int> c(S * 4);
+    CU(cudaMemcpy(c.data(), p->rds_counts, c.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t s = 0; s < S; s++) for (int j = 0; j < 3; j++) h_counts[s * 3 + j] = c[s * 4 + j];
+    if (p->rds_blocks_since_drain > 0) {
+        if (h_symbols) CU(cudaMemcpy2D(h_symbols, sym_stride, p->rds_sym, p->rds_sym_cap, (size_t)ms, S, cudaMemcpyDeviceToHost));
+        if (h_bits) CU(cudaMemcpy2D(h_bits, bits_stride, p->rds_bits, p->rds_bits_cap, std::min((size_t)mb, p->rds_bits_cap), S, cudaMemcpyDeviceToHost));
+        if (h_events) CU(cudaMemcpy2D(h_events, ev_stride * 16, p->rds_events, p->rds_ev_cap * 16, std::min((size_t)me, p->rds_ev_cap) * 16, S, cudaMemcpyDeviceToHost));
+    }
+    CU(cudaMemset(p->rds_counts, 0, S * 4 * sizeof(int)));
+    p->rds_blocks_since_drain = 0;
     return DY4_OK;
 }
 

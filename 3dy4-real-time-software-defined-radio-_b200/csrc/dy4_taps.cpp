@@ -82,3 +82,46 @@ extern "C" int dy4_mode_params(int mode, dy4_mode_params_t* m)
     m->audio_per_block = blocks_of * m->audio_upsample;
     return DY4_OK;
 }
+
+
+// ---- RDS path taps: the Python model's (model/fmMonoBlock.py:488-514, model/fmRRC.py:13-49), in double --------------
+// scipy.signal.firwin(numtaps, [lo, hi] or cutoff, window='hann'): ideal band response (difference of sincs) times a
+// symmetric Hann (window 0) or Hamming (window 1, scipy's default) window, scaled to unit gain at the band centre (band-pass) or at DC (low-pass).  Frequencies are
+// normalised to Nyquist (1.0 = Fs/2), as firwin takes them.  lo <= 0 means low-pass with cutoff hi.
+extern "C" int dy4_firwin(int num_taps, double lo, double hi, int window, double* h)
+{
+    if (!h || num_taps < 2 || hi <= 0.0 || hi >= 1.0 || lo >= hi || window < 0 || window > 1) return DY4_ERR_ARG;
+    const bool lowpass = lo <= 0.0;
+    const double left = lowpass ? 0.0 : lo, right = hi;
+    const double alpha = 0.5 * (num_taps - 1);
+    auto sinc = [](double x) { return x == 0.0 ? 1.0 : std::sin(kPi * x) / (kPi * x); };
+    for (int i = 0; i < num_taps; i++) {
+        const double mm = i - alpha;
+        double v = right * sinc(right * mm) - left * sinc(left * mm);
+        const double cw = std::cos(2.0 * kPi * i / (num_taps - 1));
+        v *= window == 0 ? 0.5 - 0.5 * cw : 0.54 - 0.46 * cw;           // scipy 'hann' / 'hamming' (symmetric)
+        h[i] = v;
+    }
+    const double scale_frequency = lowpass ? 0.0 : 0.5 * (left + right);
+    double sum = 0.0;
+    for (int i = 0; i < num_taps; i++) sum += h[i] * std::cos(kPi * (i - alpha) * scale_frequency);
+    for (int i = 0; i < num_taps; i++) h[i] /= sum;
+    return DY4_OK;
+}
+
+// model/fmRRC.py: root-raised-cosine, beta 0.90, T = 1/2375 s, centred on tap N/2 (float division)
+extern "C" int dy4_rrc_taps(double Fs, int num_taps, double* h)
+{
+    if (!h || num_taps < 1 || Fs <= 0) return DY4_ERR_ARG;
+    const double T = 1 / 2375.0, beta = 0.90;
+    for (int k = 0; k < num_taps; k++) {
+        const double t = (k - num_taps / 2.0) / Fs;
+        if (t == 0.0) h[k] = 1.0 + beta * ((4 / kPi) - 1);
+        else if (t == -T / (4 * beta) || t == T / (4 * beta))
+            h[k] = (beta / std::sqrt(2.0)) * (((1 + 2 / kPi) * std::sin(kPi / (4 * beta))) + ((1 - 2 / kPi) * std::cos(kPi / (4 * beta))));
+        else
+            h[k] = (std::sin(kPi * t * (1 - beta) / T) + 4 * beta * (t / T) * std::cos(kPi * t * (1 + beta) / T)) /
+                   (kPi * t * (1 - (4 * beta * t / T) * (4 * beta * t / T)) / T);
+    }
+    return DY4_OK;
+}

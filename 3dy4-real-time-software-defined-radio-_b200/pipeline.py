@@ -13,6 +13,7 @@ from .modes import mode_params
 
 FLAG_EXACT_AUDIO = 1
 FLAG_DEBUG_ROWS = 2
+FLAG_RDS = 4
 KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails")
 
 
@@ -22,13 +23,13 @@ def launch_count():
 
 
 class Pipeline:
-    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False, debug_rows=False):
+    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False, debug_rows=False, rds=False):
         self.mode, self.stereo, self.n_streams, self.device = int(mode), bool(stereo), int(n_streams), int(device)
         self.params = mode_params(mode)
         self.channels = 2 if stereo else 1
         self._h = C.c_void_p()
         check(lib.dy4_pipeline_create(self.mode, int(self.stereo), self.n_streams, self.device,
-                                      (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0),
+                                      (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0) | (FLAG_RDS if rds else 0),
                                       C.byref(self._h)), "dy4_pipeline_create")
 
     def close(self):
@@ -56,6 +57,7 @@ class Pipeline:
         if n_blocks is None:
             n_blocks = iq.shape[1] // p.block_size
         dev = iq.device
+        self._last_blocks = int(n_blocks)
         out = dict(out or {})
         na = n_blocks * p.audio_per_block * self.channels
         if "pcm" in want and "pcm" not in out:
@@ -94,6 +96,35 @@ class Pipeline:
         check(lib.dy4_pipeline_process_host(self._h, C.c_void_p(a.ctypes.data), row_stride, int(n_blocks),
                                             hp("pcm"), hp("audio"), int(chunk_blocks)), "dy4_pipeline_process_host")
         return out
+
+    def rds_read(self, stream=None):
+        """(rrc_i, rrc_q): the RDS baseband produced by the last process call, torch float32 [n_streams, n] each."""
+        import torch
+        dev = "cuda:%d" % self.device
+        cap = 16 + (self._last_blocks * self.params.if_per_block * 19 + 119) // 120
+        i_t = torch.empty((self.n_streams, cap), dtype=torch.float32, device=dev)
+        q_t = torch.empty((self.n_streams, cap), dtype=torch.float32, device=dev)
+        n = C.c_int()
+        if stream is None:
+            stream = torch.cuda.current_stream(i_t.device)
+        check(lib.dy4_pipeline_rds_read(self._h, C.c_void_p(i_t.data_ptr()), C.c_void_p(q_t.data_ptr()), cap, C.byref(n),
+                                        C.c_void_p(stream.cuda_stream)), "dy4_pipeline_rds_read")
+        return i_t[:, :n.value], q_t[:, :n.value]
+
+    def rds_drain(self):
+        """Everything the RDS back half decoded since the last drain: per stream, dict(symbols, bits, events) of numpy
+        arrays (events: rows of [block type 0..4 = A,B,C,C',D, bit position, false-positive flag, 16-bit word])."""
+        import numpy as np
+        ms, mb, me = C.c_int(), C.c_int(), C.c_int()
+        check(lib.dy4_pipeline_rds_bounds(self._h, C.byref(ms), C.byref(mb), C.byref(me)), "dy4_pipeline_rds_bounds")
+        S = self.n_streams
+        sym = np.zeros((S, max(ms.value, 1)), np.int8)
+        bits = np.zeros((S, max(mb.value, 1)), np.int8)
+        ev = np.zeros((S, max(me.value, 1), 4), np.int32)
+        cnt = np.zeros((S, 3), np.int32)
+        check(lib.dy4_pipeline_rds_drain(self._h, C.c_void_p(sym.ctypes.data), sym.shape[1], C.c_void_p(bits.ctypes.data), bits.shape[1],
+                                         C.c_void_p(ev.ctypes.data), ev.shape[1], C.c_void_p(cnt.ctypes.data)), "dy4_pipeline_rds_drain")
+        return [dict(symbols=sym[s, :cnt[s, 0]].copy(), bits=bits[s, :cnt[s, 1]].copy(), events=ev[s, :cnt[s, 2]].copy()) for s in range(S)]
 
     # ---- diagnostics ----------------------------------------------------------------------------
     def debug_pilot_nco(self):

@@ -4,7 +4,8 @@ Recipe of SURVEY.md §8(d): per stream s with base seed S, rng = PCG64(S+s);
 left/right tones in [300, 5000] Hz with amplitudes in [0.2, 0.5]; multiplex
 m = 0.45(L+R) + 0.1 sin(wp t + phi) + 0.45 (L-R) sin(2(wp t + phi)), wp = 2 pi 19 kHz;
 FM with 75 kHz deviation; additive N(0, 0.01^2) noise on I and Q;
-u8 = clip(round(100 x + 128), 0, 255).  The format is what the reference reads
+u8 = clip(round(100 x + 128), 0, 255).  With rds=True a 57 kHz sub-carrier (3x the pilot, amplitude 0.05) carries
+valid RDS groups: differentially encoded, biphase (Manchester) symbols at 2375 symbols/s.  The format is what the reference reads
 on stdin (rtl_sdr output, src/iofunc.cpp:113-120).
 
 Not on the hot path: this only feeds tests and the benchmark.
@@ -21,6 +22,38 @@ def stream_params(seed):
                 phi=rng.uniform(0, 2 * np.pi), noise_seed=int(rng.integers(0, 2**31)))
 
 
+RDS_OFFSET_WORDS = {"A": 0x0FC, "B": 0x198, "C": 0x168, "Cp": 0x350, "D": 0x1B4}   # IEC 62106 annex A
+RDS_POLY = 0x5B9                                                                     # x^10+x^8+x^7+x^5+x^4+x^3+1
+
+
+def rds_block(info16, offset):
+    """26-bit RDS block, first transmitted bit first: 16 information bits, then the 10-bit checkword
+    (remainder of info * x^10 by the generator polynomial, plus the offset word)."""
+    reg = info16 << 10
+    for b in range(25, 9, -1):
+        if reg & (1 << b):
+            reg ^= RDS_POLY << (b - 10)
+    word = (info16 << 10) | ((reg & 0x3FF) ^ RDS_OFFSET_WORDS[offset])
+    return [(word >> (25 - i)) & 1 for i in range(26)]
+
+
+def rds_group_bits(n_bits, seed):
+    """Source bits of whole RDS groups (blocks A, B, C, D; random information words, one PI code per stream)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pi_code = int(rng.integers(0, 1 << 16))
+    out = []
+    while len(out) < n_bits:
+        out += rds_block(pi_code, "A")
+        for off in ("B", "C", "D"):
+            out += rds_block(int(rng.integers(0, 1 << 16)), off)
+    return np.array(out[:n_bits], np.int64)
+
+
+def rds_bitstream(n_bits, seed):
+    """What modulates the 57 kHz sub-carrier: the group bits, differentially encoded (0/1)."""
+    return np.cumsum(rds_group_bits(n_bits, seed)) % 2
+
+
 def make_stream(mode, n_pairs, seed, rds=False):
     """One stream: uint8[2*n_pairs], interleaved I0 Q0 I1 Q1 ..."""
     fs = RF_FS[mode]
@@ -31,9 +64,8 @@ def make_stream(mode, n_pairs, seed, rds=False):
     wp = 2 * np.pi * 19e3 * t + p["phi"]
     m = 0.45 * (L + R) + 0.1 * np.sin(wp) + 0.45 * (L - R) * np.sin(2 * wp)
     if rds:
-        rng_b = np.random.Generator(np.random.PCG64(seed + 7919))
         nbits = int(np.ceil(t[-1] * 1187.5)) + 2
-        bits = rng_b.integers(0, 2, nbits) * 2 - 1
+        bits = rds_bitstream(nbits, seed + 7919) * 2 - 1
         sym = np.floor(t * 2375.0).astype(np.int64)          # Manchester: two half-symbols per bit
         d = bits[sym // 2] * np.where(sym % 2 == 0, 1.0, -1.0)
         m = m + 0.05 * d * np.cos(3 * wp)

@@ -64,6 +64,13 @@ int dy4_lpf_taps(float Fs, float Fc, unsigned short num_taps, int up_factor, flo
 /* filter.h:27 impulseResponseBPF(Fs, Fb, Fe, num_taps, h, upFactor) */
 int dy4_bpf_taps(float Fs, float Fb, float Fe, unsigned short num_taps, int up_factor, float* h);
 
+/* RDS path (reference: Python model only): scipy.signal.firwin(num_taps, [lo,hi], window=..., pass_zero=False) —
+ * lo <= 0 gives the low-pass firwin(num_taps, hi, window=...); window 0 = 'hann', 1 = 'hamming' (scipy's default);
+ * frequencies normalised to Nyquist — and model/fmRRC.py:13 impulseResponseRootRaisedCosine(Fs, N_taps).
+ * Double precision, as the model. */
+int dy4_firwin(int num_taps, double lo, double hi, int window, double* h);
+int dy4_rrc_taps(double Fs, int num_taps, double* h);
+
 /* ---- compatibility tier: host pointers, one stream ----------------------- */
 /* iofunc.cpp:117-119: out[k] = (raw[k]-128)/128 */
 int dy4_iq_to_float(const uint8_t* raw, size_t n, float* out);
@@ -102,6 +109,12 @@ typedef struct dy4_pipeline dy4_pipeline_t;
 #define DY4_FLAG_DEBUG_ROWS 2u    /* keep each process call in ONE sub-chunk so that dy4_pipeline_debug_buffers() returns
                                      whole pilot / NCO rows (diagnostics; disables the PLL/FIR overlap) */
 
+#define DY4_FLAG_RDS 4u           /* mode 0 stereo only: also run the RDS filtering front end of the Python model
+                                     (model/fmMonoBlock.py:673-691): 54-60 kHz band-pass, squaring, 113.5-114.5 kHz
+                                     band-pass, 114 kHz PLL (ncoScale 0.5, bandwidth 0.001), 50-sample delay, I/Q mix,
+                                     19/120 resampler (1919 taps) and 101-tap RRC -> 38 kS/s.  Read the result of the
+                                     last process call with dy4_pipeline_rds_read. */
+
 /* Create a receiver for `n_streams` independent streams in `mode` (0..3), mono (stereo=0)
  * or stereo (stereo=1), on CUDA device `device`.  All carried state starts as in
  * project.cpp:240-255 (zero history, PLL at feedbackI=1, nco_state=1). */
@@ -136,6 +149,25 @@ int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stri
  */
 int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                               int16_t* h_pcm, float* h_audio, int chunk_blocks);
+
+/* RRC-filtered RDS baseband (in-phase and quadrature, 38 kS/s) produced by the LAST process call: *n_samples of
+ * them per stream (about 19/120 of the call's IF samples; the exact count follows the absolute sample index), copied
+ * to DEVICE rows d_rrc_i / d_rrc_q (either may be NULL) of `row_stride` floats, asynchronously on `stream`. */
+int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d_rrc_q, size_t row_stride, int* n_samples, void* stream);
+
+/* RDS back half (reference: the Python model only — model/fmSupportLib.py:209-247 manchesterEncoded, model/fmMonoBlock.py
+ * :78-122 find_pattern / decode, :157-284 get_window / frame_sync_receiver, glued as in :699-730): every process call
+ * appends its in-phase RRC samples to a per-stream accumulator; each whole MODEL block of 3 040 samples (190 symbols) is
+ * decoded on the device with the model's block-to-block state.  Blocks 0-4 only recover symbol timing, blocks 5-9 pick
+ * the Manchester pairing, from block 10 on bits are decoded and the 26-bit syndrome frame synchroniser runs.
+ * dy4_pipeline_rds_bounds: upper bounds (per stream) of what has accumulated since the last drain.
+ * dy4_pipeline_rds_drain: waits for the RDS work queued so far, copies per stream the Manchester symbols (0/1, one
+ * int8 each), the decoded bits (0/1, int8) and the frame-sync events (4 x int32: block type A,B,C,C',D = 0..4, bit
+ * position, false-positive flag, the 16-bit information word) to HOST rows of the given strides (in elements /
+ * events; any pointer may be NULL), h_counts[n_streams][3] = symbols, bits, events; then empties the device rows. */
+int dy4_pipeline_rds_bounds(dy4_pipeline_t* p, int* max_symbols, int* max_bits, int* max_events);
+int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size_t sym_stride, int8_t* h_bits, size_t bits_stride,
+                           int32_t* h_events, size_t ev_stride, int32_t* h_counts);
 
 /* Diagnostics (valid after a stereo process call): device pointers to the
  * last sub-chunk's pilot and NCO rows, their stride in floats and length. */

@@ -164,3 +164,70 @@ def test_pll_locks_to_pilot(orc):
     coh = np.abs(np.mean(nco[tail] * np.exp(-2j * ph[tail])))
     assert coh > 0.49, coh                                   # 0.5 = perfectly coherent unit cosine
     assert np.abs(np.mean(nco[tail] * np.exp(-2j * 1.01 * ph[tail]))) < 0.1
+
+
+# ---------------------------------------------------------------- RDS path (reference: the Python model only)
+def _rds_golden_if(orc, dy4):
+    g = golden("rds_mode0.npz")
+    m = dy4.mode_params(0)
+    iq = dy4.synth.make_stream(0, int(g["n_blocks"]) * m.block_size // 2, int(g["seed"]), rds=True)
+    assert sha(iq) == str(g["iq_sha256"])
+    return g, orc.pipeline(0, 1, iq, want=("if",))["if"]
+
+
+def test_rds_oracle_matches_model_golden(orc, dy4):
+    """oracle/rds.py (numpy restatement) against outputs of the model's own functions (make_golden_rds.py)."""
+    from oracle import rds
+    g, fm = _rds_golden_if(orc, dy4)
+    r = rds.rds_front(fm)
+    n = len(g["rrc_i64"])
+    assert rel_l2(r["rrc_i"][:n], g["rrc_i64"]) <= 1e-9 and rel_l2(r["rrc_q"][:n], g["rrc_q64"]) <= 1e-9
+    assert rel_l2(r["rrc_i"], g["rrc_i"]) <= 2e-7 and rel_l2(r["rrc_q"], g["rrc_q"]) <= 2e-7      # fixture stored as float32
+    for k in ("rds_f", "carrier", "nco_i", "nco_q"):
+        assert rel_l2(r[k][::8], g[k + "_8"]) <= 2e-7
+    be = rds.rds_back(r["rrc_i"], r["rrc_q"])
+    assert [len(x) for x in be.symbols] == list(g["symbol_counts"])
+    assert np.array_equal(np.concatenate([np.array(x, np.int8) for x in be.symbols]), g["symbols"])
+    assert np.array_equal(np.array(be.bits, np.int8), g["bits"])
+    assert np.array_equal(np.array(be.events, np.int32).reshape(-1, 4), g["events"])
+    assert [be.errors1, be.errors2] == list(g["errors"])
+    ev = g["events"]
+    assert len(ev) >= 16 and set(ev[:, 0]) >= {0, 1, 2, 4} and not ev[:, 2].any()      # the fixture does exercise the frame sync
+
+
+def test_rds_taps_match_scipy_and_the_library(dy4):
+    """firwin / RRC designs: oracle restatement == scipy (what the model calls) == the library's C implementation."""
+    import ctypes as C
+    from scipy import signal
+    from oracle import rds
+    t = rds.model_taps()
+    nyq = 120e3
+    ref = dict(rds=signal.firwin(101, [54e3 / nyq, 60e3 / nyq], window="hann", pass_zero=False),
+               carrier=signal.firwin(101, [113.5e3 / nyq, 114.5e3 / nyq], window="hann", pass_zero=False),
+               lpf=signal.firwin(1919, 3e3 / (240e3 * 19 / 2)) * 19)
+    for k, v in ref.items():
+        assert np.abs(t[k] - v).max() <= 1e-15
+    lib = dy4._lib.lib
+    h = np.empty(101)
+    assert lib.dy4_firwin(101, 54e3 / nyq, 60e3 / nyq, 0, C.c_void_p(h.ctypes.data)) == 0
+    assert np.abs(h - ref["rds"]).max() <= 1e-15
+    h = np.empty(1919)
+    assert lib.dy4_firwin(1919, 0.0, 3e3 / (240e3 * 19 / 2), 1, C.c_void_p(h.ctypes.data)) == 0
+    assert np.abs(h * 19 - ref["lpf"]).max() <= 1e-15
+    h = np.empty(101)
+    assert lib.dy4_rrc_taps(38000.0, 101, C.c_void_p(h.ctypes.data)) == 0
+    assert np.abs(h - t["rrc"]).max() <= 1e-15
+    assert lib.dy4_firwin(101, 0.5, 0.4, 0, C.c_void_p(h.ctypes.data)) != 0          # band edges out of order
+
+
+def test_synthetic_rds_groups_are_valid(dy4):
+    """synth's RDS groups carry correct checkwords: every block's syndrome is its offset word's (model's matrix)."""
+    from oracle import rds
+    bits = dy4.synth.rds_group_bits(104 * 5, 1234)
+    for g in range(5):
+        for j, off in enumerate(("A", "B", "C", "D")):
+            blk = [int(b) for b in bits[104 * g + 26 * j:104 * g + 26 * (j + 1)]]
+            syn = tuple(sum(blk[i] for i in row) % 2 for row in rds.PARITY_ROWS)
+            assert rds.SYNDROMES.get(syn) == off
+    d = dy4.synth.rds_bitstream(300, 1234)
+    assert np.array_equal(np.diff(d) % 2, bits[1:300])                                 # differential encoding
