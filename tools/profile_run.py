@@ -5,7 +5,7 @@ import torch, dy4_b200
 S = int(os.environ.get("S", 256)); NB = int(os.environ.get("NB", 4)); REP = int(os.environ.get("REP", 2)); MODE = int(os.environ.get("MODE", 0))
 m = dy4_b200.mode_params(MODE)
 iq = dy4_b200.synth.make_batch_torch(MODE, S, NB * m.block_size // 2, base_seed=65, device="cuda")
-p = dy4_b200.Pipeline(MODE, 1, S)
+p = dy4_b200.Pipeline(MODE, 1, S, debug_rows=bool(int(os.environ.get("WHOLE", 0))))   # WHOLE=1: one sub-chunk per call (whole-job launches)
 for _ in range(REP):
     out = p.process(iq, want=("pcm",))
 torch.cuda.synchronize()

@@ -116,6 +116,75 @@ __global__ void k_fmul2_fadd2(float* out, float a, float b) {
     ((unsigned long long*)out)[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the bit-exact MAC of the FIR kernels: p = RN(x*h) as FFMA2(x, h, -0) with -0 in a vector register, acc = RN(acc + p).
+// x is refreshed from another accumulator chain every iteration so the products cannot be hoisted out of the loop.
+template <int MODE>   // 0: taps in registers, 1: taps as immediates, 2: FADD2 only
+__global__ void k_exact2(float* out, float a, float b) {
+    unsigned long long acc[NCH], x[NCH];
+    __shared__ unsigned long long snz[256];
+    snz[threadIdx.x] = 0x8000000080000000ull;
+    unsigned long long nz = *(volatile unsigned long long*)&snz[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = pk(threadIdx.x + i, i); x[i] = pk(a * i, threadIdx.x); }
+    unsigned long long h0 = pk(a, a), h1 = pk(b, b);
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int i = 0; i < NCH; i++) {
+            if (MODE == 0) acc[i] = fadd2(acc[i], ffma2(x[i], h0, nz));
+            else if (MODE == 2) acc[i] = fadd2(acc[i], x[i]);
+            else acc[i] = fadd2(acc[i], ffma2(x[i], pk(0.00123f + 0.001f * i, 0.00123f + 0.001f * i), nz));
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; i++) {
+            if (MODE == 0) acc[i] = fadd2(acc[i], ffma2(x[(i + 1) % NCH], h1, nz));
+            else if (MODE == 2) acc[i] = fadd2(acc[i], x[(i + 1) % NCH]);
+            else acc[i] = fadd2(acc[i], ffma2(x[(i + 1) % NCH], pk(-0.0456f + 0.002f * i, -0.0456f + 0.002f * i), nz));
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; i++) x[i] = acc[(i + 5) % NCH];          // register renaming only after unrolling by the compiler
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s ^= acc[i];
+    ((unsigned long long*)out)[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Where do the adds of the exact MAC go?  ncu shows FFMA2/FADD2 on the fmaheavy pipe only; scalar FADD can also use fmalite.
+// SCALAR_OF_16 of the 16 chains per half-iteration do their add as two scalar FADDs (I and Q apart), the rest as one FADD2.
+template <int SCALAR_OF_16>
+__global__ void k_exact_mix(float* out, float a, float b) {
+    unsigned long long acc[NCH], x[NCH];
+    __shared__ unsigned long long snz[256];
+    snz[threadIdx.x] = 0x8000000080000000ull;
+    unsigned long long nz = *(volatile unsigned long long*)&snz[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) { acc[i] = pk(threadIdx.x + i, i); x[i] = pk(a * i, threadIdx.x); }
+    for (int it = 0; it < ITER / 2; it++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                const float t = (h ? -0.0456f : 0.00123f) + 0.001f * i;
+                const unsigned long long p = ffma2(x[(i + h) % NCH], pk(t, t), nz);
+                if (i < SCALAR_OF_16) {
+                    float al, ah, pl, ph;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(al), "=f"(ah) : "l"(acc[i]));
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(pl), "=f"(ph) : "l"(p));
+                    acc[i] = pk(__fadd_rn(al, pl), __fadd_rn(ah, ph));
+                } else {
+                    acc[i] = fadd2(acc[i], p);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; i++) x[i] = acc[(i + 5) % NCH];
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s ^= acc[i];
+    ((unsigned long long*)out)[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_dfma(double* out, double a, double b) {
     double acc[NCH];
 #pragma unroll
@@ -184,6 +253,15 @@ int main() {
     run_tput("ffma2 packed", k_ffma2, buf, n, 4);          // one instr = 2 MAC
     run_tput("fmul2+fadd2", k_fmul2_fadd2, buf, n, 4);    // 2 instr = 2 MAC
     run_tput("dfma", k_dfma, (double*)buf, n / 4, 2);
+    // exact MAC pairs: one op = FFMA2 + FADD2 = 2 MACs = 4 flop (the FIR kernels' arithmetic); ceiling = half the FFMA2 rate
+    run_tput("exact2 reg taps", k_exact2<0>, buf, n, 4);
+    run_tput("exact2 imm taps", k_exact2<1>, buf, n, 4);
+    run_tput("fadd2 only", k_exact2<2>, buf, n, 2);
+    run_tput("exact mix 0/16", k_exact_mix<0>, buf, n, 4);
+    run_tput("exact mix 4/16", k_exact_mix<4>, buf, n, 4);
+    run_tput("exact mix 8/16", k_exact_mix<8>, buf, n, 4);
+    run_tput("exact mix 11/16", k_exact_mix<11>, buf, n, 4);
+    run_tput("exact mix 16/16", k_exact_mix<16>, buf, n, 4);
 
     long long* cyc; CK(cudaMallocManaged(&cyc, 8));
     const char* names[] = {"DFMA", "FFMA", "atan2(double)", "sincos small", "sincos large", "F2F+DFMA+F2F", "ddiv", "cos small", "cos large", "fdividef"};
