@@ -565,8 +565,10 @@ k_frontend_stream(const uint8_t* __restrict__ iq, long long row_stride, const ui
     float* orow = if_out + (long long)s * if_stride;
     const u64 neg_bias = pk2(-8388736.0f, -8388736.0f);
 
-    // 16-byte group `i` (0..4, ascending time) of the body that ends below output index M: samples D*M-40+8i .. +7
-    auto load_group = [&](int M, int i) -> uint4 {
+    // 16-byte group `i` (0..4, ascending time) of the body that ends below output index M: samples D*M-40+8i .. +7.
+    // Only the first segment of a stream ever reaches below the chunk (offsets < 0: carried tail, then don't-care);
+    // everywhere else the load is a plain pointer + immediate offset from a per-body base.
+    auto load_group_checked = [&](int M, int i) -> uint4 {
         const long long off = 2LL * D * M - 2 * BODY + 16 * i;
         if (off >= 0) return __ldg(reinterpret_cast<const uint4*>(row + off));
         if (off >= -DY4_IQ_TAIL) return __ldg(reinterpret_cast<const uint4*>(tail + DY4_IQ_TAIL + off));
@@ -584,9 +586,11 @@ k_frontend_stream(const uint8_t* __restrict__ iq, long long row_stride, const ui
     constexpr int PF = 3;
     uint4 q[PF + 1];
 #pragma unroll
-    for (int j = 0; j <= PF; j++) q[j] = load_group(m_hi, 4 - j);
+    for (int j = 0; j <= PF; j++) q[j] = load_group_checked(m_hi, 4 - j);
 
-    for (int M = m_hi; M + TOP >= m_lo; M -= NOUT) {
+    const uint4* base = reinterpret_cast<const uint4*>(row + 2LL * D * m_hi - 2 * BODY);   // group 0 of the current body
+    for (int M = m_hi; M + TOP >= m_lo; M -= NOUT, base -= 2 * BODY / 16) {
+        const bool plain = M >= 2 * NOUT;               // every group this body asks for lies inside the chunk
 #pragma unroll
         for (int gi = 4; gi >= 0; gi--) {
             const uint4 gv = q[0];
@@ -594,7 +598,8 @@ k_frontend_stream(const uint8_t* __restrict__ iq, long long row_stride, const ui
             for (int j = 0; j < PF; j++) q[j] = q[j + 1];
             {   // refill the far end of the queue: PF+1 groups below the current one (wrapping into the next body)
                 const int ahead = gi - (PF + 1);
-                q[PF] = ahead >= 0 ? load_group(M, ahead) : load_group(M - NOUT, ahead + 5);
+                if (plain) q[PF] = __ldg(base + ahead);
+                else q[PF] = ahead >= 0 ? load_group_checked(M, ahead) : load_group_checked(M - NOUT, ahead + 5);
             }
 #pragma unroll
             for (int l = 7; l >= 0; l--) {                  // samples of the group, newest first

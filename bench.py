@@ -34,9 +34,12 @@ BLOCKS_PER_STREAM = 47           # 47 x 21.33 ms = 1.003 s per stream
 METRIC = "aggregate_iq_msamples_per_s_stereo_fm"
 UNIT = "Msamples/s"
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45: SMs x lanes x 2 flop x max SM clock
-# DRAM traffic of k_frontend from the `ncu --set full` capture summarised in profiles/r1_ncu_frontend.md:
-# (209.88 + 28.41) MB for 256 streams x 8 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
-NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (209.879296e6 + 28.413440e6) / (256 * 8 * 51200)
+# Measured ceiling of the BIT-EXACT multiply-add (FFMA2(x,h,-0) then FADD2: two packed instructions on the fmaheavy pipe per
+# pair of MACs), tools/ubench.cu "exact2" on this pool's B200 (profiles/ubench_r1b.txt): 36.3 TFLOP/s = 0.49 of the FMA peak.
+EXACT_MAC_CEILING_TFLOPS = 36.3
+# DRAM traffic of k_frontend_stream from the `ncu --set full` capture summarised in profiles/r1_ncu_frontend_stream.md:
+# (1297.74 + 248.79) MB for 256 streams x 47 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
+NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (1297.743e6 + 248.788736e6) / (256 * 47 * 51200)
 
 
 def measured_peaks():
@@ -301,20 +304,25 @@ def run_gpu_arm(args):
     for k, v in (iso or {}).items():
         if v["launches"] and alg[k]["mac"]:
             avg = v["ms"] / v["launches"]
-            isolated[k] = {"avg_ms": round(avg, 4), "fp32_TFLOPs": round(2 * alg[k]["mac"] * pairs_per_step / (avg * 1e-3) / 1e12, 2),
-                           "frac_of_fma_peak": round(2 * alg[k]["mac"] * pairs_per_step / (avg * 1e-3) / 1e12 / FP32_PEAK_TFLOPS_NOMINAL, 4)}
+            tf = 2 * alg[k]["mac"] * pairs_per_step / (avg * 1e-3) / 1e12
+            isolated[k] = {"avg_ms": round(avg, 4), "fp32_TFLOPs": round(tf, 2), "frac_of_fma_peak": round(tf / FP32_PEAK_TFLOPS_NOMINAL, 4)}
+            if k in ("frontend", "twin_bpf"):        # the two bit-exact kernels
+                isolated[k]["frac_of_exact_ceiling"] = round(tf / EXACT_MAC_CEILING_TFLOPS, 4)
     roofline = {
-        "kernel": "k_frontend_tma (TMA-staged uint8 IQ -> 101-tap decimating FIR on I,Q -> FM discriminator)",
+        "kernel": "k_frontend_stream (packed uint8 IQ -> 101-tap decimating FIR on I,Q in transposed form -> FM discriminator)",
         "bound": "fp32", "achieved": fe["fp32_TFLOPs"], "peak": round(FP32_PEAK_TFLOPS_NOMINAL, 2), "unit": "TFLOP/s",
         "frac": round(fe["fp32_TFLOPs"] / FP32_PEAK_TFLOPS_NOMINAL, 4),
         "peak_source": "148 SMs x 128 FP32 lanes x 2 x 1.965 GHz; tools/ubench measures 71.6 TFLOP/s FFMA on this pool",
-        "note": "bit-exact (unfused multiply then add) costs 2 FP32 instructions per MAC: the issue-limited ceiling of this kernel is frac 0.5",
-        "issue_frac": round(2 * fe["fp32_TFLOPs"] / FP32_PEAK_TFLOPS_NOMINAL, 4),
+        "note": "bit-exact arithmetic (unfused multiply then add) costs two packed FP32 instructions per pair of MACs, both on the fmaheavy pipe: "
+                "the measured ceiling of that instruction pair is %.1f TFLOP/s (tools/ubench.cu exact2, profiles/ubench_r1b.txt), frac %.2f" % (
+                    EXACT_MAC_CEILING_TFLOPS, EXACT_MAC_CEILING_TFLOPS / FP32_PEAK_TFLOPS_NOMINAL),
+        "exact_mac_ceiling": EXACT_MAC_CEILING_TFLOPS,
+        "frac_of_exact_ceiling": round(fe["fp32_TFLOPs"] / EXACT_MAC_CEILING_TFLOPS, 4),
         "hbm": {"achieved": fe["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(fe["GBps"] / hbm_peak, 4), "peak_source": hbm_src},
         "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"],
         "algorithmic_bytes": int(alg["frontend"]["bytes"] * pairs_per_step),
         "traffic": int(NCU_FRONTEND_DRAM_BYTES_PER_PAIR * pairs_per_step),
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r1_ncu_frontend.md, scaled to this launch",
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r1_ncu_frontend_stream.md, scaled to this launch",
         "whole_job_launches": isolated,
         "whole_job_note": "same kernels, one launch per step over the whole batch, not overlapped with the PLL (second, untimed-for-value pass)",
     }

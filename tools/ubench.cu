@@ -222,6 +222,30 @@ __global__ void k_lat(double* out, long long* cyc, double seed, int n) {
     if (threadIdx.x == 0) *cyc = t1 - t0;
 }
 
+// issue interval of double-precision instructions for ONE warp (what the per-stream PLL sees: one warp per SM):
+// NCHAIN independent DFMA/DADD chains, so latency is hidden and the pipe's per-warp issue rate shows.
+template <int NCHAIN, int MIX>
+__global__ void k_dp_issue(double* out, long long* cyc, double seed, int n) {
+    double v[NCHAIN];
+#pragma unroll
+    for (int i = 0; i < NCHAIN; i++) v[i] = seed + i + threadIdx.x;
+    long long t0 = clock64();
+    for (int it = 0; it < n; it++) {
+#pragma unroll
+        for (int i = 0; i < NCHAIN; i++) {
+            if (MIX == 0) v[i] = fma(v[i], 1.0000001, 1e-9);
+            else if (MIX == 1) v[i] = __dadd_rn(v[i], 1e-9);
+            else v[i] = __dmul_rn(v[i], 1.0000001);
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCHAIN; i++) s += v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 template <typename K, typename T>
 void run_tput(const char* name, K kern, T* buf, double ops_per_thread, int flops_per_op) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
@@ -267,6 +291,9 @@ int main() {
     const char* names[] = {"DFMA", "FFMA", "atan2(double)", "sincos small", "sincos large", "F2F+DFMA+F2F", "ddiv", "cos small", "cos large", "fdividef"};
     int nrep = 2000;
 #define LAT(OP) { k_lat<OP><<<1, 32>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); k_lat<OP><<<1, 32>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); printf("lat %-16s %8.1f cycles/iter\n", names[OP], (double)*cyc / nrep); }
+#define DPI(NC, MIX, THREADS, NAME) { k_dp_issue<NC, MIX><<<1, THREADS>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); k_dp_issue<NC, MIX><<<1, THREADS>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); printf("dp issue %-28s %6.2f cycles per instruction per warp\n", NAME, (double)*cyc / nrep / NC); }
+    DPI(16, 0, 32, "DFMA 1 warp x16 chains") DPI(16, 1, 32, "DADD 1 warp x16 chains") DPI(16, 2, 32, "DMUL 1 warp x16 chains")
+    DPI(16, 0, 8, "DFMA 8 lanes x16 chains") DPI(16, 0, 64, "DFMA 2 warps (2 SMSPs)") DPI(16, 0, 160, "DFMA 5 warps (2 on SMSP0)") DPI(4, 0, 32, "DFMA 1 warp x4 chains")
     LAT(0) LAT(1) LAT(2) LAT(3) LAT(4) LAT(5) LAT(6) LAT(7) LAT(8) LAT(9)
     return 0;
 }
