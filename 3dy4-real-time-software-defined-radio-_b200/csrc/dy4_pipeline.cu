@@ -59,14 +59,14 @@ struct dy4_pipeline {
     float *rds_f = nullptr, *rds_carrier = nullptr, *rds_nco_i = nullptr, *rds_nco_q = nullptr, *rds_lp = nullptr, *rds_out = nullptr;
     double *rds_theta = nullptr, *rds_pll_state = nullptr;
     float *rds_tail = nullptr, *rds_mix_tail = nullptr, *rds_lp_tail = nullptr, *d_rds_poly = nullptr, *d_rds_rrc = nullptr;
-    size_t rds_cap = 0; int rds_n_out = 0; long long if_abs = 0;
+    size_t rds_cap = 0, rds_out_cap = 0; int rds_n_out = 0, rds_call_n = 0; long long if_abs = 0;   // rds_out: the whole call's RRC rows; rds_call_n of them so far
     // RDS back half: accumulation rows of in-phase RRC samples, decoder state, growing output rows
     float* rds_acc = nullptr; size_t rds_acc_cap = 0; int rds_left = 0, rds_consumed = 0;
     int *rds_dec_state = nullptr, *rds_counts = nullptr, *rds_events = nullptr;
     int8_t *rds_sym = nullptr, *rds_bits = nullptr;
     size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0;
     long long rds_blocks_since_drain = 0;
-    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr;
+    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
     // host-facing staging
@@ -79,8 +79,8 @@ struct dy4_pipeline {
     bool prof = false;
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
-    double acc_ms[DY4_NUM_KERNELS] = {0, 0, 0, 0, 0};
-    long long acc_n[DY4_NUM_KERNELS] = {0, 0, 0, 0, 0};
+    double acc_ms[DY4_NUM_KERNELS] = {};
+    long long acc_n[DY4_NUM_KERNELS] = {};
 };
 
 namespace {
@@ -137,7 +137,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     std::vector<float> h(S * 8, 0.0f);
     for (size_t s = 0; s < S; s++) { h[s * 8 + 0] = 1.0f; h[s * 8 + 5] = 1.0f; }   // PLLState, project.cpp:46-53
     CU(cudaMemcpyAsync(p->pll_state, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    p->if_abs = 0; p->rds_n_out = 0;
+    p->if_abs = 0; p->rds_n_out = 0; p->rds_call_n = 0;
     if (p->flags & DY4_FLAG_RDS) {
         CU(cudaMemsetAsync(p->rds_tail, 0, S * DY4_IF_TAIL * sizeof(float), st));
         CU(cudaMemsetAsync(p->rds_mix_tail, 0, S * 2 * DY4_MIX_TAIL * sizeof(float), st));
@@ -166,7 +166,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 16 : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
-    const bool whole = (p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)) != 0;    // RDS branch: one sub-chunk per call (round 1)
+    const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
     int nsub = 3;                                      // largest sub-chunk = a third of the job (see plan_subchunks)
     if (const char* e = std::getenv("DY4_SUBCHUNKS")) nsub = std::max(1, atoi(e));
     if (p->stereo && !whole && n_blocks >= 8) blocks = std::min(blocks, (n_blocks + nsub - 1) / nsub);
@@ -205,16 +205,17 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     }
     if (p->flags & DY4_FLAG_RDS) {
         cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta);
-        cudaFree(p->rds_lp); cudaFree(p->rds_out);
+        cudaFree(p->rds_lp);
         CU(cudaMalloc(&p->rds_f, bytes)); CU(cudaMalloc(&p->rds_carrier, bytes));
         CU(cudaMalloc(&p->rds_nco_i, bytes)); CU(cudaMalloc(&p->rds_nco_q, bytes)); CU(cudaMalloc(&p->rds_theta, 2 * bytes));
         p->rds_cap = (p->ws_stride * 19 + 119) / 120 + 4;
         CU(cudaMalloc(&p->rds_lp, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
-        CU(cudaMalloc(&p->rds_out, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
         if (!p->s_rds) {
             CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_rds_set[0], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_rds_set[1], cudaEventDisableTiming));
         }
     }
     p->ws_blocks = blocks;
@@ -291,7 +292,7 @@ int run_rds_decode(dy4_pipeline* p, cudaStream_t st)
     const int n_new = p->rds_n_out;
     int rc;
     if ((rc = grow_rows(p->rds_acc, p->rds_acc_cap, (size_t)p->rds_left + p->rds_consumed + n_new + 64, S, 1, st))) return rc;
-    CU(dy4_launch_rds_append(p->rds_out, 2LL * (long long)p->rds_cap, n_new, p->rds_acc, (long long)p->rds_acc_cap, p->rds_consumed, p->rds_left,
+    CU(dy4_launch_rds_append(p->rds_out + (p->rds_call_n - n_new), 2LL * (long long)p->rds_out_cap, n_new, p->rds_acc, (long long)p->rds_acc_cap, p->rds_consumed, p->rds_left,
                              p->n_streams, st));
     const int total = p->rds_left + n_new;
     const int nblk = total / DY4_RDS_BLOCK;
@@ -324,26 +325,31 @@ int run_rds(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
     ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
     ba.pilot = p->rds_f; ba.sband = nullptr; ba.out_stride = (long long)p->ws_stride;
     ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = 4; ba.variant = 1; ba.neg_zero2 = kNegZero2;
-    CU(dy4_launch_bpf(ba, st));                                   // RDS channel extraction, 54-60 kHz
-    ba.if_in = p->rds_f; ba.if_tail = p->rds_tail; ba.pilot = p->rds_carrier; ba.mode = 5; ba.variant = 2;
-    CU(dy4_launch_bpf(ba, st));                                   // squaring + 113.5-114.5 kHz carrier extraction
+    {
+        Timer t(p, DY4_K_RDS_BPF, st);
+        CU(dy4_launch_bpf(ba, st));                               // RDS channel extraction, 54-60 kHz
+        ba.if_in = p->rds_f; ba.if_tail = p->rds_tail; ba.pilot = p->rds_carrier; ba.mode = 5; ba.variant = 2;
+        CU(dy4_launch_bpf(ba, st));                               // squaring + 113.5-114.5 kHz carrier extraction
+    }
     Dy4RdsArgs ra{};
     ra.rds_f = p->rds_f; ra.stride = (long long)p->ws_stride; ra.rds_tail = p->rds_tail; ra.carrier = p->rds_carrier;
     ra.theta = p->rds_theta; ra.wide_stride = (long long)p->ws_stride; ra.nco_i = p->rds_nco_i; ra.nco_q = p->rds_nco_q;
     ra.pll_state = p->rds_pll_state; ra.mix_tail = p->rds_mix_tail; ra.lp = p->rds_lp; ra.lp_stride = (long long)p->rds_cap;
-    ra.lp_tail = p->rds_lp_tail; ra.out_i = p->rds_out; ra.out_q = p->rds_out + p->rds_cap; ra.out_stride = 2LL * (long long)p->rds_cap;
+    ra.lp_tail = p->rds_lp_tail; ra.out_i = p->rds_out + p->rds_call_n; ra.out_q = p->rds_out + p->rds_out_cap + p->rds_call_n; ra.out_stride = 2LL * (long long)p->rds_out_cap;
     ra.taps_poly = p->d_rds_poly; ra.up_pad = 20; ra.taps_rrc = p->d_rds_rrc; ra.n_if = n_if; ra.n_streams = p->n_streams;
     ra.if_abs = p->if_abs; ra.up = 19; ra.down = 120;
     ra.m_first = (19 * p->if_abs + 119) / 120;
     ra.n_out = (int)((19 * (p->if_abs + n_if) + 119) / 120 - ra.m_first);
     const double bw = 0.001;                                      // fmMonoBlock.py:444-447
     ra.w = 2 * 3.141592653589793 * (114e3 / 240e3); ra.Kp = bw * 2.666; ra.Ki = (bw * bw) * 3.555; ra.nco_scale = 0.5; ra.phase_adjust = 0.0;
-    CU(dy4_launch_rds_pll(ra, st));
+    { Timer t(p, DY4_K_RDS_PLL, st); CU(dy4_launch_rds_pll(ra, st)); }
+    Timer t_bb(p, DY4_K_RDS_BASEBAND, st);                        // until the end of this function: resampler, RRC, carry, decoding
     CU(dy4_launch_rds_resample(ra, st));
     Dy4TailArgs ta{};                                             // history of the band-pass output for the next call
     ta.if_in = p->rds_f; ta.if_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.if_tail = p->rds_tail; ta.n_streams = p->n_streams;
     CU(dy4_launch_tails(ta, st));
     p->rds_n_out = ra.n_out;
+    p->rds_call_n += ra.n_out;
     p->if_abs += n_if;
     return run_rds_decode(p, st);
 }
@@ -412,7 +418,17 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     const int ch = p->stereo ? 2 : 1;
     int rc = ensure_workspace(p, n_blocks);
     if (rc) return rc;
-    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)));
+    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+    if (p->flags & DY4_FLAG_RDS) {                     // RRC rows of the whole call (read back by dy4_pipeline_rds_read)
+        const size_t need = ((size_t)n_blocks * m.if_per_block * 19 + 119) / 120 + 8;
+        if (need > p->rds_out_cap) {
+            CU(cudaStreamSynchronize(p->s_rds));
+            cudaFree(p->rds_out); p->rds_out = nullptr;
+            CU(cudaMalloc(&p->rds_out, (size_t)p->n_streams * 2 * need * sizeof(float)));
+            p->rds_out_cap = need;
+        }
+        p->rds_call_n = 0;
+    }
     auto sub = [&](int b, int nb, long long seq) {
         SubChunk c;
         c.nb = nb;
@@ -449,11 +465,14 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         const int b = plan[i].first;
         const SubChunk c = sub(b, plan[i].second, p->seq);
         if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
+        // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
+        if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
             CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
             if ((rc = run_rds(p, c, p->s_rds))) return rc;
+            CU(cudaEventRecord(p->ev_rds_set[c.set], p->s_rds));
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
         CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
@@ -558,7 +577,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
     cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
     cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
-    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); }
+    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); }
     cudaFree(p->ws_nco0);
@@ -634,7 +653,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
         const int wn = std::min(window, n_blocks - w0);
         int rc = ensure_workspace(p, wn);
         if (rc) return rc;
-        const auto plan = plan_subchunks(wn, p->ws_blocks, p->stereo && !(p->flags & (DY4_FLAG_DEBUG_ROWS | DY4_FLAG_RDS)));
+        const auto plan = plan_subchunks(wn, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
         const int nsub = (int)plan.size();
         while ((int)p->ev_up.size() < nsub) {
             cudaEvent_t a, d;
@@ -689,14 +708,14 @@ extern "C" int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d
 {
     if (!p || !(p->flags & DY4_FLAG_RDS) || !n_samples) { dy4_set_error("dy4_pipeline_rds_read: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
-    *n_samples = p->rds_n_out;
-    if (p->rds_n_out <= 0) return DY4_OK;
-    if (row_stride < (size_t)p->rds_n_out) { dy4_set_error("dy4_pipeline_rds_read: row stride smaller than the sample count"); return DY4_ERR_ARG; }
+    *n_samples = p->rds_call_n;
+    if (p->rds_call_n <= 0) return DY4_OK;
+    if (row_stride < (size_t)p->rds_call_n) { dy4_set_error("dy4_pipeline_rds_read: row stride smaller than the sample count"); return DY4_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_rrc_i) CU(cudaMemcpy2DAsync(d_rrc_i, row_stride * sizeof(float), p->rds_out, 2 * p->rds_cap * sizeof(float),
-                                      (size_t)p->rds_n_out * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
-    if (d_rrc_q) CU(cudaMemcpy2DAsync(d_rrc_q, row_stride * sizeof(float), p->rds_out + p->rds_cap, 2 * p->rds_cap * sizeof(float),
-                                      (size_t)p->rds_n_out * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+    if (d_rrc_i) CU(cudaMemcpy2DAsync(d_rrc_i, row_stride * sizeof(float), p->rds_out, 2 * p->rds_out_cap * sizeof(float),
+                                      (size_t)p->rds_call_n * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+    if (d_rrc_q) CU(cudaMemcpy2DAsync(d_rrc_q, row_stride * sizeof(float), p->rds_out + p->rds_out_cap, 2 * p->rds_out_cap * sizeof(float),
+                                      (size_t)p->rds_call_n * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
     return DY4_OK;
 }
 

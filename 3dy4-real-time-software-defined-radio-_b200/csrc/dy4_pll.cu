@@ -103,7 +103,7 @@ __device__ __forceinline__ double pll_step_any(float x, float x_next, PllRegs& s
 }
 
 template <int GRID, bool SELB>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_pll(const float* __restrict__ in, long long in_stride, const double* __restrict__ inv, double* __restrict__ theta, long long wide_stride,
       float* __restrict__ nco0, float* __restrict__ state, int n, int n_streams, PllConst c)
 {

@@ -14,12 +14,14 @@
 #include "dy4_kernels.h"
 #include "dy4_internal.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr double kTwoPiHi = 6.283185307179586, kTwoPiLo = 2.4492935982947064e-16, kInvTwoPi = 0.15915494309189535;
 constexpr double kPi = 3.141592653589793;
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_rds_pll(const float* __restrict__ carrier, long long stride, double* __restrict__ theta, long long wide_stride,
           double* __restrict__ state, int n, int n_streams, double w, double Kp, double Ki)
 {
@@ -338,7 +340,8 @@ cudaError_t dy4_launch_rds_decode(const Dy4RdsDecodeArgs& a, cudaStream_t st)
 cudaError_t dy4_launch_rds_pll(const Dy4RdsArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
-    k_rds_pll<<<(a.n_streams + 31) / 32, 32, 0, st>>>(a.carrier, a.stride, a.theta, a.wide_stride, a.pll_state, a.n_if, a.n_streams, a.w, a.Kp, a.Ki);
+    static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // same knob as the stereo PLL
+    k_rds_pll<<<(a.n_streams + threads - 1) / threads, threads, 0, st>>>(a.carrier, a.stride, a.theta, a.wide_stride, a.pll_state, a.n_if, a.n_streams, a.w, a.Kp, a.Ki);
     g_dy4_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

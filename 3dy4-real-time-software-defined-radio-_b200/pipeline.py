@@ -14,7 +14,7 @@ from .modes import mode_params
 FLAG_EXACT_AUDIO = 1
 FLAG_DEBUG_ROWS = 2
 FLAG_RDS = 4
-KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails")
+KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails", "rds_bpf", "rds_pll", "rds_baseband")
 
 
 def launch_count():
@@ -111,9 +111,10 @@ class Pipeline:
                                         C.c_void_p(stream.cuda_stream)), "dy4_pipeline_rds_read")
         return i_t[:, :n.value], q_t[:, :n.value]
 
-    def rds_drain(self):
+    def rds_drain(self, raw=False):
         """Everything the RDS back half decoded since the last drain: per stream, dict(symbols, bits, events) of numpy
-        arrays (events: rows of [block type 0..4 = A,B,C,C',D, bit position, false-positive flag, 16-bit word])."""
+        arrays (events: rows of [block type 0..4 = A,B,C,C',D, bit position, false-positive flag, 16-bit word]).
+        raw=True returns the padded arrays and the counts instead: (symbols[S,:], bits[S,:], events[S,:,4], counts[S,3])."""
         import numpy as np
         ms, mb, me = C.c_int(), C.c_int(), C.c_int()
         check(lib.dy4_pipeline_rds_bounds(self._h, C.byref(ms), C.byref(mb), C.byref(me)), "dy4_pipeline_rds_bounds")
@@ -124,6 +125,8 @@ class Pipeline:
         cnt = np.zeros((S, 3), np.int32)
         check(lib.dy4_pipeline_rds_drain(self._h, C.c_void_p(sym.ctypes.data), sym.shape[1], C.c_void_p(bits.ctypes.data), bits.shape[1],
                                          C.c_void_p(ev.ctypes.data), ev.shape[1], C.c_void_p(cnt.ctypes.data)), "dy4_pipeline_rds_drain")
+        if raw:
+            return sym, bits, ev, cnt
         return [dict(symbols=sym[s, :cnt[s, 0]].copy(), bits=bits[s, :cnt[s, 1]].copy(), events=ev[s, :cnt[s, 2]].copy()) for s in range(S)]
 
     # ---- diagnostics ----------------------------------------------------------------------------

@@ -83,7 +83,7 @@ def make_batch(mode, n_streams, n_pairs, base_seed=65, rds=False):
     return np.stack([make_stream(mode, n_pairs, base_seed + s, rds) for s in range(n_streams)])
 
 
-def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chunk_streams=16):
+def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chunk_streams=16, rds=False):
     """Same signal model generated on the GPU with torch (benchmark input only:
     the random draws differ from make_batch, the statistics do not)."""
     import torch
@@ -99,6 +99,14 @@ def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chun
         R = col("aR") * torch.sin(2 * np.pi * col("fR") * t)
         wp = 2 * np.pi * 19e3 * t + col("phi")
         m = 0.45 * (L + R) + 0.1 * torch.sin(wp) + 0.45 * (L - R) * torch.sin(2 * wp)
+        if rds:                                      # same sub-carrier as make_stream(rds=True)
+            nbits = int(np.ceil(n_pairs / fs * 1187.5)) + 2
+            bits = torch.tensor(np.stack([rds_bitstream(nbits, base_seed + s + 7919) for s in range(s0, s1)]) * 2 - 1,
+                                dtype=torch.float64, device=device)
+            sym = torch.floor(t * 2375.0).to(torch.int64)
+            d = bits[:, sym // 2] * torch.where(sym % 2 == 0, 1.0, -1.0).to(torch.float64)
+            m = m + 0.05 * d * torch.cos(3 * wp)
+            del bits, sym, d
         del L, R, wp
         phase = (2 * np.pi * 75e3 / fs) * torch.cumsum(m, dim=1)
         del m

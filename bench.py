@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MODE, STEREO = 0, 1
+RDS = False                      # --rds: BASELINE configs[3], the stereo receiver plus the RDS path
 STREAMS_PER_GPU = 256
 BLOCKS_PER_STREAM = 47           # 47 x 21.33 ms = 1.003 s per stream
 METRIC = "aggregate_iq_msamples_per_s_stereo_fm"
@@ -157,7 +158,7 @@ def workload_config():
     return {
         "workload": "%smode %d stereo FM (8-bit IQ -> IF -> L/R int16 PCM), %d independent synthetic streams per GPU x %d blocks"
                     % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU) == (0, 256) else "", MODE, STREAMS_PER_GPU, BLOCKS_PER_STREAM),
-        "mode": MODE, "stereo": True, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
+        "mode": MODE, "stereo": True, "rds": RDS, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
         "input_bytes_per_gpu": STREAMS_PER_GPU * BLOCKS_PER_STREAM * {0: 102400, 1: 81920, 2: 160000, 3: 128000}[MODE],
         "l2": "inputs are larger than the 126 MB L2 (see input_bytes_per_gpu); no flush needed",
         "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32, f64 libm in the PLL); "
@@ -186,10 +187,10 @@ def run_gpu_arm(args):
     n_if, n_audio = nb * m.if_per_block, nb * m.audio_per_block
 
     # synthetic input, generated on the GPU; stream s of the whole job uses seed 65+s
-    d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev)
+    d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev, rds=RDS)
     if S > 512:                                      # very large batches: tile 512 distinct streams (generation time, not a kernel matter)
         d_iq = d_iq.repeat((S + 511) // 512, 1)[:S].contiguous()
-    pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank)
+    pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, rds=RDS)
     out = {"pcm": torch.empty((S, n_audio * 2), dtype=torch.int16, device=dev)}
     max_steps_between_resets = max(1, int(55.0 / (nb * (m.block_size / 2) / m.rf_Fs)))   # float PLL sample counter saturates at 2^24 (~69.9 s)
 
@@ -197,6 +198,8 @@ def run_gpu_arm(args):
         if i % max_steps_between_resets == 0:
             pipe.reset()
         pipe.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
+        if RDS:
+            pipe.rds_drain(raw=True)                 # symbols / bits / frame-sync events of this step, to the host
 
     for i in range(args.warmup):
         step(i)
@@ -252,7 +255,7 @@ def run_gpu_arm(args):
     # In the timed region above the job is cut into sub-chunks of 1, 2, 4, ... blocks whose FIR kernels run beside the
     # PLL of their predecessor: good for the step, but small concurrent launches understate what a kernel can do.
     iso = None
-    if rank == 0:
+    if rank == 0 and not RDS:
         pipe_iso = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, debug_rows=True)
         for i in range(2):
             pipe_iso.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
@@ -286,6 +289,10 @@ def run_gpu_arm(args):
         "pll": {"bytes": 8 / rd, "mac": 0.0},
         "audio": {"bytes": 12 / rd + 4 / ad, "mac": 2 * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
+        # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
+        "rds_bpf": {"bytes": 16 / rd, "mac": 2 * 101 / rd},
+        "rds_pll": {"bytes": 28 / rd, "mac": 0.0},
+        "rds_baseband": {"bytes": 12 / rd, "mac": 2 * 2 * 101 * 19 / 120 / rd},
     }
     total_kernel_ms = sum(v["ms"] for v in prof.values()) or 1.0
     kernels = {}
@@ -360,7 +367,7 @@ def run_gpu_arm(args):
 
 
 def main():
-    global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE
+    global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -371,8 +378,9 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: BASELINE configs[1], 256)")
     ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STREAM, help="blocks per stream per step (default 47 = 1.003 s)")
     ap.add_argument("--mode", type=int, default=MODE, help="receiver mode 0..3 (default 0)")
+    ap.add_argument("--rds", action="store_true", help="BASELINE configs[3]: also run the RDS path (mode 0 stereo; e.g. --streams 4096 --blocks 6)")
     args = ap.parse_args()
-    STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE = args.streams, args.blocks, args.mode
+    STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS = args.streams, args.blocks, args.mode, args.rds
     args.warmup = max(args.warmup, 3) if args.impl == "dy4" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
