@@ -64,14 +64,37 @@ k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __
     const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
     const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
 
-    // logical pair p <-> IF-rate index i = D*m0 - HALO + p ; pair = (delayed IF, mixed)
+    // logical pair p <-> IF-rate index i = D*m0 - HALO + p ; pair = (delayed IF, mixed).
+    // Staged four pairs at a time: D*m0 - HALO is a multiple of 4, so the NCO and stereo-band rows are read with aligned
+    // 16-byte loads and the delayed IF (offset -50: 8-byte aligned) with two 8-byte loads; units that touch the carried
+    // history or the end of the row take the element-wise path.  A unit never straddles a pad (CH % 4 == 0).
     constexpr int NP = D * T + HALO;
-    for (int p = tid; p < NP; p += NT) {
+    static_assert(NP % 4 == 0 && CH % 4 == 0 && (D * T) % 4 == 0 && HALO % 4 == 0 && DELAY % 2 == 0, "vector staging geometry");
+    for (int u = tid; u < NP / 4; u += NT) {
+        const int p = 4 * u;
         const int i = D * m0 - HALO + p;
-        float2 v;
-        v.x = if_at(row, itail, n_if, i - DELAY);
-        v.y = STEREO ? mix_at(nrow, srow, mtail, n_if, i) : 0.0f;
-        sm[p + 2 * (p / CH)] = v;
+        float x0, x1, x2, x3, y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        if (i - DELAY >= 0 && i + 3 < n_if) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(row + i - DELAY));
+            const float2 b = __ldg(reinterpret_cast<const float2*>(row + i - DELAY + 2));
+            x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
+            if (STEREO) {
+                const float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + i));
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + i));
+                y0 = __fmul_rn(__fmul_rn(nv.x, sv.x), 2.0f); y1 = __fmul_rn(__fmul_rn(nv.y, sv.y), 2.0f);     // filter.cpp:264
+                y2 = __fmul_rn(__fmul_rn(nv.z, sv.z), 2.0f); y3 = __fmul_rn(__fmul_rn(nv.w, sv.w), 2.0f);
+            }
+        } else {
+            x0 = if_at(row, itail, n_if, i - DELAY); x1 = if_at(row, itail, n_if, i + 1 - DELAY);
+            x2 = if_at(row, itail, n_if, i + 2 - DELAY); x3 = if_at(row, itail, n_if, i + 3 - DELAY);
+            if (STEREO) {
+                y0 = mix_at(nrow, srow, mtail, n_if, i); y1 = mix_at(nrow, srow, mtail, n_if, i + 1);
+                y2 = mix_at(nrow, srow, mtail, n_if, i + 2); y3 = mix_at(nrow, srow, mtail, n_if, i + 3);
+            }
+        }
+        float4* d = reinterpret_cast<float4*>(&sm[p + 2 * (p / CH)]);
+        d[0] = make_float4(x0, y0, x1, y1);
+        d[1] = make_float4(x2, y2, x3, y3);
     }
     __syncthreads();
 
