@@ -19,6 +19,8 @@
 #include "dy4_kernels.h"
 #include "dy4_internal.h"
 
+#include <algorithm>
+
 namespace {
 
 __constant__ TapPairs c_audio2[4];   // (h,h) pairs of the 101-tap audio low-pass, modes with U == 1
@@ -170,18 +172,28 @@ k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __
 }
 
 // ---- U > 1: one thread per output, tile of NT outputs per block ---------------------------------------
-template <int NT, bool EXACT, bool STEREO>
-__global__ void __launch_bounds__(NT)
+// The span of input the tile needs is staged in shared memory as (delayed IF, mixed) pairs, and so is the whole
+// transposed tap table [tap j][phase] (101 x up_pad floats, 59 KB for U = 147): consecutive outputs differ in phase by
+// D mod U, so a warp's tap reads fall on distinct banks, where the same reads through the read-only path cost several
+// L1 wavefronts each.  Both filters of an output advance with one packed FFMA2 per tap (fused: the PLL never sees
+// this kernel's output); EXACT keeps them unfused.
+// Lane mapping: consecutive outputs read inputs D/U = 5.44 (8.71) samples apart, a stride that piles a warp's 8-byte
+// sample reads onto a few banks.  Lane l of a warp therefore takes every K-th output (K = 9 for 147/800, 7 for
+// 147/1280: K*D/U is within 0.05 of an ODD integer, 49 and 61), K warps interleave to cover 32*K consecutive outputs,
+// and both the sample reads and the tap reads (phase stride K*D mod U = -3, -7) are bank-conflict free.
+template <int NTMAX, bool EXACT, bool STEREO>
+__global__ void __launch_bounds__(NTMAX)
 k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
              const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
              const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
              int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
-             const float* __restrict__ taps_poly, int up_pad, int span_max)
+             const float* __restrict__ taps_poly, int up_pad, int span_max, u64 nz, int K)
 {
+    const int NT = blockDim.x;                                              // 32 * K * groups outputs per tile
     extern __shared__ __align__(16) float sm_f[];
     constexpr int DELAY = DY4_NTAPS / 2;
-    float* s_ifd = sm_f;                 // delayed IF over the tile's span
-    float* s_mix = sm_f + span_max;      // mixed signal over the same span
+    float* s_taps = sm_f;                                                   // [DY4_NTAPS][up_pad]
+    float2* s_x = reinterpret_cast<float2*>(sm_f + DY4_NTAPS * up_pad);     // (delayed IF, mixed) over the tile's span
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * NT;
     const int s = blockIdx.x;
@@ -191,34 +203,55 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
     const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
     const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
 
+    for (int t = tid; t < DY4_NTAPS * up_pad / 4; t += NT)                  // up_pad is a multiple of 4
+        reinterpret_cast<float4*>(s_taps)[t] = __ldg(reinterpret_cast<const float4*>(taps_poly) + t);
     const int m_last = min(m0 + NT, n_audio) - 1;
-    const int i_lo = (int)(((long long)m0 * down) / up) - (DY4_NTAPS - 1);
+    const int i_lo = ((int)(((long long)m0 * down) / up) - (DY4_NTAPS - 1)) & ~3;   // aligned down: 16-byte loads below
     const int i_hi = (int)(((long long)m_last * down) / up);
     const int span = i_hi - i_lo + 1;
-    for (int p = tid; p < span; p += NT) {
+    for (int p = 4 * tid; p < span; p += 4 * NT) {
         const int i = i_lo + p;
-        s_ifd[p] = if_at(row, itail, n_if, i - DELAY);
-        if (STEREO) s_mix[p] = mix_at(nrow, srow, mtail, n_if, i);
+        float x0, x1, x2, x3, y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        if (i - DELAY >= 0 && i + 3 < n_if) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(row + i - DELAY));
+            const float2 b = __ldg(reinterpret_cast<const float2*>(row + i - DELAY + 2));
+            x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
+            if (STEREO) {
+                const float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + i));
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + i));
+                y0 = __fmul_rn(__fmul_rn(nv.x, sv.x), 2.0f); y1 = __fmul_rn(__fmul_rn(nv.y, sv.y), 2.0f);     // filter.cpp:264
+                y2 = __fmul_rn(__fmul_rn(nv.z, sv.z), 2.0f); y3 = __fmul_rn(__fmul_rn(nv.w, sv.w), 2.0f);
+            }
+        } else {
+            x0 = if_at(row, itail, n_if, i - DELAY); x1 = if_at(row, itail, n_if, i + 1 - DELAY);
+            x2 = if_at(row, itail, n_if, i + 2 - DELAY); x3 = if_at(row, itail, n_if, i + 3 - DELAY);
+            if (STEREO) {
+                y0 = mix_at(nrow, srow, mtail, n_if, i); y1 = mix_at(nrow, srow, mtail, n_if, i + 1);
+                y2 = mix_at(nrow, srow, mtail, n_if, i + 2); y3 = mix_at(nrow, srow, mtail, n_if, i + 3);
+            }
+        }
+        float4* d = reinterpret_cast<float4*>(s_x + p);
+        d[0] = make_float4(x0, y0, x1, y1);
+        d[1] = make_float4(x2, y2, x3, y3);
     }
     __syncthreads();
 
-    const int m = m0 + tid;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int m = m0 + 32 * K * (warp / K) + lane * K + (warp % K);
     if (m >= n_audio) return;
     const long long n = (long long)m * down;
     const int phase = (int)(n % up);
     const int base = (int)(n / up) - i_lo;          // position of x[floor(mD/U)] in the span
-    float mono = 0.0f, diff = 0.0f;
+    const u64* xs = reinterpret_cast<const u64*>(s_x) + base;
+    const float* hp = s_taps + phase;
+    u64 acc = 0ull;
 #pragma unroll 4
     for (int j = 0; j < DY4_NTAPS; j++) {
-        const float h = __ldg(taps_poly + j * up_pad + phase);
-        if (EXACT) {
-            mono = __fadd_rn(mono, __fmul_rn(h, s_ifd[base - j]));
-            if (STEREO) diff = __fadd_rn(diff, __fmul_rn(h, s_mix[base - j]));
-        } else {
-            mono = fmaf(h, s_ifd[base - j], mono);
-            if (STEREO) diff = fmaf(h, s_mix[base - j], diff);
-        }
+        const float h = hp[j * up_pad];
+        acc = tap2<EXACT>(acc, xs[-j], pk2(h, h), nz);
     }
+    float mono, diff;
+    upk2(acc, mono, diff);
     if (STEREO) {
         const float l = __fadd_rn(mono, diff), r = __fsub_rn(mono, diff);
         if (audio) *reinterpret_cast<float2*>(audio + (long long)s * audio_stride + 2LL * m) = make_float2(l, r);
@@ -255,13 +288,42 @@ cudaError_t dispatch_u1(const Dy4AudioArgs& a, cudaStream_t st)
 template <bool EXACT, bool STEREO>
 cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
 {
-    constexpr int NT = 128;
-    const int span_max = (int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 3;
-    const size_t smem = sizeof(float) * 2 * span_max;
+    constexpr int NTMAX = 640;
+    if (a.up_pad % 4) return cudaErrorInvalidValue;
+    // K: the output interleave that minimises shared-memory bank conflicts (see the kernel's header), found by counting
+    // them for a few sample warps: 8-byte sample reads are served per half-warp over 16 bank pairs, tap reads over 32 banks
+    static int k_up = 0, k_down = 0, k_best = 1;
+    if (k_up != a.up || k_down != a.down) {
+        long long best = -1;
+        for (int k = 1; k <= 10; k++) {
+            long long cost = 0;
+            for (int w = 0; w < 64; w++) {
+                int cx[2][16] = {}, ct[32] = {};
+                for (int l = 0; l < 32; l++) {
+                    const long long n = (long long)(w * 37 + 5 + l * k) * a.down;
+                    cx[l >> 4][(n / a.up) & 15]++;
+                    ct[(n % a.up) & 31]++;
+                }
+                int m0 = 0, m1 = 0, mt = 0;
+                for (int i = 0; i < 16; i++) { m0 = std::max(m0, cx[0][i]); m1 = std::max(m1, cx[1][i]); }
+                for (int i = 0; i < 32; i++) mt = std::max(mt, ct[i]);
+                cost += m0 + m1 + mt;
+            }
+            if (best < 0 || cost < best) { best = cost; k_best = k; }
+        }
+        k_up = a.up; k_down = a.down;
+    }
+    const int K = k_best;
+    const int NT = 32 * K * 2;                         // one 59 KB tap table per CTA, amortised over 64*K outputs
+    const int span_max = ((int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 3 + 4 + 7) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)DY4_NTAPS * a.up_pad + 2 * (size_t)span_max);
+    auto kern = k_audio_poly<NTMAX, EXACT, STEREO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     dim3 grid(a.n_streams, (a.n_audio + NT - 1) / NT);
-    k_audio_poly<NT, EXACT, STEREO><<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
-                                                            a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
-                                                            a.up, a.down, a.taps_poly, a.up_pad, span_max);
+    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
+                                 a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
+                                 a.up, a.down, a.taps_poly, a.up_pad, span_max, a.neg_zero2, K);
     g_dy4_launches++;
     return cudaGetLastError();
 }
