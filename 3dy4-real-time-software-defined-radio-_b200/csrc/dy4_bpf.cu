@@ -17,11 +17,14 @@ namespace {
 
 __constant__ TapPairs c_bpf2[6];   // (pilot[k], stereo-band[k]) pairs per mode; [4],[5]: RDS band-pass and RDS carrier band-pass, (h,h)
 
-template <int R, int NT, bool EXACT, bool SQUARE>
+// TWOSTREAMS (the single-filter launches of the RDS path, (h,h) tap tables): the two halves of the packed registers
+// carry two STREAMS (2b, 2b+1) through the same filter instead of one stream through two filters, so no lane is wasted;
+// both outputs go to `pilot` rows, `sband` is unused.
+template <int R, int NT, bool EXACT, bool SQUARE, bool TWOSTREAMS>
 __global__ void __launch_bounds__(NT)
 k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
            float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if,
-           u64 nz, int mode)
+           u64 nz, int mode, int n_streams)
 {
     constexpr int T = NT * R;
     constexpr int HALO = 128;                       // >= 100, keeps 16-byte alignment of global loads
@@ -29,8 +32,12 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     __shared__ __align__(16) float2 sm[NP + 2 * (NP / R) + 8];
     const int tid = threadIdx.x;
     const int n0 = blockIdx.y * T;                    // streams on grid.x (no 65535 limit), tiles on grid.y
-    const float* row = if_in + (long long)blockIdx.x * if_stride;
-    const float* tail = if_tail + (long long)blockIdx.x * DY4_IF_TAIL;
+    const int sa = TWOSTREAMS ? 2 * blockIdx.x : blockIdx.x;
+    const int sb = TWOSTREAMS ? min(sa + 1, n_streams - 1) : sa;            // odd stream count: the last CTA filters its stream twice
+    const float* row = if_in + (long long)sa * if_stride;
+    const float* tail = if_tail + (long long)sa * DY4_IF_TAIL;
+    const float* row_b = if_in + (long long)sb * if_stride;
+    const float* tail_b = if_tail + (long long)sb * DY4_IF_TAIL;
 
     // stage 4 samples per step as 4 duplicated pairs; logical pair p <-> sample n0 - HALO + p
     for (int u = tid; u < NP / 4; u += NT) {
@@ -40,10 +47,17 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
         else if (i + 3 < n_if) v = __ldg(reinterpret_cast<const float4*>(row + i));
         else { v.x = i < n_if ? row[i] : 0.f; v.y = i + 1 < n_if ? row[i + 1] : 0.f; v.z = i + 2 < n_if ? row[i + 2] : 0.f; v.w = 0.f; }
         if (SQUARE) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }     // RDS carrier recovery: the filter input is the squared signal
+        float4 vb = v;
+        if (TWOSTREAMS) {
+            if (i < 0) vb = *reinterpret_cast<const float4*>(tail_b + DY4_IF_TAIL + i);
+            else if (i + 3 < n_if) vb = __ldg(reinterpret_cast<const float4*>(row_b + i));
+            else { vb.x = i < n_if ? row_b[i] : 0.f; vb.y = i + 1 < n_if ? row_b[i + 1] : 0.f; vb.z = i + 2 < n_if ? row_b[i + 2] : 0.f; vb.w = 0.f; }
+            if (SQUARE) { vb.x *= vb.x; vb.y *= vb.y; vb.z *= vb.z; vb.w *= vb.w; }
+        }
         const int p = 4 * u;
         float4* d = reinterpret_cast<float4*>(&sm[p + 2 * (p / R)]);
-        d[0] = make_float4(v.x, v.x, v.y, v.y);
-        d[1] = make_float4(v.z, v.z, v.w, v.w);
+        d[0] = make_float4(v.x, vb.x, v.y, vb.y);
+        d[1] = make_float4(v.z, vb.z, v.w, vb.w);
     }
     __syncthreads();
 
@@ -68,17 +82,18 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     float op[R], os[R];
 #pragma unroll
     for (int r = 0; r < R; r++) upk2(acc[r], op[r], os[r]);
-    const long long o = (long long)blockIdx.x * out_stride + n0 + tid * R;
+    const long long o = (long long)sa * out_stride + n0 + tid * R;
+    float* second = TWOSTREAMS ? (sb != sa ? pilot + (long long)(sb - sa) * out_stride : nullptr) : sband;   // where the high halves go
     const int left = n_if - (n0 + tid * R);
     if (left >= R) {
 #pragma unroll
         for (int r = 0; r < R; r += 4) {
             *reinterpret_cast<float4*>(pilot + o + r) = make_float4(op[r], op[r + 1], op[r + 2], op[r + 3]);
-            if (sband) *reinterpret_cast<float4*>(sband + o + r) = make_float4(os[r], os[r + 1], os[r + 2], os[r + 3]);
+            if (second) *reinterpret_cast<float4*>(second + o + r) = make_float4(os[r], os[r + 1], os[r + 2], os[r + 3]);
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = op[r]; if (sband) sband[o + r] = os[r]; }
+        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = op[r]; if (second) second[o + r] = os[r]; }
     }
 }
 
@@ -88,10 +103,10 @@ cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     constexpr int R = 8, NT = 128;
-    dim3 grid(a.n_streams, (a.n_if + NT * R - 1) / (NT * R));
-    if (a.variant == 0) k_twin_bpf<R, NT, true, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
-    else if (a.variant == 1) k_twin_bpf<R, NT, false, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
-    else k_twin_bpf<R, NT, false, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode);
+    dim3 grid(a.variant == 0 ? a.n_streams : (a.n_streams + 1) / 2, (a.n_if + NT * R - 1) / (NT * R));
+    if (a.variant == 0) k_twin_bpf<R, NT, true, false, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
+    else if (a.variant == 1) k_twin_bpf<R, NT, false, false, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
+    else k_twin_bpf<R, NT, false, true, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
     g_dy4_launches++;
     return cudaGetLastError();
 }

@@ -22,7 +22,8 @@ struct Dy4BpfArgs {
     const float* if_tail;                       // [n_streams][DY4_IF_TAIL] IF samples preceding the chunk
     float* pilot; float* sband; long long out_stride;
     int n_if, n_streams, mode;                  // mode 0..3: (pilot, stereo) table; 4, 5: RDS band-pass / carrier tables
-    int variant;                                // 0 exact pair; 1 fused; 2 fused on the SQUARED input.  sband may be NULL.
+    int variant;                                // 0: exact (pilot, stereo) pair of one stream; 1: ONE fused (h,h) filter over two streams per CTA -> pilot rows;
+                                                // 2: as 1 on the SQUARED input
     unsigned long long neg_zero2;
 };
 

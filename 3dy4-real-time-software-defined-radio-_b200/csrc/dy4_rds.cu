@@ -21,6 +21,12 @@ namespace {
 constexpr double kTwoPiHi = 6.283185307179586, kTwoPiLo = 2.4492935982947064e-16, kInvTwoPi = 0.15915494309189535;
 constexpr double kPi = 3.141592653589793;
 
+// The detector needs the phase argument reduced to (-pi, pi].  Reducing w*k + phase from scratch every sample (it reaches
+// 1e5 rad) would put a Cody-Waite reduction on the serial chain; instead the reduced phase r is reduced ONCE per launch
+// and then advanced incrementally, r += (w mod 2pi) + dphase, wrapped by at most one turn.  Its rounding (1e-16 per
+// step) is far inside the path's tolerance — the model itself is float64 — while the unreduced argument theta, which the
+// NCO rows are computed from, is still formed as w*k + phase exactly as the model does.  Per sample the dependent chain
+// is: select eD -> integ -> dphase -> r -> wrap.
 __global__ void __launch_bounds__(128)
 k_rds_pll(const float* __restrict__ carrier, long long stride, double* __restrict__ theta, long long wide_stride,
           double* __restrict__ state, int n, int n_streams, double w, double Kp, double Ki)
@@ -28,24 +34,41 @@ k_rds_pll(const float* __restrict__ carrier, long long stride, double* __restric
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     double* st = state + (long long)s * 8;
-    double integ = st[0], phase = st[1], k = st[2], th = st[3];
+    double integ = st[0], phase = st[1], k = st[2];
+    const double th0 = st[3];
+    double r;
+    {   // reduced phase of the carried argument: th - 2 pi rint(th / 2 pi), two-part 2 pi
+        const double q = rint(th0 * kInvTwoPi);
+        r = fma(-q, kTwoPiLo, fma(-q, kTwoPiHi, th0));
+    }
+    const double w_red = w - kTwoPiHi * rint(w * kInvTwoPi);      // w is below 2 pi here: exact
     const float* x = carrier + (long long)s * stride;
     double* y = theta + (long long)s * wide_stride;
-    for (int i = 0; i < n; i++) {
-        const float xv = x[i];
-        // reduced phase of the previous feedback pair: th - 2 pi rint(th / 2 pi)
-        const double q = rint(th * kInvTwoPi);
-        const double r = fma(-q, kTwoPiLo, fma(-q, kTwoPiHi, th));
-        double eD = 0.0;                                           // fmPll: errorI == 0 -> errorD = 0  (fmMonoBlock.py:359)
-        if (xv > 0.0f) eD = -r;
-        else if (xv < 0.0f) eD = (r > 0.0 ? kPi : -kPi) - r;
-        integ = integ + Ki * eD;                                   // :363
-        phase = phase + Kp * eD + integ;                           // :364
+    auto step = [&](float xv) -> double {
+        const double rw = r + w_red, rw2 = rw - kTwoPiHi;          // beside the chain: both wraps of the next phase
+        // fmPll: errorD = atan2(-x sin t, x cos t) = -t (x > 0) or pi - t wrapped (x < 0); 0 for x == 0 (fmMonoBlock.py:355-362)
+        const double e_neg = (r > 0.0 ? kPi : -kPi) - r;
+        const double eD = xv > 0.0f ? -r : (xv < 0.0f ? e_neg : 0.0);
+        integ = fma(Ki, eD, integ);                                // :363
+        const double dph = fma(Kp, eD, integ);
+        phase += dph;                                              // :364
         k += 1.0;                                                  // :367
-        th = w * k + phase;                                        // :368
-        y[i] = th;
+        const double a = rw + dph, b = rw2 + dph;
+        r = a > kPi ? b : a;
+        return fma(w, k, phase);                                   // :368
+    };
+    int i = 0;
+    for (; i < n && (i & 3); i++) y[i] = step(x[i]);
+    float4 v = i + 4 <= n ? *reinterpret_cast<const float4*>(x + i) : make_float4(0, 0, 0, 0);
+    for (; i + 4 <= n; i += 4) {
+        const float4 cur = v;
+        if (i + 8 <= n) v = *reinterpret_cast<const float4*>(x + i + 4);
+        const double t0 = step(cur.x), t1 = step(cur.y), t2 = step(cur.z), t3 = step(cur.w);
+        *reinterpret_cast<double2*>(y + i) = make_double2(t0, t1);
+        *reinterpret_cast<double2*>(y + i + 2) = make_double2(t2, t3);
     }
-    st[0] = integ; st[1] = phase; st[2] = k; st[3] = th;
+    for (; i < n; i++) y[i] = step(x[i]);
+    st[0] = integ; st[1] = phase; st[2] = k; st[3] = n > 0 ? y[n - 1] : th0;
 }
 
 // nco_i[k] = cos(theta[k-1]*scale + adj), nco_q[k] = sin(...); [0] from the carried state (fmMonoBlock.py:353-354,373-376)

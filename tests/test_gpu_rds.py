@@ -47,6 +47,7 @@ def test_rds_golden(dy4, splits):
     g, iq = golden_iq(dy4)
     ri, rq, dr = run_rds(dy4, iq, splits)
     assert ri.shape[1] == len(g["rrc_i"])
+    print("rel-L2 of the RRC baseband vs the model:", rel_l2(ri[0], g["rrc_i"]), rel_l2(rq[0], g["rrc_q"]))
     assert rel_l2(ri[0], g["rrc_i"]) <= TOL_L2 and rel_l2(rq[0], g["rrc_q"]) <= TOL_L2
     n = len(g["rrc_i64"])
     assert rel_l2(ri[0, :n], g["rrc_i64"]) <= TOL_L2 and rel_l2(rq[0, :n], g["rrc_q64"]) <= TOL_L2
