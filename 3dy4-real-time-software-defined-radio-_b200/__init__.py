@@ -6,6 +6,7 @@ as in the header:
 
 * ``filterh``  — the reference's include/filter.h functions by their own names
   (impulseResponseLPF, blockConvolveFIR, fmPLL, ...) on numpy arrays.
+* ``fourierh`` — include/fourier.h (DFT, IDFT, estimatePSD) likewise, plus a batched PSD over device rows.
 * ``Pipeline`` — the batched receiver over many independent streams.
 
 There is no CPU fallback: everything that computes calls libdy4b200.so, and
@@ -19,8 +20,9 @@ from ._lib import lib, Dy4Error, LIB_PATH, build_library  # noqa: F401
 from .modes import mode_params, ModeParams  # noqa: F401
 from .pipeline import Pipeline, launch_count  # noqa: F401
 from . import filterh  # noqa: F401
+from . import fourierh  # noqa: F401
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401
 
 PACKAGE_DIR = _os.path.dirname(_os.path.abspath(__file__))
-__all__ = ["lib", "Dy4Error", "Pipeline", "mode_params", "ModeParams", "filterh", "synth", "launch_count", "build_library"]
+__all__ = ["lib", "Dy4Error", "Pipeline", "mode_params", "ModeParams", "filterh", "fourierh", "synth", "launch_count", "build_library"]

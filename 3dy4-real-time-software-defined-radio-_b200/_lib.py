@@ -43,6 +43,10 @@ def _load():
         "dy4_bpf_taps": (i, [f, f, f, us, i, vp]),
         "dy4_firwin": (i, [i, C.c_double, C.c_double, i, vp]),
         "dy4_rrc_taps": (i, [C.c_double, i, vp]),
+        "dy4_dft": (i, [vp, sz, vp]),
+        "dy4_idft": (i, [vp, sz, vp]),
+        "dy4_estimate_psd": (i, [vp, sz, i, i, vp, vp]),
+        "dy4_psd_batch": (i, [vp, sz, i, sz, i, i, vp, sz, vp]),
         "dy4_iq_to_float": (i, [vp, sz, vp]),
         "dy4_convolve_fir": (i, [vp, vp, sz, vp, sz]),
         "dy4_block_fir": (i, [vp, vp, sz, vp, sz, vp, sz]),

@@ -99,6 +99,25 @@ int dy4_pointwise_subtract(const float* a, const float* b, size_t n, float* out)
 /* filter.h:34 interleave: out has nl+nr floats */
 int dy4_interleave(const float* left, size_t nl, const float* right, size_t nr, float* out);
 
+/* ---- Fourier diagnostics: reference include/fourier.h, src/fourier.cpp ---- */
+/* Not on the receiver's path (project.cpp never calls them); SURVEY.md §8f rank 3.  Complex vectors are interleaved
+ * (re, im) floats.  The reference's DFT uses twiddles exp(i * float(-2 PI k m / n)) — the angle is narrowed to float
+ * BEFORE cosf/sinf — and sums over k in float; these entry points reproduce exactly that (twiddle table built on the
+ * host with the same libm, unfused float accumulation on the device), not an FFT.  n, nfft <= 2048.
+ * fourier.h:20 DFT(x, Xf): n real samples -> n complex bins */
+int dy4_dft(const float* x, size_t n, float* Xf);
+/* fourier.h:38 IDFT(Xf, x): n complex bins -> n complex samples, divided by n */
+int dy4_idft(const float* Xf, size_t n, float* x);
+/* fourier.h:31 estimatePSD(samples, nFFT, Fs, freq, psd_est): floor(n/nfft) Hann-windowed segments, DFT of each,
+ * 10 log10((1/(Fs nfft/2)) 2 |X|^2) per bin, averaged over the segments; freq and psd receive nfft/2 floats
+ * (freq may be NULL).  Host pointers. */
+int dy4_estimate_psd(const float* samples, size_t n, int nfft, int Fs, float* freq, float* psd);
+/* The same PSD for n_streams rows of n samples on the DEVICE (rows row_stride floats apart), e.g. the IF or audio
+ * rows of a dy4_pipeline_process call: d_psd[n_streams][nfft/2], rows psd_stride floats apart, asynchronously on
+ * `stream` (a cudaStream_t). */
+int dy4_psd_batch(const float* d_samples, size_t row_stride, int n_streams, size_t n, int nfft, int Fs,
+                  float* d_psd, size_t psd_stride, void* stream);
+
 /* ---- throughput tier: batched receiver ----------------------------------- */
 typedef struct dy4_pipeline dy4_pipeline_t;
 

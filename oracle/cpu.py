@@ -139,6 +139,26 @@ class CpuReceiver:
         self._f("pcm16")(_fp(x), C.c_long(x.size), C.c_void_p(out.ctypes.data))
         return out
 
+    # ---- Fourier diagnostics (src/fourier.cpp) --------------------------------
+    def dft(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(x.size, np.complex64)
+        self._f("dft")(C.c_void_p(x.ctypes.data), C.c_int(x.size), C.c_void_p(out.ctypes.data))
+        return out
+
+    def idft(self, Xf):
+        Xf = np.ascontiguousarray(Xf, np.complex64)
+        out = np.empty(Xf.size, np.complex64)
+        self._f("idft")(C.c_void_p(Xf.ctypes.data), C.c_int(Xf.size), C.c_void_p(out.ctypes.data))
+        return out
+
+    def estimate_psd(self, samples, nfft, Fs):
+        s = np.ascontiguousarray(samples, np.float32)
+        freq, psd = np.empty(nfft // 2, np.float32), np.empty(nfft // 2, np.float32)
+        self._f("estimate_psd")(C.c_void_p(s.ctypes.data), C.c_long(s.size), C.c_int(nfft), C.c_int(Fs),
+                                C.c_void_p(freq.ctypes.data), C.c_void_p(psd.ctypes.data))
+        return freq, psd
+
     # ---- whole receiver over one stream ------------------------------------
     def pipeline(self, mode, stereo, iq, want=("if", "audio", "pcm", "pilot", "nco")):
         iq = np.ascontiguousarray(iq, np.uint8)

@@ -25,6 +25,9 @@
 #include <string.h>
 
 #define DY4_PI 3.14159265358979323846 /* include/dy4.h:14 — a double literal */
+#ifndef DY4_LOG10
+#define DY4_LOG10(v) log10((double)(v))   /* fourier.cpp:75 calls the unqualified ::log10 on a float (see tests/test_oracle.py: checked against the reference build) */
+#endif
 #define DY4_NUM_TAPS 101              /* src/project.cpp:142 */
 
 /* ---- mode table: src/project.cpp:178-238 -------------------------------- */
@@ -297,4 +300,68 @@ long DY4_FN(pipeline)(int mode, int stereo, const uint8_t* iq, long nbytes,
     free(xf); free(xi); free(xq); free(di); free(dq); free(fm); free(delayed); free(pilot);
     free(sband); free(nco); free(mixed); free(mono); free(diff); free(outb);
     return nblocks;
+}
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fourier diagnostics — reference src/fourier.cpp (not on the receiver's hot path).
+ * std::exp(std::complex<float>(0, a)) is cexpf(0 + ia) = (cosf(a), sinf(a)); float * complex<float> multiplies both
+ * parts by the float; complex<float> * complex<float> is libgcc's __mulsc3 (four products, a difference and a sum).
+ * ---------------------------------------------------------------------------------------------------------------- */
+void DY4_FN(dft)(const float* x, int n, float* Xf)
+{
+    for (int m = 0; m < n; m++) {                                  /* fourier.cpp:16 */
+        float re = 0.0f, im = 0.0f;
+        for (int k = 0; k < n; k++) {                              /* :17 */
+            const float a = (float)(-2 * DY4_PI * (k * m) / (double)(size_t)n);   /* :18: double expression narrowed by the complex<float> constructor */
+            const float wr = cosf(a), wi = sinf(a);
+            const float pr = wr * x[k], pi_ = wi * x[k];           /* :19 */
+            re = re + pr; im = im + pi_;
+        }
+        Xf[2 * m] = re; Xf[2 * m + 1] = im;
+    }
+}
+
+void DY4_FN(idft)(const float* Xf, int n, float* x)
+{
+    for (unsigned k = 0; k < (unsigned)n; k++) {                   /* :100 */
+        float re = 0.0f, im = 0.0f;
+        for (unsigned m = 0; m < (unsigned)n; m++) {               /* :101 */
+            const float a = (float)(2 * DY4_PI * (k * m) / (double)(size_t)n);    /* :102 */
+            const float wr = cosf(a), wi = sinf(a);
+            const float ar = Xf[2 * m], ai = Xf[2 * m + 1];
+            const float ac = ar * wr, bd = ai * wi, ad = ar * wi, bc = ai * wr;   /* :103, __mulsc3 */
+            re = re + (ac - bd); im = im + (ad + bc);
+        }
+        x[2 * k] = re / (float)n; x[2 * k + 1] = im / (float)n;    /* :105 */
+    }
+}
+
+void DY4_FN(estimate_psd)(const float* samples, long n, int nfft, int Fs, float* freq, float* psd)
+{
+    const float df = (float)Fs / (float)nfft;                      /* :40 */
+    const int half = nfft / 2;
+    for (int i = 0; i < half; i++) freq[i] = df * (float)i;        /* :43-45 */
+    float* hann = (float*)malloc(sizeof(float) * (size_t)nfft);
+    for (int i = 0; i < nfft; i++) hann[i] = (float)pow(sin((float)i * DY4_PI / (float)nfft), 2);   /* :49-51 */
+    const int nseg = (int)floorf((float)n / (float)nfft);          /* :54 */
+    float* win = (float*)malloc(sizeof(float) * (size_t)nfft);
+    float* Xf = (float*)malloc(sizeof(float) * 2 * (size_t)nfft);
+    float* list = (float*)malloc(sizeof(float) * (size_t)half * (size_t)(nseg > 0 ? nseg : 1));
+    for (int s = 0; s < nseg; s++) {                               /* :58 */
+        for (int j = 0; j < nfft; j++) win[j] = samples[(long)s * nfft + j] * hann[j];   /* :61-63 */
+        DY4_FN(dft)(win, nfft, Xf);                                /* :67 */
+        for (int j = 0; j < half; j++) {                           /* :73-76 */
+            const float mag = hypotf(Xf[2 * j], Xf[2 * j + 1]);    /* std::abs(complex<float>) */
+            float v = (float)((1.0 / ((float)Fs * (float)nfft / 2.0)) * 2.0 * pow((double)mag, 2));
+            v = (float)(10.0 * DY4_LOG10(v));
+            list[(size_t)s * half + j] = v;
+        }
+    }
+    for (int i = 0; i < half; i++) {                               /* :84-89 */
+        float acc = 0.0f;
+        for (int s = 0; s < nseg; s++) acc = acc + list[(size_t)i + (size_t)s * half];
+        psd[i] = acc / (float)nseg;
+    }
+    free(hann); free(win); free(Xf); free(list);
 }

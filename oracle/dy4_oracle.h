@@ -78,6 +78,17 @@ long DY4_FN(pipeline)(int mode, int stereo, const uint8_t* iq, long nbytes,
                       float* if_out, float* audio_out, int16_t* pcm_out,
                       float* pilot_out, float* nco_out);
 
+/*
+ * Fourier diagnostics, reference src/fourier.cpp.  Complex vectors are interleaved (re, im) floats.
+ *   dft           :14-23   naive O(n^2) DFT of a real vector, float twiddles exp(i * float(-2 PI k m / n))
+ *   idft          :98-107  naive inverse DFT of a complex vector, divided by n
+ *   estimate_psd  :37-94   Hann-windowed segments of nfft samples, DFT, 10 log10 of the scaled power, segment average;
+ *                          freq and psd hold nfft/2 floats
+ */
+void DY4_FN(dft)(const float* x, int n, float* Xf);
+void DY4_FN(idft)(const float* Xf, int n, float* x);
+void DY4_FN(estimate_psd)(const float* samples, long n, int nfft, int Fs, float* freq, float* psd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,4 +207,27 @@ long dy4r_pipeline(int mode, int stereo, const uint8_t* iq, long nbytes,
     return nblocks;
 }
 
+/* ---- Fourier diagnostics: the reference's own fourier.cpp ---------------------------------------------------- */
+void dy4r_dft(const float* x, int n, float* Xf)
+{
+    std::vector<float> xv(x, x + n);
+    std::vector<std::complex<float>> X;
+    DFT(xv, X);
+    for (int i = 0; i < n; i++) { Xf[2 * i] = X[i].real(); Xf[2 * i + 1] = X[i].imag(); }
+}
+void dy4r_idft(const float* Xf, int n, float* x)
+{
+    std::vector<std::complex<float>> X(n), xv;
+    for (int i = 0; i < n; i++) X[i] = std::complex<float>(Xf[2 * i], Xf[2 * i + 1]);
+    IDFT(X, xv);
+    for (int i = 0; i < n; i++) { x[2 * i] = xv[i].real(); x[2 * i + 1] = xv[i].imag(); }
+}
+void dy4r_estimate_psd(const float* samples, long n, int nfft, int Fs, float* freq, float* psd)
+{
+    std::vector<float> sv(samples, samples + n), f, p;
+    estimatePSD(sv, nfft, Fs, f, p);
+    std::memcpy(freq, f.data(), sizeof(float) * f.size());
+    std::memcpy(psd, p.data(), sizeof(float) * p.size());
+}
+
 } /* extern "C" */

@@ -231,3 +231,39 @@ def test_synthetic_rds_groups_are_valid(dy4):
             assert rds.SYNDROMES.get(syn) == off
     d = dy4.synth.rds_bitstream(300, 1234)
     assert np.array_equal(np.diff(d) % 2, bits[1:300])                                 # differential encoding
+
+
+# ---------------------------------------------------------------- Fourier diagnostics (src/fourier.cpp)
+def test_fourier_oracle_matches_golden(orc):
+    """The C restatement of DFT / IDFT / estimatePSD against what the reference's own fourier.cpp returned."""
+    g = golden("fourier.npz")
+    assert np.array_equal(orc.dft(g["x64"]).view(np.uint32), g["X64"].view(np.uint32))
+    assert np.array_equal(orc.dft(g["x512"]).view(np.uint32), g["X512"].view(np.uint32))
+    assert np.array_equal(orc.idft(g["X64"]).view(np.uint32), g["x64_back"].view(np.uint32))
+    freq, psd = orc.estimate_psd(g["sig"], 512, 240000)
+    assert np.array_equal(freq, g["freq"]) and np.array_equal(bits(psd), bits(g["psd"]))
+
+
+def test_fourier_oracle_equals_reference_live(orc, refl):
+    rng = np.random.Generator(np.random.PCG64(11))
+    for n in (1, 2, 7, 16, 100, 256):
+        x = rng.uniform(-10, 10, n).astype(np.float32)
+        X = refl.dft(x)
+        assert np.array_equal(orc.dft(x).view(np.uint32), X.view(np.uint32))
+        assert np.array_equal(orc.idft(X).view(np.uint32), refl.idft(X).view(np.uint32))
+    s = rng.normal(0, 1, 3000).astype(np.float32)
+    for nfft in (64, 256):
+        a, b = orc.estimate_psd(s, nfft, 48000), refl.estimate_psd(s, nfft, 48000)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+
+
+def test_fourier_properties(orc):
+    """What the reference's own unit tests check (test/idft_unittest.cpp:45-60, fft_unittest.cpp:40-60), with a
+    meaningful tolerance: IDFT(DFT(x)) returns x, and the DFT agrees with numpy's FFT to the accuracy its float
+    twiddle angles allow."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = rng.uniform(-10, 10, 128).astype(np.float32)
+    X = orc.dft(x)
+    back = orc.idft(X)
+    assert np.abs(back.real - x).max() < 1e-3 and np.abs(back.imag).max() < 1e-3
+    assert rel_l2(np.stack([X.real, X.imag]), np.stack([np.fft.fft(x).real, np.fft.fft(x).imag])) < 1e-4
