@@ -783,11 +783,22 @@ extern "C" int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long
 }
 
 // ---- checkpoint of carried state -------------------------------------------------------------------
+// RDS part of a checkpoint (DY4_FLAG_RDS): a 16-byte header {if_abs, samples held for the decoder}, then per stream the
+// band-pass / mixer / resampler histories, the carrier PLL state, the decoder state and the RRC samples the decoder has
+// not consumed yet (less than one model block).  Decoded symbols / bits / events are results, not state: drain first.
+static size_t rds_state_bytes(const dy4_pipeline_t* p)
+{
+    if (!(p->flags & DY4_FLAG_RDS)) return 0;
+    const size_t S = (size_t)p->n_streams;
+    return 16 + S * (DY4_IF_TAIL * sizeof(float) + 4 * DY4_MIX_TAIL * sizeof(float) + 8 * sizeof(double) +
+                     DY4_RDS_STATE_INTS * sizeof(int) + DY4_RDS_BLOCK * sizeof(float));
+}
+
 extern "C" size_t dy4_pipeline_state_size(const dy4_pipeline_t* p)
 {
     if (!p) return 0;
     const size_t S = (size_t)p->n_streams;
-    return S * (DY4_IQ_TAIL + (DY4_IF_TAIL + DY4_MIX_TAIL + 8) * sizeof(float));
+    return S * (DY4_IQ_TAIL + (DY4_IF_TAIL + DY4_MIX_TAIL + 8) * sizeof(float)) + rds_state_bytes(p);
 }
 
 extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
@@ -800,7 +811,20 @@ extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
     CU(cudaMemcpy(o, p->iq_tail, S * DY4_IQ_TAIL, cudaMemcpyDeviceToHost)); o += S * DY4_IQ_TAIL;
     CU(cudaMemcpy(o, if_tail_slot(p, p->seq), S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(o, p->mix_tail, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_MIX_TAIL * sizeof(float);
-    CU(cudaMemcpy(o, p->pll_state, S * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(o, p->pll_state, S * 8 * sizeof(float), cudaMemcpyDeviceToHost)); o += S * 8 * sizeof(float);
+    if (p->flags & DY4_FLAG_RDS) {
+        long long hdr[2] = {p->if_abs, (long long)p->rds_left};
+        std::memcpy(o, hdr, 16); o += 16;
+        CU(cudaMemcpy(o, p->rds_tail, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
+        CU(cudaMemcpy(o, p->rds_mix_tail, S * 2 * DY4_MIX_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * 2 * DY4_MIX_TAIL * sizeof(float);
+        CU(cudaMemcpy(o, p->rds_lp_tail, S * 2 * DY4_MIX_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * 2 * DY4_MIX_TAIL * sizeof(float);
+        CU(cudaMemcpy(o, p->rds_pll_state, S * 8 * sizeof(double), cudaMemcpyDeviceToHost)); o += S * 8 * sizeof(double);
+        CU(cudaMemcpy(o, p->rds_dec_state, S * DY4_RDS_STATE_INTS * sizeof(int), cudaMemcpyDeviceToHost)); o += S * DY4_RDS_STATE_INTS * sizeof(int);
+        std::memset(o, 0, S * DY4_RDS_BLOCK * sizeof(float));
+        if (p->rds_left > 0)
+            CU(cudaMemcpy2D(o, DY4_RDS_BLOCK * sizeof(float), p->rds_acc + p->rds_consumed, p->rds_acc_cap * sizeof(float),
+                            (size_t)p->rds_left * sizeof(float), S, cudaMemcpyDeviceToHost));
+    }
     return DY4_OK;
 }
 
@@ -814,6 +838,25 @@ extern "C" int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf)
     CU(cudaMemcpy(p->iq_tail, o, S * DY4_IQ_TAIL, cudaMemcpyHostToDevice)); o += S * DY4_IQ_TAIL;
     CU(cudaMemcpy(if_tail_slot(p, p->seq), o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(p->mix_tail, o, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_MIX_TAIL * sizeof(float);
-    CU(cudaMemcpy(p->pll_state, o, S * 8 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->pll_state, o, S * 8 * sizeof(float), cudaMemcpyHostToDevice)); o += S * 8 * sizeof(float);
+    if (p->flags & DY4_FLAG_RDS) {
+        long long hdr[2];
+        std::memcpy(hdr, o, 16); o += 16;
+        if (hdr[1] < 0 || hdr[1] >= DY4_RDS_BLOCK) { dy4_set_error("dy4_pipeline_set_state: corrupt RDS header"); return DY4_ERR_ARG; }
+        p->if_abs = hdr[0];
+        CU(cudaMemcpy(p->rds_tail, o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
+        CU(cudaMemcpy(p->rds_mix_tail, o, S * 2 * DY4_MIX_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * 2 * DY4_MIX_TAIL * sizeof(float);
+        CU(cudaMemcpy(p->rds_lp_tail, o, S * 2 * DY4_MIX_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * 2 * DY4_MIX_TAIL * sizeof(float);
+        CU(cudaMemcpy(p->rds_pll_state, o, S * 8 * sizeof(double), cudaMemcpyHostToDevice)); o += S * 8 * sizeof(double);
+        CU(cudaMemcpy(p->rds_dec_state, o, S * DY4_RDS_STATE_INTS * sizeof(int), cudaMemcpyHostToDevice)); o += S * DY4_RDS_STATE_INTS * sizeof(int);
+        int rc = grow_rows(p->rds_acc, p->rds_acc_cap, (size_t)DY4_RDS_BLOCK + 64, S, 1, p->s_rds ? p->s_rds : (cudaStream_t)0);
+        if (rc) return rc;
+        p->rds_left = (int)hdr[1]; p->rds_consumed = 0;
+        if (p->rds_left > 0)
+            CU(cudaMemcpy2D(p->rds_acc, p->rds_acc_cap * sizeof(float), o, DY4_RDS_BLOCK * sizeof(float),
+                            (size_t)p->rds_left * sizeof(float), S, cudaMemcpyHostToDevice));
+        CU(cudaMemset(p->rds_counts, 0, S * 4 * sizeof(int)));
+        p->rds_blocks_since_drain = 0; p->rds_call_n = 0; p->rds_n_out = 0;
+    }
     return DY4_OK;
 }

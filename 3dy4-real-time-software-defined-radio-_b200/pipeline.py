@@ -85,6 +85,7 @@ class Pipeline:
         assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[0] == self.n_streams and a.strides[1] == 1
         if n_blocks is None:
             n_blocks = a.shape[1] // p.block_size
+        self._last_blocks = int(n_blocks)
         na = n_blocks * p.audio_per_block * self.channels
         out = dict(out or {})
         if "pcm" in want and "pcm" not in out:

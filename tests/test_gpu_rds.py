@@ -110,3 +110,30 @@ def test_rds_needs_mode0_stereo(dy4):
         dy4.Pipeline(2, 1, 2, rds=True)
     with pytest.raises(Exception):
         dy4.Pipeline(0, 0, 2, rds=True)
+
+
+def test_rds_checkpoint_and_host_path(dy4):
+    """Checkpoint after 27 blocks, restore into a fresh receiver, feed the rest: the RRC baseband of the second part and
+    every symbol / bit / event are those of the uninterrupted run.  The second part goes through process_host()."""
+    import torch
+    g, iq = golden_iq(dy4)
+    m = dy4.mode_params(0)
+    cut = 27 * m.block_size
+    ri_all, rq_all, dr_all = run_rds(dy4, iq, [27, 33])
+    a = dy4.Pipeline(0, 1, 1, rds=True)
+    a.process(torch.from_numpy(iq[None, :cut]).cuda(), want=("pcm",))
+    first = a.rds_drain()
+    state = a.get_state()
+    a.close()
+    b = dy4.Pipeline(0, 1, 1, rds=True)
+    b.set_state(state)
+    b.process_host(iq[None, cut:].copy(), want=("pcm",))
+    i_t, q_t = b.rds_read()
+    torch.cuda.synchronize()
+    second = b.rds_drain()
+    b.close()
+    n2 = i_t.shape[1]
+    assert np.array_equal(i_t.cpu().numpy()[0], ri_all[0, -n2:]) and np.array_equal(q_t.cpu().numpy()[0], rq_all[0, -n2:])
+    for k in ("symbols", "bits", "events"):
+        assert np.array_equal(np.concatenate([first[0][k], second[0][k]]), dr_all[0][k]), k
+    assert np.array_equal(dr_all[0]["bits"], g["bits"])
