@@ -66,6 +66,8 @@ def _load():
         "dy4_pipeline_reset": (i, [vp]),
         "dy4_pipeline_process": (i, [vp, vp, sz, i, vp, vp, vp, vp]),
         "dy4_pipeline_process_host": (i, [vp, vp, sz, i, vp, vp, i]),
+        "dy4_pinned_alloc": (vp, [sz]),
+        "dy4_pinned_free": (None, [vp]),
         "dy4_pipeline_rds_read": (i, [vp, vp, vp, sz, C.POINTER(i), vp]),
         "dy4_pipeline_rds_bounds": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "dy4_pipeline_rds_drain": (i, [vp, vp, sz, vp, sz, vp, sz, vp]),

@@ -704,6 +704,15 @@ extern "C" int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pil
     return DY4_OK;
 }
 
+extern "C" void* dy4_pinned_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { dy4_cuda_fail(e, "dy4_pinned_alloc"); return nullptr; }
+    return p;
+}
+extern "C" void dy4_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d_rrc_q, size_t row_stride, int* n_samples, void* stream)
 {
     if (!p || !(p->flags & DY4_FLAG_RDS) || !n_samples) { dy4_set_error("dy4_pipeline_rds_read: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }

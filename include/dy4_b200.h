@@ -169,6 +169,10 @@ int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stri
 int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                               int16_t* h_pcm, float* h_audio, int chunk_blocks);
 
+/* Page-locked host memory for the buffers handed to dy4_pipeline_process_host (pageable memory works too, slower). */
+void* dy4_pinned_alloc(size_t bytes);
+void dy4_pinned_free(void* p);
+
 /* RRC-filtered RDS baseband (in-phase and quadrature, 38 kS/s) produced by the LAST process call: *n_samples of
  * them per stream (about 19/120 of the call's IF samples; the exact count follows the absolute sample index), copied
  * to DEVICE rows d_rrc_i / d_rrc_q (either may be NULL) of `row_stride` floats, asynchronously on `stream`. */

@@ -303,3 +303,24 @@ def test_more_than_65535_streams(dy4, checker):
         ref = checker.pipeline(1, 1, base[s])
         assert np.abs(first[s].cpu().numpy().astype(np.int32) - ref["pcm"]).max() <= 1
     p.close()
+
+
+@pytest.mark.parametrize("mode,stereo,per_call", [(0, 1, 1), (0, 0, 3), (2, 1, 2), (1, 1, 5)])
+def test_streaming_command_line(dy4, mode, stereo, per_call):
+    """dy4_project: the reference's `project <mode> <mono|stereo>` boundary (uint8 IQ on stdin, int16 PCM on stdout,
+    partial trailing block dropped, exit status 1 at end of input) over the throughput tier, one stream.  The bytes on
+    stdout must be the reference's for any blocks-per-call cadence."""
+    import os
+    import subprocess
+    exe = os.path.join(dy4.PACKAGE_DIR, "dy4_project")
+    assert os.path.exists(exe), "dy4_project not built (make -C csrc)"
+    iq = golden("mode%d_stereo.npz" % mode)["iq"]
+    want = golden("mode%d_%s.npz" % (mode, "stereo" if stereo else "mono"))["pcm"]
+    data = iq.tobytes() + b"\x80" * 1000                           # a partial trailing block: dropped (project.cpp:293-296)
+    p = subprocess.run([exe, str(mode), "stereo" if stereo else "mono", str(per_call)], input=data, capture_output=True, timeout=300)
+    assert p.returncode == 1, p.stderr[-500:]
+    assert b"End of input stream reached" in p.stderr
+    got = np.frombuffer(p.stdout, np.int16)
+    assert got.size == want.size and np.array_equal(got, want)
+    bad = subprocess.run([exe, "7", "stereo"], input=b"", capture_output=True, timeout=60)
+    assert bad.returncode == 1 and b"Wrong mode" in bad.stderr
