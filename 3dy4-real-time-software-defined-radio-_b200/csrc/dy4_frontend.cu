@@ -656,9 +656,9 @@ cudaError_t launch_stream(const Dy4FrontendArgs& a, cudaStream_t st)
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     // Segment length.  The ramp costs 100/D + 1 outputs per segment, so segments should be long; but the grid should
-    // also be ONE full wave of resident CTAs (a second, nearly empty wave leaves most SMs idle while it drains):
-    // give every stream the largest number of segments that still fits the resident thread count, never going below
-    // 64 outputs per segment (small launches then simply do not fill the machine).  A multiple of 8 keeps segment
+    // also be WHOLE waves of resident CTAs (a last, nearly empty wave leaves most SMs idle while it drains):
+    // give every stream the largest number of segments that still fits those waves, never going below 64 outputs per
+    // segment (small launches then simply do not fill the machine).  A multiple of 8 keeps segment
     // ends on 16-byte input and output groups.
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
@@ -668,7 +668,11 @@ cudaError_t launch_stream(const Dy4FrontendArgs& a, cudaStream_t st)
     }
     static const int forced = std::getenv("DY4_FE_SEG") ? atoi(std::getenv("DY4_FE_SEG")) : 0;
     const long long resident = (long long)sms * ctas_per_sm * 128;
-    const long long segs_fit = std::max<long long>(1, resident / a.n_streams);
+    // whole waves: with the longest useful segment (1024 outputs) the launch needs `waves` waves of resident threads;
+    // fill exactly that many with as many (hence as short as necessary) segments per stream as fit
+    const long long threads_min = (long long)a.n_streams * ((a.n_if + 1023) / 1024);
+    const long long waves = std::max<long long>(1, (threads_min + resident - 1) / resident);
+    const long long segs_fit = std::max<long long>(1, waves * resident / a.n_streams);
     int seg = (int)((a.n_if + segs_fit - 1) / segs_fit);
     seg = std::max(64, (seg + 7) & ~7);
     if (forced >= 8) seg = forced & ~7;
