@@ -187,24 +187,28 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
              const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
              const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
              int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
-             const float* __restrict__ taps_poly, int up_pad, int span_max, u64 nz, int K)
+             const float* __restrict__ taps_poly, int up_pad, int span_max, u64 nz, int K, int tiles_per_stream, int n_tiles)
 {
+    // Persistent CTAs: the 59 KB tap table is loaded ONCE per CTA and then tiles (stream, NT consecutive outputs) are
+    // walked in a grid-stride loop — re-loading the table per tile moved more bytes through L2 than the signal itself.
     const int NT = blockDim.x;                                              // 32 * K * groups outputs per tile
     extern __shared__ __align__(16) float sm_f[];
     constexpr int DELAY = DY4_NTAPS / 2;
     float* s_taps = sm_f;                                                   // [DY4_NTAPS][up_pad]
     float2* s_x = reinterpret_cast<float2*>(sm_f + DY4_NTAPS * up_pad);     // (delayed IF, mixed) over the tile's span
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * NT;
-    const int s = blockIdx.x;
+    for (int t = tid; t < DY4_NTAPS * up_pad / 4; t += NT)                  // up_pad is a multiple of 4
+        reinterpret_cast<float4*>(s_taps)[t] = __ldg(reinterpret_cast<const float4*>(taps_poly) + t);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int s = tile / tiles_per_stream;
+    const int m0 = (tile - s * tiles_per_stream) * NT;
+    __syncthreads();                                                        // table visible; the previous tile's span no longer read
     const float* row = if_in + (long long)s * if_stride;
     const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
     const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
     const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
     const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
 
-    for (int t = tid; t < DY4_NTAPS * up_pad / 4; t += NT)                  // up_pad is a multiple of 4
-        reinterpret_cast<float4*>(s_taps)[t] = __ldg(reinterpret_cast<const float4*>(taps_poly) + t);
     const int m_last = min(m0 + NT, n_audio) - 1;
     const int i_lo = ((int)(((long long)m0 * down) / up) - (DY4_NTAPS - 1)) & ~3;   // aligned down: 16-byte loads below
     const int i_hi = (int)(((long long)m_last * down) / up);
@@ -238,7 +242,7 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
 
     const int warp = tid >> 5, lane = tid & 31;
     const int m = m0 + 32 * K * (warp / K) + lane * K + (warp % K);
-    if (m >= n_audio) return;
+    if (m >= n_audio) continue;
     const long long n = (long long)m * down;
     const int phase = (int)(n % up);
     const int base = (int)(n / up) - i_lo;          // position of x[floor(mD/U)] in the span
@@ -260,6 +264,7 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
         if (audio) audio[(long long)s * audio_stride + m] = mono;
         if (pcm) pcm[(long long)s * pcm_stride + m] = pcm16(mono);
     }
+    }   // tile loop
 }
 
 template <int D, int R, int NT, bool EXACT, bool STEREO>
@@ -320,10 +325,18 @@ cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
     auto kern = k_audio_poly<NTMAX, EXACT, STEREO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid(a.n_streams, (a.n_audio + NT - 1) / NT);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    const int tiles_per_stream = (a.n_audio + NT - 1) / NT;
+    const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
+    if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)sms * std::max(per_sm, 1));
     kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
                                  a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
-                                 a.up, a.down, a.taps_poly, a.up_pad, span_max, a.neg_zero2, K);
+                                 a.up, a.down, a.taps_poly, a.up_pad, span_max, a.neg_zero2, K, tiles_per_stream, (int)n_tiles);
     g_dy4_launches++;
     return cudaGetLastError();
 }
