@@ -86,7 +86,9 @@ struct Dy4RdsArgs {
     long long m_first; int n_out;               // absolute index of the first resampler output of this chunk and their count
     double w, Kp, Ki, nco_scale, phase_adjust;
     int up, down;
+    int span_max;                               // set by the launcher: pairs of shared memory reserved for a tile's samples
 };
+cudaError_t dy4_upload_taps_rrc(const float* rrc);                            // 101 RRC taps -> constant memory (per device)
 cudaError_t dy4_launch_rds_pll(const Dy4RdsArgs& a, cudaStream_t st);        // carrier -> theta -> nco_i / nco_q
 cudaError_t dy4_launch_rds_resample(const Dy4RdsArgs& a, cudaStream_t st);   // delay, mix, 19/120 resampler, RRC, tails
 

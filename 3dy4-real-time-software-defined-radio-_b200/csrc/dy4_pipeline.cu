@@ -539,6 +539,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
         for (int k = 0; k < DY4_NTAPS; k++) rrc[k] = (float)r[k];
         CU(cudaMalloc(&p->d_rds_poly, poly.size() * sizeof(float)));
         CU(cudaMemcpy(p->d_rds_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(dy4_upload_taps_rrc(rrc.data()));
         CU(cudaMalloc(&p->d_rds_rrc, rrc.size() * sizeof(float)));
         CU(cudaMemcpy(p->d_rds_rrc, rrc.data(), rrc.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&p->rds_tail, S * DY4_IF_TAIL * sizeof(float)));

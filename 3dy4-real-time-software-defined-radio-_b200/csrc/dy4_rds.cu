@@ -121,17 +121,22 @@ k_rds_resample(Dy4RdsArgs a)
         }
         sm_mix[p] = v;
     }
+    // the polyphase table [tap][phase] (101 x 20 floats) next to the samples in shared memory
+    float* s_taps = reinterpret_cast<float*>(sm_mix + a.span_max);
+    for (int t = tid; t < DY4_NTAPS * a.up_pad; t += NT) s_taps[t] = __ldg(a.taps_poly + t);
     __syncthreads();
     const int j = j0 + tid;
     if (j >= a.n_out) return;
     const long long m = a.m_first + j, n = m * a.down;
     const int phase = (int)(n % a.up);
     const int base = (int)(n / a.up - a.if_abs - i_lo);
+    const u64* xs = reinterpret_cast<const u64*>(sm_mix) + base;
+    const float* hp = s_taps + phase;
     u64 acc = 0ull;
-#pragma unroll 4
+#pragma unroll 8
     for (int t = 0; t < DY4_NTAPS; t++) {
-        const float h = __ldg(a.taps_poly + t * a.up_pad + phase);
-        acc = ffma2(f2_as_u64(sm_mix[base - t]), pk2(h, h), acc);
+        const float h = hp[t * a.up_pad];
+        acc = ffma2(xs[-t], pk2(h, h), acc);
     }
     float yi, yq;
     upk2(acc, yi, yq);
@@ -139,24 +144,51 @@ k_rds_resample(Dy4RdsArgs a)
     lp[j] = yi; lp[a.lp_stride + j] = yq;
 }
 
-// RRC: 101-tap FIR at the resampler's output rate, I and Q; history from lp_tail
-__global__ void __launch_bounds__(128)
+// RRC: 101-tap FIR at the resampler's output rate on the (I, Q) pair; history from lp_tail.  A tile of NT*R outputs
+// plus its 100-sample history is staged in shared memory as (I, Q) pairs; every thread keeps R consecutive outputs in
+// registers and walks its window once, newest sample first (taps ascending), one packed FFMA2 per tap and output.
+__constant__ float2 c_rrc2[DY4_NTAPS + 3];       // (h, h) pairs of the RRC taps
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT)
 k_rds_rrc(Dy4RdsArgs a)
 {
-    const int s = blockIdx.x, j = blockIdx.y * blockDim.x + threadIdx.x;
-    if (j >= a.n_out) return;
+    constexpr int T = NT * R, HALO = DY4_NTAPS - 1;
+    __shared__ __align__(16) float2 sm[T + HALO + 2 * ((T + HALO) / R) + 8];
+    const int s = blockIdx.x, tid = threadIdx.x, j0 = blockIdx.y * T;
     const float* lp = a.lp + (long long)s * 2 * a.lp_stride;
     const float* lt = a.lp_tail + (long long)s * 2 * DY4_MIX_TAIL;
-    float ai = 0.f, aq = 0.f;
-    for (int k = 0; k < DY4_NTAPS; k++) {
-        const int i = j - k;
-        const float h = __ldg(a.taps_rrc + k);
-        const float xi = i >= 0 ? lp[i] : lt[DY4_MIX_TAIL + i];
-        const float xq = i >= 0 ? lp[a.lp_stride + i] : lt[2 * DY4_MIX_TAIL + i];
-        ai = fmaf(h, xi, ai); aq = fmaf(h, xq, aq);
+    for (int p = tid; p < T + HALO; p += NT) {                    // logical pair p <-> sample j0 - HALO + p
+        const int i = j0 - HALO + p;
+        float2 v;
+        if (i < 0) v = make_float2(lt[DY4_MIX_TAIL + i], lt[2 * DY4_MIX_TAIL + i]);
+        else if (i < a.n_out) v = make_float2(lp[i], lp[a.lp_stride + i]);
+        else v = make_float2(0.f, 0.f);
+        sm[p + 2 * (p / R)] = v;                                  // two pad pairs per R: neighbouring threads' loads on distinct banks
     }
-    a.out_i[(long long)s * a.out_stride + j] = ai;
-    a.out_q[(long long)s * a.out_stride + j] = aq;
+    __syncthreads();
+    // output r of this thread is sample j0 + tid*R + r; tap k reads logical pair tid*R + r + HALO - k = tid*R + q, q = r + HALO - k
+    const u64* w = reinterpret_cast<const u64*>(sm) + (R + 2) * tid;
+    const u64* hh = reinterpret_cast<const u64*>(c_rrc2);
+    u64 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int q = R - 1 + HALO; q >= 0; q--) {
+        const u64 x = w[q + 2 * (q / R)];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r + HALO - q;
+            if (k >= 0 && k < DY4_NTAPS) acc[r] = ffma2(x, hh[k], acc[r]);
+        }
+    }
+    float* oi = a.out_i + (long long)s * a.out_stride;
+    float* oq = a.out_q + (long long)s * a.out_stride;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = j0 + tid * R + r;
+        if (j < a.n_out) { float yi, yq; upk2(acc[r], yi, yq); oi[j] = yi; oq[j] = yq; }
+    }
 }
 
 // carry: last 128 mixed I/Q samples, last 128 resampler outputs, NCO state
@@ -360,6 +392,13 @@ cudaError_t dy4_launch_rds_decode(const Dy4RdsDecodeArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+cudaError_t dy4_upload_taps_rrc(const float* rrc)
+{
+    float2 h[DY4_NTAPS + 3] = {};
+    for (int k = 0; k < DY4_NTAPS; k++) h[k] = make_float2(rrc[k], rrc[k]);
+    return cudaMemcpyToSymbol(c_rrc2, h, sizeof(h));
+}
+
 cudaError_t dy4_launch_rds_pll(const Dy4RdsArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
@@ -382,11 +421,14 @@ cudaError_t dy4_launch_rds_resample(const Dy4RdsArgs& a, cudaStream_t st)
         constexpr int NT = 128;
         const int span_max = (int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 4;
         dim3 grid(a.n_streams, (a.n_out + NT - 1) / NT);
-        k_rds_resample<NT><<<grid, NT, span_max * sizeof(float2), st>>>(a);
+        Dy4RdsArgs b = a;
+        b.span_max = span_max;
+        k_rds_resample<NT><<<grid, NT, span_max * sizeof(float2) + DY4_NTAPS * a.up_pad * sizeof(float), st>>>(b);
         g_dy4_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        dim3 g2(a.n_streams, (a.n_out + 127) / 128);
-        k_rds_rrc<<<g2, 128, 0, st>>>(a);
+        constexpr int RR = 4, RNT = 128;
+        dim3 g2(a.n_streams, (a.n_out + RR * RNT - 1) / (RR * RNT));
+        k_rds_rrc<RR, RNT><<<g2, RNT, 0, st>>>(a);
         g_dy4_launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
