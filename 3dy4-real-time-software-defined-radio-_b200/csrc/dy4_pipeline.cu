@@ -194,7 +194,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.inv, 2 * bytes));
         }
     }
-    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, (size_t)p->n_streams * sizeof(float)));
+    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 2 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set
     if (p->stereo && !p->s_pll) {
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -355,16 +355,18 @@ int run_rds(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
 }
 
 // the serial part, on its own stream: pilot -> NCO row
-int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
+// `parts`: the reciprocal pre-pass rides at the end of front(c) and the NCO pass at the start of back(c), both on the
+// main stream; only the serial loop is queued on the PLL stream, so consecutive loops run back to back there.
+int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
 {
     const dy4_mode_params_t& m = p->mp;
     auto& w = p->ws[c.set];
     Dy4PllArgs pa;
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
-    pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0;
+    pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
     pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
-    { Timer t(p, DY4_K_PLL, st); CU(dy4_launch_pll(pa, st)); }
+    { Timer t(p, (parts & DY4_PLL_LOOP) ? DY4_K_PLL : DY4_K_PLL_AUX, st); CU(dy4_launch_pll_parts(pa, st, parts)); }
     return DY4_OK;
 }
 
@@ -468,6 +470,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
         if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
+        if ((rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
             CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
@@ -476,10 +479,11 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
         CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
-        if ((rc = run_pll(p, c, p->s_pll))) return rc;
+        if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_LOOP))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
         if (have_prev) {
             CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
+            if ((rc = run_pll(p, prev, st, DY4_PLL_NCO))) return rc;
             if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
             if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
         }
@@ -487,6 +491,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     }
     if (have_prev) {
         CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
+        if ((rc = run_pll(p, prev, st, DY4_PLL_NCO))) return rc;
         if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
         if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
     }

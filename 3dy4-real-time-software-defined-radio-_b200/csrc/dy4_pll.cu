@@ -198,7 +198,11 @@ k_pll_prep(const float* __restrict__ in, long long in_stride, double* __restrict
 
 }  // namespace
 
-cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
+cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st) { return dy4_launch_pll_parts(a, st, DY4_PLL_PREP | DY4_PLL_LOOP | DY4_PLL_NCO); }
+
+// The three passes can be queued on different streams: only the serial loop belongs on the PLL stream, its
+// data-parallel pre-pass (reciprocals) and post-pass (NCO row) ride with the FIR kernels (dy4_pipeline.cu).
+cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts)
 {
     if (a.n <= 0 || a.n_streams <= 0) return cudaSuccess;
     PllConst c;
@@ -211,7 +215,7 @@ cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
     c.ncoScale = a.ncoScale;
     c.phaseAdjust = a.phaseAdjust;
     static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
-    {
+    if (parts & DY4_PLL_PREP) {
         dim3 gp(a.n_streams, (a.n + 255) / 256);
         k_pll_prep<<<gp, 256, 0, st>>>(a.in, a.in_stride, a.inv, a.wide_stride, a.n);
         g_dy4_launches++;
@@ -221,14 +225,18 @@ cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st)
     // DY4_PLL_NARROW=f2f selects the plain double->float->double narrowing of trigArg instead of the
     // magic-constant rounding inside a tracked binade (A/B knob; results are identical, see tests).
     static const bool f2f = std::getenv("DY4_PLL_NARROW") && std::string(std::getenv("DY4_PLL_NARROW")) == "f2f";
-    const dim3 g((a.n_streams + threads - 1) / threads);
-    if (f2f) k_pll<0, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
-    else k_pll<2, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
-    g_dy4_launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    dim3 grid(a.n_streams, (a.n + 255) / 256);
-    k_nco<<<grid, 256, 0, st>>>(a.theta, a.wide_stride, a.nco0, a.nco, a.nco_stride, a.n, a.ncoScale, a.phaseAdjust);
-    g_dy4_launches++;
+    if (parts & DY4_PLL_LOOP) {
+        const dim3 g((a.n_streams + threads - 1) / threads);
+        if (f2f) k_pll<0, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
+        else k_pll<2, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
+        g_dy4_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (parts & DY4_PLL_NCO) {
+        dim3 grid(a.n_streams, (a.n + 255) / 256);
+        k_nco<<<grid, 256, 0, st>>>(a.theta, a.wide_stride, a.nco0, a.nco, a.nco_stride, a.n, a.ncoScale, a.phaseAdjust);
+        g_dy4_launches++;
+    }
     return cudaGetLastError();
 }

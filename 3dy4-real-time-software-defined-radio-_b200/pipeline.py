@@ -14,7 +14,7 @@ from .modes import mode_params
 FLAG_EXACT_AUDIO = 1
 FLAG_DEBUG_ROWS = 2
 FLAG_RDS = 4
-KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails", "rds_bpf", "rds_pll", "rds_baseband")
+KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails", "rds_bpf", "rds_pll", "rds_baseband", "pll_aux")
 
 
 def launch_count():

@@ -286,9 +286,10 @@ def run_gpu_arm(args):
     alg = {
         "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
         "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
-        "pll": {"bytes": 8 / rd, "mac": 0.0},
+        "pll": {"bytes": 20 / rd, "mac": 0.0},           # pilot 4 + reciprocal 8 in, phase row 8 out per IF sample
         "audio": {"bytes": 12 / rd + 4 / ad, "mac": 2 * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
+        "pll_aux": {"bytes": 24 / rd, "mac": 0.0},       # reciprocals (4 in, 8 out) and NCO row (8 in, 4 out) per IF sample
         # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
         "rds_bpf": {"bytes": 16 / rd, "mac": 2 * 101 / rd},
         "rds_pll": {"bytes": 28 / rd, "mac": 0.0},
@@ -336,10 +337,11 @@ def run_gpu_arm(args):
     pll = kernels.get("pll")
     pll_info = None
     if pll:
-        pll_info = {"share_of_step": pll["share"], "avg_launch_ms": pll["avg_ms"],
-                    "ns_per_sample_per_stream": round(pll["avg_ms"] * 1e6 / n_if, 2),
-                    "stream_samples_per_s": round(S * n_if / (pll["avg_ms"] * 1e-3), 0),
-                    "note": "serial recurrence per stream, one thread per stream: bound by FP64 libm latency, not FLOPs or bytes"}
+        pll_ms_per_step = prof["pll"]["ms"] / args.steps           # the serial loops of all sub-chunks of a step
+        pll_info = {"share_of_step": pll["share"], "avg_launch_ms": pll["avg_ms"], "ms_per_step": round(pll_ms_per_step, 3),
+                    "ns_per_sample_per_stream": round(pll_ms_per_step * 1e6 / n_if, 2),
+                    "stream_samples_per_s": round(S * n_if / (pll_ms_per_step * 1e-3), 0),
+                    "note": "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
 
     # ---- CPU baseline: the reference's own code on the host cores, bounded sample (N=1 only) ----------------
     cpu = None

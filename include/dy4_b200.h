@@ -198,15 +198,16 @@ int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pilot, const f
 
 /* Per-kernel timing with CUDA events on the launch stream.  enable!=0 turns it on.
  * get: ms[] and launches[] have DY4_NUM_KERNELS entries, accumulated since the last reset. */
-#define DY4_NUM_KERNELS 8
+#define DY4_NUM_KERNELS 9
 #define DY4_K_FRONTEND 0
 #define DY4_K_BPF 1
-#define DY4_K_PLL 2
+#define DY4_K_PLL 2           /* the serial loop only */
 #define DY4_K_AUDIO 3
 #define DY4_K_TAILS 4
 #define DY4_K_RDS_BPF 5       /* RDS: the two band-pass launches */
 #define DY4_K_RDS_PLL 6       /* RDS: carrier PLL + NCO rows */
 #define DY4_K_RDS_BASEBAND 7  /* RDS: mix + 19/120 resampler + RRC + carry + symbol/bit/frame decoding */
+#define DY4_K_PLL_AUX 8       /* the PLL's data-parallel passes (reciprocals before, NCO row after), on the main stream */
 int dy4_pipeline_profile(dy4_pipeline_t* p, int enable);
 int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long* launches, int reset);
 /* total kernels launched by this library in this process */
