@@ -251,7 +251,7 @@ int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_o
     Dy4FrontendArgs fa;
     fa.iq = c.iq; fa.row_stride = (long long)row_stride; fa.iq_tail = p->iq_tail;
     fa.if_out = w.w_if; fa.if_stride = (long long)p->ws_stride; fa.n_if = n_if; fa.n_streams = p->n_streams;
-    fa.rf_decim = m.rf_decim; fa.exact = 1; fa.taps_g = p->d_rf_taps; fa.mode = p->mode; fa.neg_zero2 = kNegZero2;
+    fa.rf_decim = m.rf_decim; fa.exact = (p->stereo || (p->flags & DY4_FLAG_EXACT_AUDIO)) ? 1 : 0; /* the PLL needs a bit-exact IF; mono does not */ fa.taps_g = p->d_rf_taps; fa.mode = p->mode; fa.neg_zero2 = kNegZero2;
     { Timer t(p, DY4_K_FRONTEND, st); CU(dy4_launch_frontend(fa, st)); }
     if (c.d_if) CU(cudaMemcpy2DAsync(c.d_if, if_out_stride * sizeof(float), w.w_if, p->ws_stride * sizeof(float),
                                      (size_t)n_if * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));

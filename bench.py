@@ -156,9 +156,10 @@ class ClockSampler(threading.Thread):
 
 def workload_config():
     return {
-        "workload": "%smode %d stereo FM (8-bit IQ -> IF -> L/R int16 PCM), %d independent synthetic streams per GPU x %d blocks"
-                    % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU) == (0, 256) else "", MODE, STREAMS_PER_GPU, BLOCKS_PER_STREAM),
-        "mode": MODE, "stereo": True, "rds": RDS, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
+        "workload": "%smode %d %s FM (8-bit IQ -> IF -> %s int16 PCM), %d independent synthetic streams per GPU x %d blocks"
+                    % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU, STEREO) == (0, 256, 1) else "", MODE, "stereo" if STEREO else "mono",
+                       "L/R" if STEREO else "mono", STREAMS_PER_GPU, BLOCKS_PER_STREAM),
+        "mode": MODE, "stereo": bool(STEREO), "rds": RDS, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
         "input_bytes_per_gpu": STREAMS_PER_GPU * BLOCKS_PER_STREAM * {0: 102400, 1: 81920, 2: 160000, 3: 128000}[MODE],
         "l2": "inputs are larger than the 126 MB L2 (see input_bytes_per_gpu); no flush needed",
         "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32, f64 libm in the PLL); "
@@ -191,7 +192,8 @@ def run_gpu_arm(args):
     if S > 512:                                      # very large batches: tile 512 distinct streams (generation time, not a kernel matter)
         d_iq = d_iq.repeat((S + 511) // 512, 1)[:S].contiguous()
     pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, rds=RDS)
-    out = {"pcm": torch.empty((S, n_audio * 2), dtype=torch.int16, device=dev)}
+    nch = 2 if STEREO else 1
+    out = {"pcm": torch.empty((S, n_audio * nch), dtype=torch.int16, device=dev)}
     max_steps_between_resets = max(1, int(55.0 / (nb * (m.block_size / 2) / m.rf_Fs)))   # float PLL sample counter saturates at 2^24 (~69.9 s)
 
     def step(i):
@@ -233,7 +235,7 @@ def run_gpu_arm(args):
     # ---- end to end through the public host API: pinned host input, H2D + kernels + D2H PCM every step -----
     h_iq = torch.empty((S, nb * m.block_size), dtype=torch.uint8).pin_memory()
     h_iq.copy_(d_iq)
-    h_pcm = torch.empty((S, n_audio * 2), dtype=torch.int16).pin_memory()
+    h_pcm = torch.empty((S, n_audio * nch), dtype=torch.int16).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
     pipe.reset()
     pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)   # warm-up (allocates staging)
@@ -287,7 +289,7 @@ def run_gpu_arm(args):
         "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
         "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
         "pll": {"bytes": 20 / rd, "mac": 0.0},           # pilot 4 + reciprocal 8 in, phase row 8 out per IF sample
-        "audio": {"bytes": 12 / rd + 4 / ad, "mac": 2 * 101 / ad},
+        "audio": {"bytes": (12 if STEREO else 4) / rd + 4 / ad, "mac": (2 if STEREO else 1) * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
         "pll_aux": {"bytes": 24 / rd, "mac": 0.0},       # reciprocals (4 in, 8 out) and NCO row (8 in, 4 out) per IF sample
         # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
@@ -314,18 +316,19 @@ def run_gpu_arm(args):
             avg = v["ms"] / v["launches"]
             tf = 2 * alg[k]["mac"] * pairs_per_step / (avg * 1e-3) / 1e12
             isolated[k] = {"avg_ms": round(avg, 4), "fp32_TFLOPs": round(tf, 2), "frac_of_fma_peak": round(tf / FP32_PEAK_TFLOPS_NOMINAL, 4)}
-            if k in ("frontend", "twin_bpf"):        # the two bit-exact kernels
+            if k in ("frontend", "twin_bpf") and STEREO:        # the two bit-exact kernels
                 isolated[k]["frac_of_exact_ceiling"] = round(tf / EXACT_MAC_CEILING_TFLOPS, 4)
     roofline = {
         "kernel": "k_frontend_stream (packed uint8 IQ -> 101-tap decimating FIR on I,Q in transposed form -> FM discriminator)",
         "bound": "fp32", "achieved": fe["fp32_TFLOPs"], "peak": round(FP32_PEAK_TFLOPS_NOMINAL, 2), "unit": "TFLOP/s",
         "frac": round(fe["fp32_TFLOPs"] / FP32_PEAK_TFLOPS_NOMINAL, 4),
         "peak_source": "148 SMs x 128 FP32 lanes x 2 x 1.965 GHz; tools/ubench measures 71.6 TFLOP/s FFMA on this pool",
-        "note": "bit-exact arithmetic (unfused multiply then add) costs two packed FP32 instructions per pair of MACs, both on the fmaheavy pipe: "
-                "the measured ceiling of that instruction pair is %.1f TFLOP/s (tools/ubench.cu exact2, profiles/ubench_r1b.txt), frac %.2f" % (
-                    EXACT_MAC_CEILING_TFLOPS, EXACT_MAC_CEILING_TFLOPS / FP32_PEAK_TFLOPS_NOMINAL),
-        "exact_mac_ceiling": EXACT_MAC_CEILING_TFLOPS,
-        "frac_of_exact_ceiling": round(fe["fp32_TFLOPs"] / EXACT_MAC_CEILING_TFLOPS, 4),
+        "note": ("bit-exact arithmetic (unfused multiply then add) costs two packed FP32 instructions per pair of MACs, both on the fmaheavy pipe: "
+                 "the measured ceiling of that instruction pair is %.1f TFLOP/s (tools/ubench.cu exact2, profiles/ubench_r1b.txt), frac %.2f" % (
+                     EXACT_MAC_CEILING_TFLOPS, EXACT_MAC_CEILING_TFLOPS / FP32_PEAK_TFLOPS_NOMINAL)) if STEREO else
+                "mono receiver: nothing chaotic downstream, so the front end's multiply-add is fused (one FFMA2 per tap and I/Q pair); the ceiling is the FMA peak",
+        "exact_mac_ceiling": EXACT_MAC_CEILING_TFLOPS if STEREO else None,
+        "frac_of_exact_ceiling": round(fe["fp32_TFLOPs"] / EXACT_MAC_CEILING_TFLOPS, 4) if STEREO else None,
         "hbm": {"achieved": fe["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(fe["GBps"] / hbm_peak, 4), "peak_source": hbm_src},
         "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"],
         "algorithmic_bytes": int(alg["frontend"]["bytes"] * pairs_per_step),
@@ -357,7 +360,7 @@ def run_gpu_arm(args):
         "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": S * nb * m.block_size,
-                "d2h_bytes_per_step": S * n_audio * 2 * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+                "d2h_bytes_per_step": S * n_audio * nch * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
                 "timing": "host clock around the synchronous process_host() calls, max over ranks",
                 "pcm_equals_device_path": pcm_matches},
         "gpu_launches": total_launches,
@@ -369,7 +372,7 @@ def run_gpu_arm(args):
 
 
 def main():
-    global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS
+    global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS, STEREO
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -380,9 +383,11 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: BASELINE configs[1], 256)")
     ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STREAM, help="blocks per stream per step (default 47 = 1.003 s)")
     ap.add_argument("--mode", type=int, default=MODE, help="receiver mode 0..3 (default 0)")
+    ap.add_argument("--mono", action="store_true", help="mono receiver (BASELINE configs[0]'s path: no pilot / PLL / L-R branch)")
     ap.add_argument("--rds", action="store_true", help="BASELINE configs[3]: also run the RDS path (mode 0 stereo; e.g. --streams 4096 --blocks 6)")
     args = ap.parse_args()
     STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS = args.streams, args.blocks, args.mode, args.rds
+    STEREO = 0 if args.mono else 1
     args.warmup = max(args.warmup, 3) if args.impl == "dy4" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -121,9 +121,10 @@ int dy4_psd_batch(const float* d_samples, size_t row_stride, int n_streams, size
 /* ---- throughput tier: batched receiver ----------------------------------- */
 typedef struct dy4_pipeline dy4_pipeline_t;
 
-#define DY4_FLAG_EXACT_AUDIO 1u   /* also run the stages the PLL never sees (stereo-band BPF, resamplers)
-                                     with unfused multiply-add: every output is then bit-identical to
-                                     the reference instead of within ~1e-7 (default: fused where safe) */
+#define DY4_FLAG_EXACT_AUDIO 1u   /* also run the stages the PLL never sees (stereo-band BPF, resamplers; in a MONO
+                                     receiver the RF front end too) with unfused multiply-add: every output is then
+                                     bit-identical to the reference instead of within ~1e-7 (default: fused where
+                                     nothing chaotic is downstream; a stereo receiver's IF is always bit-identical) */
 
 #define DY4_FLAG_DEBUG_ROWS 2u    /* keep each process call in ONE sub-chunk so that dy4_pipeline_debug_buffers() returns
                                      whole pilot / NCO rows (diagnostics; disables the PLL/FIR overlap) */
