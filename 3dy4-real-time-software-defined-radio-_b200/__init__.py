@@ -21,8 +21,9 @@ from .modes import mode_params, ModeParams  # noqa: F401
 from .pipeline import Pipeline, launch_count  # noqa: F401
 from . import filterh  # noqa: F401
 from . import fourierh  # noqa: F401
+from . import rds_app  # noqa: F401
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401
 
 PACKAGE_DIR = _os.path.dirname(_os.path.abspath(__file__))
-__all__ = ["lib", "Dy4Error", "Pipeline", "mode_params", "ModeParams", "filterh", "fourierh", "synth", "launch_count", "build_library"]
+__all__ = ["lib", "Dy4Error", "Pipeline", "mode_params", "ModeParams", "filterh", "fourierh", "rds_app", "synth", "launch_count", "build_library"]

@@ -70,7 +70,7 @@ def _load():
         "dy4_pinned_free": (None, [vp]),
         "dy4_pipeline_rds_read": (i, [vp, vp, vp, sz, C.POINTER(i), vp]),
         "dy4_pipeline_rds_bounds": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
-        "dy4_pipeline_rds_drain": (i, [vp, vp, sz, vp, sz, vp, sz, vp]),
+        "dy4_pipeline_rds_drain": (i, [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp]),
         "dy4_pipeline_debug_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), psz, C.POINTER(i)]),
         "dy4_pipeline_profile": (i, [vp, i]),
         "dy4_pipeline_profile_get": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]),

@@ -97,14 +97,15 @@ cudaError_t dy4_launch_rds_resample(const Dy4RdsArgs& a, cudaStream_t st);   // 
 // RDS back half (model/fmSupportLib.py:209-247, model/fmMonoBlock.py:78-284, 699-730): one thread per stream walks whole
 // model blocks of DY4_RDS_BLOCK in-phase RRC samples: symbol timing, Manchester + differential decoding, frame sync.
 constexpr int DY4_RDS_BLOCK = 3040;            // 16 samples/symbol x 190 symbols = 19 200 IF samples x 19/120
-constexpr int DY4_RDS_STATE_INTS = 16;
+constexpr int DY4_RDS_STATE_INTS = 20;
 struct Dy4RdsDecodeArgs {
     const float* acc; long long acc_stride; int n_blocks;      // n_blocks whole model blocks at the start of every row
     int* state;                                                // [n_streams][DY4_RDS_STATE_INTS]
-    int* counts;                                               // [n_streams][4]: symbols, bits, events written so far
+    int* counts;                                               // [n_streams][4]: symbols, bits, events, groups written so far
     int8_t* sym; long long sym_stride; int sym_cap;
     int8_t* bits; long long bits_stride; int bits_cap;
     int* events; long long ev_stride; int ev_cap;              // 4 ints per event: type (A,B,C,C',D = 0..4), bit position, false-positive flag, 16-bit word
+    int* groups; long long grp_stride; int grp_cap;            // 4 ints per complete group handed to the application layer: the A, B, C, D words
     int n_streams;
 };
 cudaError_t dy4_launch_rds_append(const float* rrc_i, long long rrc_stride, int n_new, float* acc, long long acc_stride,

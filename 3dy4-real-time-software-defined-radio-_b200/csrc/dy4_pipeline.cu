@@ -62,9 +62,9 @@ struct dy4_pipeline {
     size_t rds_cap = 0, rds_out_cap = 0; int rds_n_out = 0, rds_call_n = 0; long long if_abs = 0;   // rds_out: the whole call's RRC rows; rds_call_n of them so far
     // RDS back half: accumulation rows of in-phase RRC samples, decoder state, growing output rows
     float* rds_acc = nullptr; size_t rds_acc_cap = 0; int rds_left = 0, rds_consumed = 0;
-    int *rds_dec_state = nullptr, *rds_counts = nullptr, *rds_events = nullptr;
+    int *rds_dec_state = nullptr, *rds_counts = nullptr, *rds_events = nullptr, *rds_groups = nullptr;
     int8_t *rds_sym = nullptr, *rds_bits = nullptr;
-    size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0;
+    size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0, rds_grp_cap = 0;
     long long rds_blocks_since_drain = 0;
     cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
@@ -146,7 +146,11 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
         for (size_t s = 0; s < S; s++) { d[s * 8 + 4] = 1.0; d[s * 8 + 5] = 1.0; }   // ncoState = q_ncoState = 1.0 (fmMonoBlock.py:455,459)
         CU(cudaMemcpyAsync(p->rds_pll_state, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         std::vector<int> ds(S * DY4_RDS_STATE_INTS, 0);
-        for (size_t s = 0; s < S; s++) { ds[s * DY4_RDS_STATE_INTS + 7] = 24; ds[s * DY4_RDS_STATE_INTS + 9] = -1; }   // window_index = 24, offsetState = '' (fmMonoBlock.py:580,592)
+        for (size_t s = 0; s < S; s++) {
+            int* d = &ds[s * DY4_RDS_STATE_INTS];
+            d[7] = 24; d[9] = -1;                                  // window_index = 24, offsetState = '' (fmMonoBlock.py:580,592)
+            d[15] = d[16] = d[17] = d[18] = -1;                    // msgs.a .. msgs.d = [] (:596-600)
+        }
         CU(cudaMemcpyAsync(p->rds_dec_state, ds.data(), ds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(p->rds_counts, 0, S * 4 * sizeof(int), st));
         p->rds_left = 0; p->rds_consumed = 0; p->rds_blocks_since_drain = 0;
@@ -304,12 +308,14 @@ int run_rds_decode(dy4_pipeline* p, cudaStream_t st)
     if ((rc = grow_rows(p->rds_sym, p->rds_sym_cap, need_sym, S, 1, st))) return rc;
     if ((rc = grow_rows(p->rds_bits, p->rds_bits_cap, need_bits, S, 1, st))) return rc;
     if ((rc = grow_rows(p->rds_events, p->rds_ev_cap, need_bits, S, 4, st))) return rc;    // at most one event per window, one window per bit
+    if ((rc = grow_rows(p->rds_groups, p->rds_grp_cap, need_bits, S, 4, st))) return rc;   // likewise one group per window at most
     Dy4RdsDecodeArgs da{};
     da.acc = p->rds_acc; da.acc_stride = (long long)p->rds_acc_cap; da.n_blocks = nblk;
     da.state = p->rds_dec_state; da.counts = p->rds_counts;
     da.sym = p->rds_sym; da.sym_stride = (long long)p->rds_sym_cap; da.sym_cap = (int)p->rds_sym_cap;
     da.bits = p->rds_bits; da.bits_stride = (long long)p->rds_bits_cap; da.bits_cap = (int)p->rds_bits_cap;
     da.events = p->rds_events; da.ev_stride = (long long)p->rds_ev_cap; da.ev_cap = (int)p->rds_ev_cap;
+    da.groups = p->rds_groups; da.grp_stride = (long long)p->rds_grp_cap; da.grp_cap = (int)p->rds_grp_cap;
     da.n_streams = p->n_streams;
     CU(dy4_launch_rds_decode(da, st));
     return DY4_OK;
@@ -582,7 +588,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->d_rf_taps); cudaFree(p->d_taps_poly);
     cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
     cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
-    cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
+    cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_groups); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
     if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); }
@@ -745,7 +751,7 @@ extern "C" int dy4_pipeline_rds_bounds(dy4_pipeline_t* p, int* max_symbols, int*
 }
 
 extern "C" int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size_t sym_stride, int8_t* h_bits, size_t bits_stride,
-                                      int32_t* h_events, size_t ev_stride, int32_t* h_counts)
+                                      int32_t* h_events, size_t ev_stride, int32_t* h_groups, size_t grp_stride, int32_t* h_counts)
 {
     if (!p || !(p->flags & DY4_FLAG_RDS) || !h_counts) { dy4_set_error("dy4_pipeline_rds_drain: pipeline was not created with DY4_FLAG_RDS"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
@@ -753,17 +759,19 @@ extern "C" int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size
     const size_t S = (size_t)p->n_streams;
     int ms, mb, me;
     dy4_pipeline_rds_bounds(p, &ms, &mb, &me);
-    if ((h_symbols && sym_stride < (size_t)ms) || (h_bits && bits_stride < (size_t)mb) || (h_events && ev_stride < (size_t)me)) {
+    if ((h_symbols && sym_stride < (size_t)ms) || (h_bits && bits_stride < (size_t)mb) || (h_events && ev_stride < (size_t)me) ||
+        (h_groups && grp_stride < (size_t)me)) {
         dy4_set_error("dy4_pipeline_rds_drain: row strides smaller than dy4_pipeline_rds_bounds");
         return DY4_ERR_ARG;
     }
     std::vector<int> c(S * 4);
     CU(cudaMemcpy(c.data(), p->rds_counts, c.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    for (size_t s = 0; s < S; s++) for (int j = 0; j < 3; j++) h_counts[s * 3 + j] = c[s * 4 + j];
+    for (size_t s = 0; s < S; s++) for (int j = 0; j < 4; j++) h_counts[s * 4 + j] = c[s * 4 + j];
     if (p->rds_blocks_since_drain > 0) {
         if (h_symbols) CU(cudaMemcpy2D(h_symbols, sym_stride, p->rds_sym, p->rds_sym_cap, (size_t)ms, S, cudaMemcpyDeviceToHost));
         if (h_bits) CU(cudaMemcpy2D(h_bits, bits_stride, p->rds_bits, p->rds_bits_cap, std::min((size_t)mb, p->rds_bits_cap), S, cudaMemcpyDeviceToHost));
         if (h_events) CU(cudaMemcpy2D(h_events, ev_stride * 16, p->rds_events, p->rds_ev_cap * 16, std::min((size_t)me, p->rds_ev_cap) * 16, S, cudaMemcpyDeviceToHost));
+        if (h_groups) CU(cudaMemcpy2D(h_groups, grp_stride * 16, p->rds_groups, p->rds_grp_cap * 16, std::min((size_t)me, p->rds_grp_cap) * 16, S, cudaMemcpyDeviceToHost));
     }
     CU(cudaMemset(p->rds_counts, 0, S * 4 * sizeof(int)));
     p->rds_blocks_since_drain = 0;

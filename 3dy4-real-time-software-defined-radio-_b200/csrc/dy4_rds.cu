@@ -225,7 +225,7 @@ k_rds_finish(Dy4RdsArgs a)
 // restatement in oracle/rds.py).  Serial, branchy and tiny: one thread per stream.
 constexpr int RB_SPS = 16, RB_BLOCK = DY4_RDS_BLOCK, RB_NSYM = RB_BLOCK / RB_SPS, RB_MAXBITS = (RB_NSYM + 1) / 2;
 enum { RS_BLOCK = 0, RS_MIDX, RS_FOUND, RS_SYMSTATE, RS_ERR1, RS_ERR2, RS_BITSTATE, RS_WINDEX, RS_SYNCED, RS_OFFSET,
-       RS_NUMSYNCED, RS_BITPOS, RS_LASTPOS, RS_WSTATE_LEN, RS_WSTATE, RS_PAD };   // DY4_RDS_STATE_INTS = 16
+       RS_NUMSYNCED, RS_BITPOS, RS_LASTPOS, RS_WSTATE_LEN, RS_WSTATE, RS_MSG_A, RS_MSG_B, RS_MSG_C, RS_MSG_D, RS_PAD };   // DY4_RDS_STATE_INTS = 20
 
 // rows of the parity-check matrix as masks over the 26-bit window, window element j = bit j (fmMonoBlock.py:183-192)
 __constant__ unsigned c_rds_rows[10] = {
@@ -246,7 +246,9 @@ k_rds_decode(Dy4RdsDecodeArgs a)
     int synced = st[RS_SYNCED], offset_state = st[RS_OFFSET], num_synced = st[RS_NUMSYNCED], bit_pos = st[RS_BITPOS];
     int last_pos = st[RS_LASTPOS], wstate_len = st[RS_WSTATE_LEN];
     unsigned wstate = (unsigned)st[RS_WSTATE];                   // the previous bits' last 25, element j = bit j
-    int n_sym = cnt[0], n_bits = cnt[1], n_ev = cnt[2];
+    int msgs[4] = {st[RS_MSG_A], st[RS_MSG_B], st[RS_MSG_C], st[RS_MSG_D]};   // last A, B, C, D words while in sync; -1 = none (fmMonoBlock.py:596-600)
+    int n_sym = cnt[0], n_bits = cnt[1], n_ev = cnt[2], n_grp = cnt[3];
+    int* o_grp = a.groups + (long long)s * a.grp_stride * 4;
     int8_t* o_sym = a.sym + (long long)s * a.sym_stride;
     int8_t* o_bits = a.bits + (long long)s * a.bits_stride;
     int* o_ev = a.events + (long long)s * a.ev_stride * 4;
@@ -324,7 +326,7 @@ k_rds_decode(Dy4RdsDecodeArgs a)
 
                     unsigned syn = 0;
                     for (int i = 0; i < 10; i++) syn |= (unsigned)(__popc(w & c_rds_rows[i]) & 1) << i;
-                    int t = -1;
+                    int t = -1, msg_word = -1;                     // msg = [] unless a syndrome matches
                     for (int i = 0; i < 5; i++) if (syn == c_rds_syn[i]) t = i;
                     if (t >= 0) {
                         const int old_offset = offset_state;
@@ -333,6 +335,7 @@ k_rds_decode(Dy4RdsDecodeArgs a)
                         const int false_pos = (bit_pos != last_pos + 26 && old_offset >= 0) ? 1 : 0;
                         int msg = 0;
                         for (int j = 0; j < 16; j++) msg = (msg << 1) | (int)((w >> j) & 1u);
+                        msg_word = msg;
                         if (n_ev < a.ev_cap) { o_ev[4 * n_ev] = t; o_ev[4 * n_ev + 1] = bit_pos; o_ev[4 * n_ev + 2] = false_pos; o_ev[4 * n_ev + 3] = msg; }
                         n_ev++;
                         offset_state = synced ? t : -1;
@@ -340,6 +343,19 @@ k_rds_decode(Dy4RdsDecodeArgs a)
                     }
                     bit_pos += synced ? 26 : 1;
                     if (num_synced > 3 && !synced) synced = 1;
+                    // the glue of the model's main loop (fmMonoBlock.py:716-730): while in sync the word of the CURRENT
+                    // offset state replaces that block's slot (an unmatched window empties it; C' never lands in the C
+                    // slot), out of sync everything is dropped; a complete A,B,C,D set goes to the application layer
+                    if (synced) {
+                        const int slot = offset_state == 0 ? 0 : offset_state == 1 ? 1 : offset_state == 2 ? 2 : offset_state == 4 ? 3 : -1;
+                        if (slot >= 0) msgs[slot] = msg_word;
+                    } else {
+                        msgs[0] = msgs[1] = msgs[2] = msgs[3] = -1;
+                    }
+                    if (msgs[0] >= 0 && msgs[1] >= 0 && msgs[2] >= 0 && msgs[3] >= 0) {
+                        if (n_grp < a.grp_cap) { o_grp[4 * n_grp] = msgs[0]; o_grp[4 * n_grp + 1] = msgs[1]; o_grp[4 * n_grp + 2] = msgs[2]; o_grp[4 * n_grp + 3] = msgs[3]; }
+                        n_grp++;
+                    }
                 }
             }
         }
@@ -349,7 +365,8 @@ k_rds_decode(Dy4RdsDecodeArgs a)
     st[RS_ERR1] = errors1; st[RS_ERR2] = errors2; st[RS_BITSTATE] = bit_state; st[RS_WINDEX] = window_index;
     st[RS_SYNCED] = synced; st[RS_OFFSET] = offset_state; st[RS_NUMSYNCED] = num_synced; st[RS_BITPOS] = bit_pos;
     st[RS_LASTPOS] = last_pos; st[RS_WSTATE_LEN] = wstate_len; st[RS_WSTATE] = (int)wstate;
-    cnt[0] = n_sym; cnt[1] = n_bits; cnt[2] = n_ev;
+    st[RS_MSG_A] = msgs[0]; st[RS_MSG_B] = msgs[1]; st[RS_MSG_C] = msgs[2]; st[RS_MSG_D] = msgs[3];
+    cnt[0] = n_sym; cnt[1] = n_bits; cnt[2] = n_ev; cnt[3] = n_grp;
 }
 
 // append this call's in-phase RRC samples to the per-stream accumulation row (after moving what the decoder left

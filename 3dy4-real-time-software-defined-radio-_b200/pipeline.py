@@ -114,8 +114,9 @@ class Pipeline:
 
     def rds_drain(self, raw=False):
         """Everything the RDS back half decoded since the last drain: per stream, dict(symbols, bits, events) of numpy
-        arrays (events: rows of [block type 0..4 = A,B,C,C',D, bit position, false-positive flag, 16-bit word]).
-        raw=True returns the padded arrays and the counts instead: (symbols[S,:], bits[S,:], events[S,:,4], counts[S,3])."""
+        arrays (events: rows of [block type 0..4 = A,B,C,C',D, bit position, false-positive flag, 16-bit word]; groups:
+        rows of the [A, B, C, D] words of every complete group, the input of rds_app.ApplicationLayer).
+        raw=True returns the padded arrays and the counts instead: (symbols[S,:], bits[S,:], events[S,:,4], groups[S,:,4], counts[S,4])."""
         import numpy as np
         ms, mb, me = C.c_int(), C.c_int(), C.c_int()
         check(lib.dy4_pipeline_rds_bounds(self._h, C.byref(ms), C.byref(mb), C.byref(me)), "dy4_pipeline_rds_bounds")
@@ -123,12 +124,15 @@ class Pipeline:
         sym = np.zeros((S, max(ms.value, 1)), np.int8)
         bits = np.zeros((S, max(mb.value, 1)), np.int8)
         ev = np.zeros((S, max(me.value, 1), 4), np.int32)
-        cnt = np.zeros((S, 3), np.int32)
+        grp = np.zeros((S, max(me.value, 1), 4), np.int32)
+        cnt = np.zeros((S, 4), np.int32)
         check(lib.dy4_pipeline_rds_drain(self._h, C.c_void_p(sym.ctypes.data), sym.shape[1], C.c_void_p(bits.ctypes.data), bits.shape[1],
-                                         C.c_void_p(ev.ctypes.data), ev.shape[1], C.c_void_p(cnt.ctypes.data)), "dy4_pipeline_rds_drain")
+                                         C.c_void_p(ev.ctypes.data), ev.shape[1], C.c_void_p(grp.ctypes.data), grp.shape[1],
+                                         C.c_void_p(cnt.ctypes.data)), "dy4_pipeline_rds_drain")
         if raw:
-            return sym, bits, ev, cnt
-        return [dict(symbols=sym[s, :cnt[s, 0]].copy(), bits=bits[s, :cnt[s, 1]].copy(), events=ev[s, :cnt[s, 2]].copy()) for s in range(S)]
+            return sym, bits, ev, grp, cnt
+        return [dict(symbols=sym[s, :cnt[s, 0]].copy(), bits=bits[s, :cnt[s, 1]].copy(), events=ev[s, :cnt[s, 2]].copy(),
+                     groups=grp[s, :cnt[s, 3]].copy()) for s in range(S)]
 
     # ---- diagnostics ----------------------------------------------------------------------------
     def debug_pilot_nco(self):

@@ -186,12 +186,14 @@ int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d_rrc_q, siz
  * the Manchester pairing, from block 10 on bits are decoded and the 26-bit syndrome frame synchroniser runs.
  * dy4_pipeline_rds_bounds: upper bounds (per stream) of what has accumulated since the last drain.
  * dy4_pipeline_rds_drain: waits for the RDS work queued so far, copies per stream the Manchester symbols (0/1, one
- * int8 each), the decoded bits (0/1, int8) and the frame-sync events (4 x int32: block type A,B,C,C',D = 0..4, bit
- * position, false-positive flag, the 16-bit information word) to HOST rows of the given strides (in elements /
- * events; any pointer may be NULL), h_counts[n_streams][3] = symbols, bits, events; then empties the device rows. */
+ * int8 each), the decoded bits (0/1, int8), the frame-sync events (4 x int32: block type A,B,C,C',D = 0..4, bit
+ * position, false-positive flag, the 16-bit information word) and the complete groups the model's main loop hands to
+ * its application layer (fmMonoBlock.py:716-730; 4 x int32: the A, B, C, D words; at most max_events of them) to HOST
+ * rows of the given strides (in elements / events / groups; any pointer may be NULL), h_counts[n_streams][4] =
+ * symbols, bits, events, groups; then empties the device rows. */
 int dy4_pipeline_rds_bounds(dy4_pipeline_t* p, int* max_symbols, int* max_bits, int* max_events);
 int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size_t sym_stride, int8_t* h_bits, size_t bits_stride,
-                           int32_t* h_events, size_t ev_stride, int32_t* h_counts);
+                           int32_t* h_events, size_t ev_stride, int32_t* h_groups, size_t grp_stride, int32_t* h_counts);
 
 /* Diagnostics (valid after a stereo process call): device pointers to the
  * last sub-chunk's pilot and NCO rows, their stride in floats and length. */

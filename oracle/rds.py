@@ -182,6 +182,37 @@ PARITY_ROWS = [  # the indices summed for each syndrome bit, fmMonoBlock.py:183-
     (9, 12, 13, 14, 15, 16, 18, 19, 22, 23, 24, 25)]
 
 
+PTY_NAMES = (  # RDS programme types by 5-bit code, as the model's table lists them (RDS_Application_layer.py:11-44)
+    "No programme type or undefined", "News", "Current Affairs", "Information", "Sport", "Education", "Drama", "Culture",
+    "Science", "Varied", "Pop Music", "Rock Music", "Easy Listening Music", "Light classical", "Serious classical",
+    "Other Music", "Weather", "Finance", "Children's programmes", "Social Affairs", "Religion", "Phone In", "Travel",
+    "Leisure", "Jazz Music", "Country Music", "National Music", "Oldies Music", "Folk Music", "Documentary", "Alarm Test",
+    "Alarm")
+
+
+def process_rds_data(a, b, c, d, prev_pty, prev_pi, count):
+    """RDS_Application_layer.py:1-177 on one complete group (four 16-bit words, lists of bits).  Returns the lines the
+    model prints and its (PTYcode, PIcode, count) hand-off.  Kept as the model behaves: the service-name segment array is
+    local to the call, and the character table is keyed 'xxxx xxxx' (with a space) while the coded strings have none, so
+    no character ever matches — the printed service name is empty."""
+    lines = ["A block " + str(a), "B Block " + str(b), "C Block " + str(c), "D Block " + str(d)]
+    pi = "".join(hex(sum(a[i + j] * (2 ** (3 - j)) for j in range(4)))[2:].upper() for i in range(0, 16, 4))   # :123-129
+    pty = "".join(map(str, b[6:11]))                                                                           # :135
+    psns = [""] * 8
+    if "".join(map(str, d[0:5])) == "00000":                                                                   # :143-161
+        idx = {"00": 0, "01": 2, "10": 4, "11": 6}["".join(map(str, d[0:2]))]
+        psns[idx] = ""
+        psns[idx + 1] = ""
+        count += 1
+    if count == 4:                                                                                             # :166-169
+        lines.append("Program service: " + "".join(psns))
+        count = 0
+    if pty != prev_pty and pi != prev_pi and pty != "" and pi != []:                                           # :172-175
+        lines.append("PI code: " + pi)
+        lines.append("Program type: " + PTY_NAMES[int(pty, 2)])
+    return lines, pty, pi, count
+
+
 class RdsBackEnd:
     """The per-block glue of fmMonoBlock.py:699-730 with its state (:576-601)."""
 
@@ -193,6 +224,9 @@ class RdsBackEnd:
         self.window_index, self.synced, self.window_state = 24, False, []
         self.offset_state, self.num_synced, self.bit_pos, self.last_pos = "", 0, 0, 0
         self.symbols, self.bits, self.events = [], [], []     # everything produced so far
+        self.msgs = {"A": [], "B": [], "C": [], "D": []}      # :596-600
+        self.pty, self.pi, self.count = "", "", 0             # :523-525
+        self.groups, self.app_lines = [], []                  # complete groups handed to the application layer; what it printed
 
     def push(self, rrc_i, rrc_q):
         assert len(rrc_i) == BLOCK_RDS
@@ -210,7 +244,17 @@ class RdsBackEnd:
                 while (self.synced and widx < len(bits) - 26) or (not self.synced and widx < len(bits) - 1):   # :711
                     window = self._get_window(bits)
                     widx = self.window_index
-                    self._frame_sync(window)
+                    msg = self._frame_sync(window)
+                    if self.synced:                                       # :718-722 ('Cp' never lands in msgs.c, as in the model)
+                        if self.offset_state in self.msgs:
+                            self.msgs[self.offset_state] = msg
+                    else:                                                 # :723-727
+                        self.msgs = {"A": [], "B": [], "C": [], "D": []}
+                    if all(self.msgs[k] != [] for k in "ABCD"):           # :729-730
+                        m = self.msgs
+                        self.groups.append(tuple(int("".join(map(str, m[k])), 2) for k in "ABCD"))
+                        lines, self.pty, self.pi, self.count = process_rds_data(m["A"], m["B"], m["C"], m["D"], self.pty, self.pi, self.count)
+                        self.app_lines.extend(lines)
         self.block_count += 1
 
     def _find_pattern(self, s):                                           # :78-92
@@ -247,6 +291,7 @@ class RdsBackEnd:
     def _frame_sync(self, m):                                             # :176-284
         s = tuple(sum(m[j] for j in row) % 2 for row in PARITY_ROWS)
         t = SYNDROMES.get(s)
+        msg_bits = list(m[0:16]) if t is not None else []
         if t is not None:
             if self.offset_state in PREDECESSORS[t] or (self.offset_state == "" and not self.synced):
                 self.synced = True        # numSynced += 1 if not synced else 0  -> adds 0 (synced was just set)
@@ -263,6 +308,7 @@ class RdsBackEnd:
         self.bit_pos += 26 if self.synced else 1
         if self.num_synced > 3 and not self.synced:
             self.synced = True
+        return msg_bits
 
 
 def rds_back(rrc_i, rrc_q):

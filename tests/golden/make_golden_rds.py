@@ -6,7 +6,7 @@ is not installed here; an empty stub package on sys.path lets its functions be i
 the Python and C++ front ends differ (float64, firwin taps, atan2 demod), so the oracles are joined at the IF:
 the IF comes from the C oracle (bit-identical to the CUDA path), and the MODEL'S OWN FUNCTIONS — convolve,
 squaringNonlinearity, delayBlock, fmPll, pointwiseMultiply, resampler, impulseResponseRootRaisedCosine,
-manchesterEncoded, find_pattern, decode, get_window, frame_sync_receiver — run on it in float64 with the model's own
+manchesterEncoded, find_pattern, decode, get_window, frame_sync_receiver, process_rds_data — run on it in float64 with the model's own
 taps, parameters and block size (fmMonoBlock.py:444-447, 488-515, 568, 673-730).  Only the glue of the model's main loop
 (which cannot be imported) is restated here, line for line.
 """
@@ -32,6 +32,7 @@ from scipy import signal  # noqa: E402
 import fmMonoBlock as M  # noqa: E402
 from fmRRC import impulseResponseRootRaisedCosine  # noqa: E402
 from fmSupportLib import manchesterEncoded  # noqa: E402
+from RDS_Application_layer import process_rds_data  # noqa: E402
 import oracle  # noqa: E402
 import importlib.util  # noqa: E402
 
@@ -65,6 +66,9 @@ def main():
     offsetState, numSynced, bit_pos, last_pos = '', 0, 0, 0
     out = {k: [] for k in ("rds_f", "carrier", "nco_i", "nco_q", "rrc_i", "rrc_q")}
     symbols, sym_counts, bits, events = [], [], [], []
+    msgs = M.EmptyObject(); msgs.a = []; msgs.b = []; msgs.c = []; msgs.d = []          # fmMonoBlock.py:596-600
+    PTYcode, PIcode, count = '', '', 0                                                  # :523-525
+    groups, app_lines = [], []
     blk = M.sps * M.RDS_decim * M.rf_decim * M.audio_decim * 2 * 2 // 2 // M.rf_decim     # block_size (:568) in IF samples
     assert blk == 19200 and len(fm) % blk == 0
     for block_count in range(len(fm) // blk):
@@ -112,6 +116,18 @@ def main():
                             events.append((TYPE_CODE[found.group(1)], pos_before, int("false positive" in said), word))
                         else:
                             assert msg == []
+                        if synced:                                                        # :718-722
+                            msgs.a = msg if offsetState == 'A' else msgs.a
+                            msgs.b = msg if offsetState == 'B' else msgs.b
+                            msgs.c = msg if offsetState == 'C' else msgs.c
+                            msgs.d = msg if offsetState == 'D' else msgs.d
+                        else:                                                             # :723-727
+                            msgs.a = []; msgs.b = []; msgs.c = []; msgs.d = []
+                        if msgs.a != [] and msgs.b != [] and msgs.c != [] and msgs.d != []:   # :729-730
+                            groups.append([int("".join(str(int(b)) for b in w), 2) for w in (msgs.a, msgs.b, msgs.c, msgs.d)])
+                            mark2 = log.tell()
+                            PTYcode, PIcode, count = process_rds_data(msgs, PTYcode, PIcode, count)
+                            app_lines.extend(log.getvalue()[mark2:].splitlines())
         print("model block", block_count, "symbols", sym_counts[-1], "bits so far", len(bits), "events", len(events),
               "errors1/2", errors1, errors2, "synced", synced, flush=True)
     out = {k: np.concatenate(v) for k, v in out.items()}
@@ -124,7 +140,8 @@ def main():
                         nco_i_8=out["nco_i"][::8].astype(np.float32), nco_q_8=out["nco_q"][::8].astype(np.float32),
                         symbols=np.concatenate(symbols), symbol_counts=np.array(sym_counts, np.int32),
                         bits=np.array(bits, np.int8), events=np.array(events, np.int32).reshape(-1, 4),
-                        errors=np.array([errors1, errors2], np.int32))
+                        errors=np.array([errors1, errors2], np.int32),
+                        groups=np.array(groups, np.int32).reshape(-1, 4), app_lines=np.array("\n".join(app_lines)))
     print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
     print("bits", len(bits), "events", events[:12])
 

@@ -54,6 +54,8 @@ def test_rds_golden(dy4, splits):
     assert np.array_equal(dr[0]["symbols"], g["symbols"])
     assert np.array_equal(dr[0]["bits"], g["bits"])
     assert np.array_equal(dr[0]["events"], g["events"])
+    assert np.array_equal(dr[0]["groups"], g["groups"])
+    assert dy4.rds_app.ApplicationLayer().feed_groups(dr[0]["groups"]) == str(g["app_lines"]).split("\n")
 
 
 def test_rds_batch_against_oracle(dy4, orc):
@@ -71,6 +73,8 @@ def test_rds_batch_against_oracle(dy4, orc):
         assert np.array_equal(dr[s]["symbols"], np.concatenate([np.array(x, np.int8) for x in be.symbols]))
         assert np.array_equal(dr[s]["bits"], np.array(be.bits, np.int8))
         assert np.array_equal(dr[s]["events"], np.array(be.events, np.int32).reshape(-1, 4))
+        assert np.array_equal(dr[s]["groups"], np.array(be.groups, np.int32).reshape(-1, 4))
+        assert dy4.rds_app.ApplicationLayer().feed_groups(dr[s]["groups"]) == be.app_lines
         n_events += len(be.events)
     assert n_events >= 8 * S
 
@@ -134,6 +138,6 @@ def test_rds_checkpoint_and_host_path(dy4):
     b.close()
     n2 = i_t.shape[1]
     assert np.array_equal(i_t.cpu().numpy()[0], ri_all[0, -n2:]) and np.array_equal(q_t.cpu().numpy()[0], rq_all[0, -n2:])
-    for k in ("symbols", "bits", "events"):
+    for k in ("symbols", "bits", "events", "groups"):
         assert np.array_equal(np.concatenate([first[0][k], second[0][k]]), dr_all[0][k]), k
     assert np.array_equal(dr_all[0]["bits"], g["bits"])

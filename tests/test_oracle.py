@@ -193,6 +193,18 @@ def test_rds_oracle_matches_model_golden(orc, dy4):
     assert [be.errors1, be.errors2] == list(g["errors"])
     ev = g["events"]
     assert len(ev) >= 16 and set(ev[:, 0]) >= {0, 1, 2, 4} and not ev[:, 2].any()      # the fixture does exercise the frame sync
+    # the glue that collects A,B,C,D words and the application layer (the model's own process_rds_data in the fixture)
+    assert np.array_equal(np.array(be.groups, np.int32).reshape(-1, 4), g["groups"]) and len(g["groups"]) >= 10
+    assert be.app_lines == str(g["app_lines"]).split("\n")
+    assert any(l.startswith("PI code: ") for l in be.app_lines) and any(l.startswith("Program type: ") for l in be.app_lines)
+
+
+def test_rds_application_layer_of_the_package_matches_model(dy4):
+    """dy4_b200.rds_app.ApplicationLayer (product side, host strings) fed with the fixture's groups prints what the
+    model's process_rds_data printed."""
+    g = golden("rds_mode0.npz")
+    app = dy4.rds_app.ApplicationLayer()
+    assert app.feed_groups(g["groups"]) == str(g["app_lines"]).split("\n")
 
 
 def test_rds_taps_match_scipy_and_the_library(dy4):
