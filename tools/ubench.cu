@@ -246,6 +246,39 @@ __global__ void k_dp_issue(double* out, long long* cyc, double seed, int n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// ping-pong between two warps of one CTA through shared memory (flag + 8-byte payload per lane): the cost of handing a
+// value to a helper warp on another SMSP and getting one back — what a cross-warp split of the PLL step would pay twice.
+template <int FENCE>
+__global__ void k_pingpong(double* out, long long* cyc, int n) {
+    __shared__ volatile int s_req, s_ack;
+    __shared__ volatile double s_a[32], s_b[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_req = 0; s_ack = 0; }
+    __syncthreads();
+    double v = lane;
+    long long t0 = clock64();
+    if (warp == 0) {
+        for (int i = 1; i <= n; i++) {
+            s_a[lane] = v;
+            __syncwarp();
+            if (lane == 0) { if (FENCE) __threadfence_block(); s_req = i; }
+            while (s_ack < i) { }
+            v = s_b[lane] + 1.0;
+        }
+    } else if (warp == 1) {
+        for (int i = 1; i <= n; i++) {
+            while (s_req < i) { }
+            const double x = s_a[lane];
+            s_b[lane] = x * 1.0000001;
+            __syncwarp();
+            if (lane == 0) { if (FENCE) __threadfence_block(); s_ack = i; }
+        }
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = v;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+
 template <typename K, typename T>
 void run_tput(const char* name, K kern, T* buf, double ops_per_thread, int flops_per_op) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
@@ -294,6 +327,10 @@ int main() {
 #define DPI(NC, MIX, THREADS, NAME) { k_dp_issue<NC, MIX><<<1, THREADS>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); k_dp_issue<NC, MIX><<<1, THREADS>>>((double*)buf, cyc, 0.3, nrep); CK(cudaDeviceSynchronize()); printf("dp issue %-28s %6.2f cycles per instruction per warp\n", NAME, (double)*cyc / nrep / NC); }
     DPI(16, 0, 32, "DFMA 1 warp x16 chains") DPI(16, 1, 32, "DADD 1 warp x16 chains") DPI(16, 2, 32, "DMUL 1 warp x16 chains")
     DPI(16, 0, 8, "DFMA 8 lanes x16 chains") DPI(16, 0, 64, "DFMA 2 warps (2 SMSPs)") DPI(16, 0, 160, "DFMA 5 warps (2 on SMSP0)") DPI(4, 0, 32, "DFMA 1 warp x4 chains")
+    { k_pingpong<1><<<1, 64>>>((double*)buf, cyc, nrep); CK(cudaDeviceSynchronize()); k_pingpong<1><<<1, 64>>>((double*)buf, cyc, nrep); CK(cudaDeviceSynchronize());
+      printf("warp-to-warp round trip through shared memory  %8.1f cycles (fenced)\n", (double)*cyc / nrep);
+      k_pingpong<0><<<1, 64>>>((double*)buf, cyc, nrep); CK(cudaDeviceSynchronize());
+      printf("warp-to-warp round trip through shared memory  %8.1f cycles (volatile only)\n", (double)*cyc / nrep); }
     LAT(0) LAT(1) LAT(2) LAT(3) LAT(4) LAT(5) LAT(6) LAT(7) LAT(8) LAT(9)
     return 0;
 }
