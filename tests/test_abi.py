@@ -104,3 +104,26 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "dy4_oracle" not in src and "libdy4ref" not in src, f
+
+
+def test_streaming_command_line_argument_handling(dy4):
+    """dy4_project (the reference's `project <mode> <mono|stereo>` boundary): usage and argument errors need no GPU."""
+    import os
+    import subprocess
+    exe = os.path.join(dy4.PACKAGE_DIR, "dy4_project")
+    assert os.path.exists(exe), "dy4_project not built (make -C csrc)"
+    p = subprocess.run([exe], capture_output=True, timeout=60)
+    assert p.returncode == 1 and b"Usage" in p.stderr
+    p = subprocess.run([exe, "9", "mono"], capture_output=True, timeout=60)
+    assert p.returncode == 1 and b"Wrong mode" in p.stderr
+    p = subprocess.run([exe, "0", "quad"], capture_output=True, timeout=60)
+    assert p.returncode == 1 and b"must be mono or stereo" in p.stderr
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_streaming_command_line_has_no_cpu_fallback(dy4):
+    import os
+    import subprocess
+    exe = os.path.join(dy4.PACKAGE_DIR, "dy4_project")
+    p = subprocess.run([exe, "0", "stereo"], input=b"\x80" * 4096, capture_output=True, timeout=120)
+    assert p.returncode == 2 and p.stdout == b"" and b"dy4_project:" in p.stderr     # refuses to run: no CUDA device
