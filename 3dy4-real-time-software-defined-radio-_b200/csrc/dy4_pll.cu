@@ -190,10 +190,18 @@ k_nco(const double* __restrict__ theta, long long theta_stride, const float* __r
 __global__ void __launch_bounds__(256)
 k_pll_prep(const float* __restrict__ in, long long in_stride, double* __restrict__ inv, long long inv_stride, int n)
 {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    // four samples per thread: one 16-byte load, two 16-byte stores (rows are 16-byte aligned, see dy4_pipeline.cu)
+    const int k = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
     if (k >= n) return;
-    const float x = __ldg(in + (long long)blockIdx.x * in_stride + k);
-    inv[(long long)blockIdx.x * inv_stride + k] = fast_ok(x) ? dy4_recip(x) : 0.0;
+    const float* src = in + (long long)blockIdx.x * in_stride + k;
+    double* dst = inv + (long long)blockIdx.x * inv_stride + k;
+    if (k + 4 <= n) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+        reinterpret_cast<double2*>(dst)[0] = make_double2(fast_ok(x.x) ? dy4_recip(x.x) : 0.0, fast_ok(x.y) ? dy4_recip(x.y) : 0.0);
+        reinterpret_cast<double2*>(dst)[1] = make_double2(fast_ok(x.z) ? dy4_recip(x.z) : 0.0, fast_ok(x.w) ? dy4_recip(x.w) : 0.0);
+    } else {
+        for (int j = 0; k + j < n; j++) { const float x = __ldg(src + j); dst[j] = fast_ok(x) ? dy4_recip(x) : 0.0; }
+    }
 }
 
 }  // namespace
@@ -216,7 +224,7 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
     c.phaseAdjust = a.phaseAdjust;
     static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
     if (parts & DY4_PLL_PREP) {
-        dim3 gp(a.n_streams, (a.n + 255) / 256);
+        dim3 gp(a.n_streams, ((a.n + 3) / 4 + 255) / 256);
         k_pll_prep<<<gp, 256, 0, st>>>(a.in, a.in_stride, a.inv, a.wide_stride, a.n);
         g_dy4_launches++;
         cudaError_t e0 = cudaGetLastError();
