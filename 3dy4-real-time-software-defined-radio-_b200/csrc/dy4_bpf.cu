@@ -97,7 +97,81 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     }
 }
 
+// Default (non-exact-audio) receivers: only the PILOT output reaches the PLL and has to be bit-exact; the stereo band
+// feeds the audio resampler, where a fused multiply-add is within tolerance.  Scalar accumulators then cost three FP32
+// instructions per tap and output (FMUL + FADD for the pilot, FFMA for the stereo band) instead of the packed pair's
+// four pipe cycles, the tile is staged once (no duplicated (x,x) pairs), taps come from the constant bank as scalars.
+__constant__ float c_pilot[4][DY4_NTAPS + 3], c_stereo[4][DY4_NTAPS + 3];
+
+template <int MODE, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_bpf_mixed(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+            float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if)
+{
+    constexpr int T = NT * R, HALO = 128, NP = T + HALO;
+    __shared__ float sm[NP + NP / R + 8];                        // one pad float per R: stride R+1 between threads' windows
+    const int tid = threadIdx.x, n0 = blockIdx.y * T;
+    const float* row = if_in + (long long)blockIdx.x * if_stride;
+    const float* tail = if_tail + (long long)blockIdx.x * DY4_IF_TAIL;
+    for (int u = tid; u < NP / 4; u += NT) {
+        const int i = n0 - HALO + 4 * u;                          // multiple of 4, never straddles 0
+        float4 v;
+        if (i < 0) v = *reinterpret_cast<const float4*>(tail + DY4_IF_TAIL + i);
+        else if (i + 3 < n_if) v = __ldg(reinterpret_cast<const float4*>(row + i));
+        else { v.x = i < n_if ? row[i] : 0.f; v.y = i + 1 < n_if ? row[i + 1] : 0.f; v.z = i + 2 < n_if ? row[i + 2] : 0.f; v.w = 0.f; }
+        const int p = 4 * u;                                       // R % 4 == 0: the four samples share one pad offset
+        float* d = &sm[p + p / R];
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    constexpr int C0 = HALO - (DY4_NTAPS - 1);
+    const float* w = sm + (R + 1) * tid;
+    float ap[R], as[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { ap[r] = 0.f; as[r] = 0.f; }
+#pragma unroll
+    for (int q = R - 1 + (DY4_NTAPS - 1); q >= 0; q--) {         // window index descends: taps ascend for every output
+        const float x = w[C0 + q + (C0 + q) / R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r + (DY4_NTAPS - 1) - q;
+            if (k >= 0 && k < DY4_NTAPS) {
+                ap[r] = __fadd_rn(ap[r], __fmul_rn(c_pilot[MODE][k], x));      // filter.cpp:75, unfused: feeds the PLL
+                as[r] = fmaf(c_stereo[MODE][k], x, as[r]);
+            }
+        }
+    }
+    const long long o = (long long)blockIdx.x * out_stride + n0 + tid * R;
+    const int left = n_if - (n0 + tid * R);
+    if (left >= R) {
+#pragma unroll
+        for (int r = 0; r < R; r += 4) {
+            *reinterpret_cast<float4*>(pilot + o + r) = make_float4(ap[r], ap[r + 1], ap[r + 2], ap[r + 3]);
+            *reinterpret_cast<float4*>(sband + o + r) = make_float4(as[r], as[r + 1], as[r + 2], as[r + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) if (r < left) { pilot[o + r] = ap[r]; sband[o + r] = as[r]; }
+    }
+}
+
 }  // namespace
+
+cudaError_t dy4_launch_bpf_mixed(const Dy4BpfArgs& a, cudaStream_t st)
+{
+    if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
+    constexpr int R = 8, NT = 128;
+    dim3 grid(a.n_streams, (a.n_if + NT * R - 1) / (NT * R));
+    switch (a.mode) {
+    case 0: k_bpf_mixed<0, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 1: k_bpf_mixed<1, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 2: k_bpf_mixed<2, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 3: k_bpf_mixed<3, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    default: return cudaErrorInvalidValue;
+    }
+    g_dy4_launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
 {
@@ -111,4 +185,13 @@ cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf6) { return cudaMemcpyToSymbol(c_bpf2, bpf6, sizeof(TapPairs) * 6); }
+cudaError_t dy4_upload_taps_bpf(const TapPairs* bpf6)
+{
+    static float hp[4][DY4_NTAPS + 3], hs[4][DY4_NTAPS + 3];
+    for (int m = 0; m < 4; m++)
+        for (int k = 0; k < DY4_NTAPS + 3; k++) { hp[m][k] = bpf6[m].t[k].x; hs[m][k] = bpf6[m].t[k].y; }
+    cudaError_t e = cudaMemcpyToSymbol(c_pilot, hp, sizeof(hp));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_stereo, hs, sizeof(hs));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_bpf2, bpf6, sizeof(TapPairs) * 6);
+}

@@ -59,6 +59,7 @@ struct Dy4TailArgs {
 
 cudaError_t dy4_launch_frontend(const Dy4FrontendArgs& a, cudaStream_t st);
 cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st);
+cudaError_t dy4_launch_bpf_mixed(const Dy4BpfArgs& a, cudaStream_t st);   // pilot exact, stereo band fused (modes 0..3, both outputs)
 cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st);
 enum { DY4_PLL_PREP = 1, DY4_PLL_LOOP = 2, DY4_PLL_NCO = 4 };   // k_pll_prep (reciprocals), k_pll (serial loop), k_nco (NCO row)
 cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts);

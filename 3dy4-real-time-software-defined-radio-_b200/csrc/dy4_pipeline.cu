@@ -269,7 +269,10 @@ int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_o
         ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
         ba.pilot = w.pilot; ba.sband = w.sband; ba.out_stride = (long long)p->ws_stride;
         ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.variant = 0; ba.neg_zero2 = kNegZero2;
-        { Timer t(p, DY4_K_BPF, st); CU(dy4_launch_bpf(ba, st)); }
+        // the stereo band only has to be bit-exact when the audio is asked to be (DY4_FLAG_EXACT_AUDIO)
+        static const bool mixed_ok = !(std::getenv("DY4_BPF") && std::string(std::getenv("DY4_BPF")) == "pair");
+        const bool mixed = mixed_ok && !(p->flags & DY4_FLAG_EXACT_AUDIO);
+        { Timer t(p, DY4_K_BPF, st); CU(mixed ? dy4_launch_bpf_mixed(ba, st) : dy4_launch_bpf(ba, st)); }
     }
     return DY4_OK;
 }
