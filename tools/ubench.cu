@@ -54,6 +54,8 @@ __global__ void k_fmul_fadd(float* out, float a, float b) {
         for (int i = 0; i < NCH; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x[i], h0));
 #pragma unroll
         for (int i = 0; i < NCH; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x[(i + 1) % NCH], h1));
+#pragma unroll
+        for (int i = 0; i < NCH; i++) x[i] = acc[(i + 5) % NCH];      // refresh the operands: otherwise the products are loop-invariant and hoisted
     }
     float s = 0;
 #pragma unroll
