@@ -77,7 +77,7 @@ struct Dy4RdsArgs {
     const float* carrier;                       // 113.5-114.5 kHz band-pass of rds_f^2
     double* theta; long long wide_stride;       // scratch: PLL phase argument after each sample
     float* nco_i; float* nco_q;                 // scratch rows (stride)
-    double* pll_state;                          // [n_streams][8]: integ, phase, trigOffset, theta, ncoI_state, ncoQ_state
+    double* pll_state;                          // [n_streams][8]: integ, phase, trigOffset, reduced phase, ncoI_state, ncoQ_state
     float* mix_tail;                            // [n_streams][2][DY4_MIX_TAIL]: mixed I / Q before the chunk
     float* lp; long long lp_stride;             // scratch [n_streams][2][lp_stride]: resampler output I, Q of this chunk
     float* lp_tail;                             // [n_streams][2][DY4_MIX_TAIL] of it before the chunk

@@ -22,8 +22,8 @@ constexpr double kTwoPiHi = 6.283185307179586, kTwoPiLo = 2.4492935982947064e-16
 constexpr double kPi = 3.141592653589793;
 
 // The detector needs the phase argument reduced to (-pi, pi].  Reducing w*k + phase from scratch every sample (it reaches
-// 1e5 rad) would put a Cody-Waite reduction on the serial chain; instead the reduced phase r is reduced ONCE per launch
-// and then advanced incrementally, r += (w mod 2pi) + dphase, wrapped by at most one turn.  Its rounding (1e-16 per
+// 1e5 rad) would put a Cody-Waite reduction on the serial chain; instead the reduced phase r is part of the carried
+// state and advanced incrementally, r += (w mod 2pi) + dphase, wrapped by at most one turn.  Its rounding (1e-16 per
 // step) is far inside the path's tolerance — the model itself is float64 — while the unreduced argument theta, which the
 // NCO rows are computed from, is still formed as w*k + phase exactly as the model does.  Per sample the dependent chain
 // is: select eD -> integ -> dphase -> r -> wrap.
@@ -35,12 +35,7 @@ k_rds_pll(const float* __restrict__ carrier, long long stride, double* __restric
     if (s >= n_streams) return;
     double* st = state + (long long)s * 8;
     double integ = st[0], phase = st[1], k = st[2];
-    const double th0 = st[3];
-    double r;
-    {   // reduced phase of the carried argument: th - 2 pi rint(th / 2 pi), two-part 2 pi
-        const double q = rint(th0 * kInvTwoPi);
-        r = fma(-q, kTwoPiLo, fma(-q, kTwoPiHi, th0));
-    }
+    double r = st[3];                                             // the reduced phase is CARRIED (0 at stream start), so any chunking gives the same samples
     const double w_red = w - kTwoPiHi * rint(w * kInvTwoPi);      // w is below 2 pi here: exact
     const float* x = carrier + (long long)s * stride;
     double* y = theta + (long long)s * wide_stride;
@@ -68,7 +63,7 @@ k_rds_pll(const float* __restrict__ carrier, long long stride, double* __restric
         *reinterpret_cast<double2*>(y + i + 2) = make_double2(t2, t3);
     }
     for (; i < n; i++) y[i] = step(x[i]);
-    st[0] = integ; st[1] = phase; st[2] = k; st[3] = n > 0 ? y[n - 1] : th0;
+    st[0] = integ; st[1] = phase; st[2] = k; st[3] = r;
 }
 
 // nco_i[k] = cos(theta[k-1]*scale + adj), nco_q[k] = sin(...); [0] from the carried state (fmMonoBlock.py:353-354,373-376)

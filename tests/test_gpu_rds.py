@@ -141,3 +141,31 @@ def test_rds_checkpoint_and_host_path(dy4):
     for k in ("symbols", "bits", "events", "groups"):
         assert np.array_equal(np.concatenate([first[0][k], second[0][k]]), dr_all[0][k]), k
     assert np.array_equal(dr_all[0]["bits"], g["bits"])
+
+
+def test_rds_batch_independence_at_scale(dy4):
+    """Towards BASELINE configs[3] (many streams with the RDS path): in a 768-stream batch every stream's RRC baseband,
+    symbols, bits, events and groups are exactly those of the same stream processed alone — no cross-stream coupling at
+    any grid size.  Most streams reach frame sync (the model's timing recovery is fragile — replicated, not repaired — so
+    not all of them do)."""
+    import torch
+    m = dy4.mode_params(0)
+    S, nb = 768, 60
+    d = dy4.synth.make_batch_torch(0, S, nb * m.block_size // 2, base_seed=9000, device="cuda", rds=True)
+    p = dy4.Pipeline(0, 1, S, rds=True)
+    p.process(d, want=("pcm",))
+    ri, rq = p.rds_read()
+    torch.cuda.synchronize()
+    dr = p.rds_drain()
+    p.close()
+    assert sum(1 for x in dr if len(x["events"]) >= 8 and len(x["groups"]) >= 1) >= 0.8 * S
+    for s in (0, 301, S - 1):
+        q = dy4.Pipeline(0, 1, 1, rds=True)
+        q.process(d[s:s + 1].contiguous(), want=("pcm",))
+        qi, qq = q.rds_read()
+        torch.cuda.synchronize()
+        one = q.rds_drain()[0]
+        q.close()
+        assert torch.equal(qi[0], ri[s]) and torch.equal(qq[0], rq[s])
+        for k in ("symbols", "bits", "events", "groups"):
+            assert np.array_equal(one[k], dr[s][k]), (s, k)
