@@ -51,7 +51,7 @@ struct dy4_pipeline {
     uint8_t* iq_tail = nullptr; float* if_tail = nullptr; float* mix_tail = nullptr; float* pll_state = nullptr;
     long long seq = 0;                               // sub-chunks processed so far: selects the if_tail slot
     // workspace: two sets, sub-chunk c uses set c&1
-    struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; };
+    struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
     WorkSet ws[2];
     float* ws_nco0 = nullptr;
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
@@ -67,6 +67,7 @@ struct dy4_pipeline {
     size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0, rds_grp_cap = 0;
     long long rds_blocks_since_drain = 0;
     cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
+    bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
     // host-facing staging
@@ -161,13 +162,19 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
 
 // IF / pilot / stereo-band / NCO rows (and the PLL's double rows) for one sub-chunk, two sets.  A stereo job is cut
 // into sub-chunks (plan_subchunks) so that the FIR kernels of sub-chunk c+1 run beside the serial PLL of sub-chunk c;
-// the whole thing is capped by a byte budget (DY4_WS_BYTES, default 3 GiB).  DY4_FLAG_DEBUG_ROWS keeps the job in one
+// the whole thing is capped by a byte budget (DY4_WS_BYTES, default 8 GiB).  DY4_FLAG_DEBUG_ROWS keeps the job in one
 // sub-chunk so that dy4_pipeline_debug_buffers() sees whole rows.
 int ensure_workspace(dy4_pipeline* p, int n_blocks)
 {
-    size_t budget = 3ull << 30;
+    size_t budget = 8ull << 30;
     if (const char* e = std::getenv("DY4_WS_BYTES")) budget = std::strtoull(e, nullptr, 10);
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? 16 : 1);
+    // Table-driven PLL (dy4_plltab.h, 32 bytes of table per IF sample) while the stream count leaves the serial loop
+    // latency-bound; with many streams the direct loop's FP64 work is already throughput-bound and the table's 3x
+    // evaluations would only add to it.  DY4_PLL_TABLE_MAX=0 selects the direct loop always.
+    int tab_max = 4096;
+    if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
+    p->pll_table = p->stereo && p->n_streams <= tab_max;
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 32 : 16) : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
     const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
@@ -180,7 +187,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     if (p->ws_blocks > 0) {
         CU(cudaDeviceSynchronize());
         for (auto& w : p->ws) {
-            cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv);
+            cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab);
             w = dy4_pipeline::WorkSet();
         }
         p->ws_blocks = 0;
@@ -196,6 +203,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.nco, bytes));
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
+            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes));
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 2 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set
@@ -374,6 +382,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride;
     pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
     { Timer t(p, (parts & DY4_PLL_LOOP) ? DY4_K_PLL : DY4_K_PLL_AUX, st); CU(dy4_launch_pll_parts(pa, st, parts)); }
     return DY4_OK;
@@ -594,7 +603,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_groups); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
     if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
-    for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); }
+    for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
     cudaFree(p->ws_nco0);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);

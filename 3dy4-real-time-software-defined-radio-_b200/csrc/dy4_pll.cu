@@ -23,7 +23,9 @@
 #include "dy4_kernels.h"
 #include "dy4_internal.h"
 #include "dy4_pllmath.h"
+#include "dy4_plltab.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
@@ -169,6 +171,174 @@ k_pll(const float* __restrict__ in, long long in_stride, const double* __restric
     st[5] = nco_value((float)th, c.ncoScale, c.phaseAdjust);      // nco_state for the next launch (filter.cpp:218-219)
 }
 
+
+// ====================================================================================================================
+// Table-driven PLL (dy4_plltab.h): predict -> table -> serial pick.  Bit-identical to k_pll by construction (every step
+// is either a pick among exactly evaluated candidates, certain under its error budget, or a direct evaluation).
+// ====================================================================================================================
+constexpr int PRED_SEG = 256;      // samples per predictor thread
+constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop forgets its state as 0.98657^k (1e-6 after 1024)
+
+// 1. predicted trigArg of every sample (double) -> theta row.  One thread per (stream, segment); the first WARM samples
+// of a launch start from the exact carried state, later segments from that state as a guess plus the warm-up.
+__global__ void __launch_bounds__(128)
+k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __restrict__ state,
+              double* __restrict__ th_hat, long long wide_stride, int n, PllConst c)
+{
+    const int s = blockIdx.x;
+    const int s0 = (blockIdx.y * blockDim.x + threadIdx.x) * PRED_SEG;
+    if (s0 >= n) return;
+    const float* st = state + (long long)s * 8;
+    const float* x = in + (long long)s * in_stride;
+    double* y = th_hat + (long long)s * wide_stride;
+    const double T0 = (double)st[4], Kp = (double)c.Kp, Ki = (double)c.Ki;
+    double integ = (double)st[2], phase = (double)st[3];
+    const int kw = max(0, s0 - PRED_WARM), k1 = min(n, s0 + PRED_SEG);
+    double th_prev = c.w * dy4_pll_count(T0, kw) + phase;
+    int k = kw;
+    for (; k + 4 <= k1; k += 4) {                                   // kw, s0 are multiples of 4; rows are 16-byte aligned
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + k));
+        const double t0 = th_prev = dy4_pred_step(v.x, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase);
+        const double t1 = th_prev = dy4_pred_step(v.y, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 2)), Kp, Ki, &integ, &phase);
+        const double t2 = th_prev = dy4_pred_step(v.z, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 3)), Kp, Ki, &integ, &phase);
+        const double t3 = th_prev = dy4_pred_step(v.w, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 4)), Kp, Ki, &integ, &phase);
+        if (k >= s0) {
+            *reinterpret_cast<double2*>(y + k) = make_double2(t0, t1);
+            *reinterpret_cast<double2*>(y + k + 2) = make_double2(t2, t3);
+        }
+    }
+    for (; k < k1; k++) {
+        th_prev = dy4_pred_step(__ldg(x + k), th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase);
+        if (k >= s0) y[k] = th_prev;
+    }
+}
+
+// 2. one table row per sample: the exact errorD of the next step for the three float grid points around the prediction
+__global__ void __launch_bounds__(128)
+k_pll_table(const float* __restrict__ in, long long in_stride, const float* __restrict__ state,
+            const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
+{
+    const int s = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double T0 = (double)state[(long long)s * 8 + 4];
+    const float* x = in + (long long)s * in_stride;
+    dy4_tabrow_t r;
+    dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
+                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, 0, &r);
+    float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
+    o[0] = make_float4(r.A, r.invu, r.T0, r.T1);
+    o[1] = make_float4(r.T2, r.c, r.eps, r.u);
+}
+
+// 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
+// Table rows arrive through a per-lane shared-memory ring filled by cp.async TAB_AHEAD groups of four samples ahead,
+// so the loop never waits on global memory.
+constexpr int TAB_GROUPS = 16;     // ring size in groups of 4 samples (2 KB per lane)
+constexpr int TAB_AHEAD = 12;      // groups in flight
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TabRow { float4 a, b; };    // a = (A, invu, T0, T1), b = (T2, c, eps, u)
+
+// state_k -> state_{k+1}: picks trigArg_k (returned) and applies errorD_{k+1}
+__device__ __forceinline__ float tab_step(const TabRow& r, const float* __restrict__ x, int k, double T0, const PllConst& c,
+                                          float& integ, float& phase)
+{
+    // three speculative loop-filter updates (float adds), beside the pick
+    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, r.b.x));
+    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.z), i0));
+    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.w), i1));
+    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.b.x), i2));
+    float jf;
+    if (dy4_tab_pick(phase, r.a.x, r.a.y, r.b.z, &jf)) {
+        integ = jf < 0.0f ? i0 : (jf > 0.0f ? i2 : i1);
+        phase = jf < 0.0f ? p0 : (jf > 0.0f ? p2 : p1);
+        return fmaf(jf, r.b.w, r.b.y);
+    }
+    // not certain: this step directly (dy4_pllmath.h), as k_pll does
+    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
+    const float eD = dy4_next_errorD((double)th, x[k + 1]);
+    dy4_pll_filter(eD, c.Kp, c.Ki, &integ, &phase);
+    return th;
+}
+
+__global__ void __launch_bounds__(32)
+k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
+          double* __restrict__ theta, long long wide_stride, float* __restrict__ nco0, float* __restrict__ state,
+          int n, int n_streams, PllConst c, int lanes)
+{
+    extern __shared__ float4 ring[];                 // [TAB_GROUPS][8][lanes]: lane-interleaved, conflict-free 16-byte accesses
+    const int lane = threadIdx.x;
+    const int s = blockIdx.x * lanes + lane;
+    if (lane >= lanes || s >= n_streams || n <= 0) return;
+    float* st = state + (long long)s * 8;
+    float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
+    const double T0 = (double)st[4];
+    nco0[s] = st[5];                                 // nco_state opens this launch's NCO row (filter.cpp:184)
+    const float* x = in + (long long)s * in_stride;
+    const float4* rows = tab + (long long)s * tab_stride;
+    double* y = theta + (long long)s * wide_stride;
+    const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
+    const int n_groups = (n_pick + 3) / 4;
+    auto issue = [&](int g) {
+        if (g < n_groups) {
+            float4* dst = ring + (size_t)(g % TAB_GROUPS) * 8 * lanes + lane;
+            const float4* src = rows + (long long)g * 8;
+            const int m = min(8, 2 * (n - 4 * g));   // rows exist for k < n
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (i < m) cp_async16(dst + i * lanes, src + i);
+        }
+        cp_async_commit();
+    };
+    auto fetch = [&](int g, TabRow (&r)[4]) {
+        const float4* src = ring + (size_t)(g % TAB_GROUPS) * 8 * lanes + lane;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { r[i].a = src[(2 * i) * lanes]; r[i].b = src[(2 * i + 1) * lanes]; }
+    };
+    for (int g = 0; g < TAB_AHEAD; g++) issue(g);
+    // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
+    dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
+    TabRow ra[4], rb[4];
+    cp_async_wait<TAB_AHEAD - 1>();
+    fetch(0, ra);
+    auto process = [&](int g, const TabRow (&cur)[4], TabRow (&nxt)[4]) {
+        issue(g + TAB_AHEAD);
+        cp_async_wait<TAB_AHEAD - 1>();              // groups <= g+1 have landed
+        fetch(g + 1, nxt);                           // (a stale slot past the end: never used)
+        const int k = 4 * g;
+        if (k + 4 <= n_pick) {
+            const float t0 = tab_step(cur[0], x, k, T0, c, integ, phase);
+            const float t1 = tab_step(cur[1], x, k + 1, T0, c, integ, phase);
+            const float t2 = tab_step(cur[2], x, k + 2, T0, c, integ, phase);
+            const float t3 = tab_step(cur[3], x, k + 3, T0, c, integ, phase);
+            *reinterpret_cast<double2*>(y + k) = make_double2((double)t0, (double)t1);
+            *reinterpret_cast<double2*>(y + k + 2) = make_double2((double)t2, (double)t3);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (k + i < n_pick) y[k + i] = (double)tab_step(cur[i], x, k + i, T0, c, integ, phase);
+        }
+    };
+    for (int g = 0; g < n_groups; g += 2) {          // two groups per trip: the row registers swap roles, no copies
+        process(g, ra, rb);
+        if (g + 1 < n_groups) process(g + 1, rb, ra);
+    }
+    cp_async_wait<0>();
+    // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
+    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
+    dy4_nco_t o;
+    dy4_sincos_nco_v((double)th, 0, &o, 0);
+    y[n - 1] = (double)th;
+    st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
+    st[4] = (float)dy4_pll_count(T0, n);
+    st[5] = nco_value(th, c.ncoScale, c.phaseAdjust);          // nco_state for the next launch (filter.cpp:218-219)
+}
+
 // NCO row from the phase row: nco[0] = carried nco_state, nco[k] = cos(trigArg[k-1]*ncoScale + phaseAdjust)
 // (filter.cpp:184,219-221).  Not part of the recurrence, so it runs as a plain data-parallel pass.
 __global__ void __launch_bounds__(256)
@@ -223,6 +393,24 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
     c.ncoScale = a.ncoScale;
     c.phaseAdjust = a.phaseAdjust;
     static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
+    // Table-driven loop (dy4_plltab.h) when the caller provides the row buffer: predict -> table -> serial pick.
+    static const int tab_lanes_env = std::getenv("DY4_PLL_LANES") ? atoi(std::getenv("DY4_PLL_LANES")) : 0;
+    if (a.tab) {
+        if (parts & DY4_PLL_LOOP) {
+            const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
+            k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.n, c);
+            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
+            lanes = std::max(1, std::min(lanes, 16));
+            const size_t smem = (size_t)TAB_GROUPS * 8 * lanes * sizeof(float4);
+            k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, smem, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, a.theta, a.wide_stride,
+                                                                         a.nco0, a.state, a.n, a.n_streams, c, lanes);
+            g_dy4_launches += 3;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        parts &= DY4_PLL_NCO;
+    }
     if (parts & DY4_PLL_PREP) {
         dim3 gp(a.n_streams, ((a.n + 3) / 4 + 255) / 256);
         k_pll_prep<<<gp, 256, 0, st>>>(a.in, a.in_stride, a.inv, a.wide_stride, a.n);

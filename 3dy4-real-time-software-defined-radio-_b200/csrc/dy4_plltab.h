@@ -1,0 +1,141 @@
+// dy4_plltab.h — the PLL recurrence (src/filter.cpp:174-228) with its transcendental work moved OFF the serial chain.
+//
+// What the recurrence really depends on.  The detector input is eI = x*fbI, eQ = x*(-fbQ) with (fbI,fbQ) =
+// (cos,sin)(trigArg) — so errorD = atan2(eQ,eI) (filter.cpp:200) is a function of TWO things only: the input sample
+// x[k] (known before the loop runs) and the previous float trigArg.  And trigArg is a FLOAT (filter.cpp:188,214): it
+// lives on a grid of spacing u = ulp(trigArg) (2^-11 rad after 8 k samples, 2^-3 after 10 s).  A cheap predictor —
+// the same loop in plain double arithmetic with the detector replaced by its closed form  wrap(pi*[x<0] - trigArg),
+// no transcendental at all — stays within ONE grid point of the true float trajectory (the loop is contracting; the
+// only thing the predictor lacks is the float rounding of trigArg, |q| <= u/2, which the loop filter attenuates).
+//
+// So the work is split three ways (dy4_pll.cu):
+//   1. k_pll_predict   time-parallel (segments with a warm-up), serial only in cheap double adds: predicted trigArg
+//   2. k_pll_table     fully parallel: for every sample the EXACT errorD of the next step for the three float grid
+//                      points around the prediction (the dy4_pllmath.h sincos + detector, unchanged arithmetic)
+//   3. k_pll_tab       the serial loop: per sample a float FMA + rounding picks the grid point the true trigArg
+//                      falls on, three speculative loop-filter updates (float adds) are selected from — ~20-40
+//                      cycles instead of ~445.  Whenever the pick is not certain (outside the three candidates, within
+//                      a rounding-error guard band of a tie, binade edges, start-up) the thread evaluates that step
+//                      directly with dy4_pllmath.h, so the result is the reference's bit for bit by construction.
+//
+// Everything here is a fixed sequence of IEEE operations compiled for host and device; tools/plltab_check.c runs the
+// three parts on the host against the reference recurrence with glibc.
+#pragma once
+#include "dy4_pllmath.h"
+
+#if defined(__CUDA_ARCH__)
+#define DY4_FMULF(a, b) __fmul_rn((a), (b))
+#define DY4_FADDF(a, b) __fadd_rn((a), (b))
+#define DY4_D2F(a) __double2float_rn(a)
+#else
+#define DY4_FMULF(a, b) ((float)((float)(a) * (float)(b)))   /* host: -ffp-contract=off */
+#define DY4_FADDF(a, b) ((float)((float)(a) + (float)(b)))
+#define DY4_D2F(a) ((float)(a))
+#endif
+
+// One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
+// 32 bytes, read as two 16-byte words.
+typedef struct {
+    float A;        // (RN_d(w*T_k) - c) / u : trigArg_k = c + round(phase_k/u + A) * u   (NaN: row not usable)
+    float invu;     // 1/u, a power of two
+    float T0, T1;   // errorD of step k+1 if trigArg_k = c - u, c
+    float T2;       //                                   c + u
+    float c;        // predicted trigArg_k rounded to float
+    float eps;      // guard band (in grid units) around a tie: rounding error budget of the pick
+    float u;        // grid spacing of c's binade
+} dy4_tabrow_t;
+
+// float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
+DY4_HD double dy4_pll_count(double T0, int steps) { return fmin(T0 + (double)steps, 16777216.0); }
+
+// loop filter + phase accumulator, filter.cpp:207,210 (float, unfused, this order)
+DY4_HD void dy4_pll_filter(float eD, float Kp, float Ki, float* integ, float* phase)
+{
+    *integ = DY4_FADDF(*integ, DY4_FMULF(Ki, eD));
+    *phase = DY4_FADDF(*phase, DY4_FADDF(DY4_FMULF(Kp, eD), *integ));
+}
+
+// exact trigArg of filter.cpp:214 as a float value
+DY4_HD float dy4_pll_trigarg(double w, double T, float phase) { return DY4_D2F(DY4_ADD(DY4_MUL(w, T), (double)phase)); }
+
+DY4_HD int dy4_fast_ok(float x) { const float ax = fabsf(x); return ax > 1e-20f && ax < 1e20f; }
+
+// ---- 1. predictor: one step in plain double, no transcendental -----------------------------------------------------
+// th_prev: (predicted) trigArg of the previous step; returns the predicted trigArg of this step.
+DY4_HD double dy4_pred_step(float x, double th_prev, double wT, double Kp, double Ki, double* integ, double* phase)
+{
+    const double PI_ = 3.14159265358979323846, TWO_PI = 6.28318530717958647692, INV_2PI = 0.15915494309189533577;
+    double a = (x < 0.0f ? PI_ : 0.0) - th_prev;                 // angle of x*exp(-i*th_prev)
+    const double big = 6755399441055744.0;                       // 1.5*2^52: round to nearest integer
+    const double n = (a * INV_2PI + big) - big;
+    a = fma(-n, TWO_PI, a);                                      // into (-pi, pi]; accuracy ~1e-10 is plenty for a prediction
+    *integ = fma(Ki, a, *integ);
+    *phase = *phase + fma(Kp, a, *integ);
+    return wT + *phase;
+}
+
+// ---- 2. table row --------------------------------------------------------------------------------------------------
+// errorD of the step that follows trigArg = th (a float value) when its input sample is x: the arithmetic of
+// pll_step_fast / detector_libm in dy4_pll.cu, i.e. of filter.cpp:192-200,216-217.
+DY4_HD float dy4_next_errorD(double th, float x)
+{
+    dy4_nco_t o;
+    dy4_sincos_nco_v(th, x < 0.0f, &o, 0);
+    const float fbI = DY4_D2F(o.c), fbQ = DY4_D2F(o.s);                                   // :216-217
+    if (dy4_fast_ok(x)) {
+        const float eI = DY4_FMULF(x, fbI);                                               // :192 (x != 0)
+        const float eQ = DY4_FMULF(x, -fbQ);                                              // :193
+        return DY4_D2F(dy4_detector_atan2((double)eQ, (double)eI, &o, dy4_recip(x)));     // :200
+    }
+    const float eI = DY4_FMULF((x == 0.0f ? 1.0f : x), fbI);
+    const float eQ = DY4_FMULF(x, -fbQ);
+    return DY4_D2F(atan2((double)eQ, (double)eI));
+}
+
+#if defined(__CUDA_ARCH__)
+DY4_HD int dy4_f2i_bits(float v) { return __float_as_int(v); }
+DY4_HD float dy4_i2f_bits(int v) { return __int_as_float(v); }
+#else
+DY4_HD int dy4_f2i_bits(float v) { int b; memcpy(&b, &v, 4); return b; }
+DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
+#endif
+
+// th_hat / th_hat_prev: predicted trigArg of this and of the previous sample; wT = RN_d(w*T_k);
+// x_next: input of step k+1 (has_next == 0 for the last sample of a launch: T unused).
+// `force_invalid`: rows the serial loop must evaluate directly whatever the prediction says.
+DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_tabrow_t* r)
+{
+    const float c = DY4_D2F(th_hat);
+    const int bits = dy4_f2i_bits(c);
+    const int expo = (bits >> 23) & 0xff, mant = bits & 0x7fffff;
+    // usable: positive normal float with both neighbours in the same binade and u in a sane range (2^-40 .. 2^40)
+    int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
+    const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
+    const float invu = dy4_i2f_bits((ok ? 254 - (expo - 23) : 127) << 23);
+    const float A = DY4_D2F(DY4_MUL(DY4_SUB(wT, (double)c), (double)invu));
+    if (!(fabsf(A) < 4194304.0f)) ok = 0;                       // |phase|/u beyond 2^22: the float pick would have no fraction bits left
+    r->c = c; r->u = u; r->invu = invu;
+    r->A = ok ? A : dy4_i2f_bits(0x7fc00000);
+    r->eps = DY4_FMULF(1.1920928955078125e-07f, DY4_FADDF(fabsf(A), 2.0f));   // 2^-23 (|A| + 2)
+    r->T0 = r->T1 = r->T2 = 0.0f;
+    if (ok && has_next) {
+        r->T0 = dy4_next_errorD((double)DY4_FADDF(c, -u), x_next);
+        r->T1 = dy4_next_errorD((double)c, x_next);
+        r->T2 = dy4_next_errorD((double)DY4_FADDF(c, u), x_next);
+    }
+}
+
+// ---- 3. the pick ----------------------------------------------------------------------------------------------------
+// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *j in {-1,0,1} when it is certainly
+// c + j*u; 0 when the serial loop has to evaluate the step directly.
+// Error budget: |A - exact| <= 2^-24|A| + 2^-29, the fma rounds once (<= 2^-24*1.5), the reference's double add moves
+// the sum by <= 2^-29 u  =>  total < eps = 2^-23(|A|+2).  A NaN row fails every comparison.
+DY4_HD int dy4_tab_pick(float phase, float A, float invu, float eps, float* jf_out)
+{
+    const float q = fmaf(phase, invu, A);
+    const float r = DY4_FADDF(q, 12582912.0f);                  // 1.5*2^23: nearest integer, ties to even
+    const float jf = DY4_FADDF(r, -12582912.0f);
+    const float d = DY4_FADDF(q, -jf);                          // exact
+    *jf_out = jf;
+    return (fabsf(d) < DY4_FADDF(0.5f, -eps)) && (fabsf(jf) <= 1.0f);
+}

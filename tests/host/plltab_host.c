@@ -1,0 +1,80 @@
+/* plltab_host.c — host build of csrc/dy4_plltab.h: the three parts of the table-driven PLL (predict, table, serial
+ * pick) run exactly as the kernels of dy4_pll.cu run them, so that the construction can be checked against the
+ * reference recurrence on the CPU (tests/test_host_logic.py).  Test infrastructure only.
+ * Build: gcc -O2 -ffp-contract=off -mfma -shared -fPIC -o libplltab_host.so plltab_host.c -lm */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../3dy4-real-time-software-defined-radio-_b200/csrc/dy4_plltab.h"
+
+#define SEG 256
+#define WARM 1024
+
+/* One launch over n samples of one stream.  state: fbI fbQ integ phase trigOffset (as the reference's PLLState).
+ * theta_out[n]: float trigArg after each sample.  stats[0] += picks, stats[1] += direct evaluations. */
+void plltab_launch(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out, long* stats)
+{
+    dy4_tabrow_t* rows = (dy4_tabrow_t*)malloc(sizeof(dy4_tabrow_t) * (size_t)n);
+    double* th_hat = (double*)malloc(sizeof(double) * (size_t)n);
+    const double T0 = (double)state[4];
+    /* 1. predict: segment i covers [i*SEG, (i+1)*SEG), warm-up from the launch-start state */
+    for (int s0 = 0; s0 < n; s0 += SEG) {
+        int kw = s0 - WARM; if (kw < 0) kw = 0;
+        double integ = (double)state[2], phase = (double)state[3];
+        double th_prev = w * dy4_pll_count(T0, kw) + phase;       /* trigArg of step kw-1 (guess unless kw == 0) */
+        for (int k = kw; k < s0 + SEG && k < n; k++) {
+            th_prev = dy4_pred_step(x[k], th_prev, DY4_MUL(w, dy4_pll_count(T0, k + 1)), (double)Kp, (double)Ki, &integ, &phase);
+            if (k >= s0) th_hat[k] = th_prev;
+        }
+    }
+    /* 2. table */
+    for (int k = 0; k < n; k++)
+        dy4_tab_make_row(th_hat[k], DY4_MUL(w, dy4_pll_count(T0, k + 1)), k + 1 < n ? x[k + 1] : 0.0f, k + 1 < n, 0, &rows[k]);
+    /* 3. serial */
+    float fbI = state[0], fbQ = state[1], integ = state[2], phase = state[3];
+    {
+        const float eI = DY4_FMULF((x[0] == 0.0f ? 1.0f : x[0]), fbI), eQ = DY4_FMULF(x[0], -fbQ);
+        dy4_pll_filter(DY4_D2F(atan2((double)eQ, (double)eI)), Kp, Ki, &integ, &phase);
+    }
+    for (int k = 0; k + 1 < n; k++) {
+        const dy4_tabrow_t* r = &rows[k];
+        float jf, eD, th;
+        if (dy4_tab_pick(phase, r->A, r->invu, r->eps, &jf)) {
+            eD = jf < 0.0f ? r->T0 : (jf > 0.0f ? r->T2 : r->T1);
+            th = fmaf(jf, r->u, r->c);
+            stats[0]++;
+        } else {
+            th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);
+            eD = dy4_next_errorD((double)th, x[k + 1]);
+            stats[1]++;
+        }
+        theta_out[k] = th;
+        dy4_pll_filter(eD, Kp, Ki, &integ, &phase);
+    }
+    {
+        const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, n), phase);
+        dy4_nco_t o; dy4_sincos_nco_v((double)th, 0, &o, 0);
+        theta_out[n - 1] = th;
+        state[0] = DY4_D2F(o.c); state[1] = DY4_D2F(o.s);
+    }
+    state[2] = integ; state[3] = phase; state[4] = (float)dy4_pll_count(T0, n);
+    free(rows); free(th_hat);
+}
+
+/* the reference recurrence (filter.cpp:174-228) with glibc, same outputs */
+void pllref_launch(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out)
+{
+    float fbI = state[0], fbQ = state[1], integ = state[2], phase = state[3], T = state[4];
+    for (int k = 0; k < n; k++) {
+        const float eI = (x[k] == 0 ? 1 : x[k]) * fbI, eQ = x[k] * (-1 * fbQ);
+        const float eD = (float)atan2((double)eQ, (double)eI);
+        const float t0 = Ki * eD; integ = integ + t0;
+        const float t1 = Kp * eD; const float t2 = t1 + integ; phase = phase + t2;
+        T = T + 1.0f;
+        const float trigArg = (float)(w * (double)T + (double)phase);
+        fbI = (float)cos((double)trigArg); fbQ = (float)sin((double)trigArg);
+        theta_out[k] = trigArg;
+    }
+    state[0] = fbI; state[1] = fbQ; state[2] = integ; state[3] = phase; state[4] = T;
+}

@@ -78,3 +78,78 @@ def test_two_rank_launch_gloo(dy4, orc, tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "OK" in p.stdout
+
+
+# ---- table-driven PLL (csrc/dy4_plltab.h): host build of the three kernels' logic ------------------------------------
+def _plltab_lib(tmp_path_factory=None):
+    import ctypes as C
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host", "plltab_host.c")
+    out = os.path.join(os.path.dirname(src), "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libplltab_host.so")
+    hdrs = [src] + [os.path.join(os.path.dirname(src), "..", "..", "3dy4-real-time-software-defined-radio-_b200", "csrc", h)
+                    for h in ("dy4_plltab.h", "dy4_pllmath.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(h) > os.path.getmtime(so) for h in hdrs):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so, src, "-lm"])
+    return C.CDLL(so)
+
+
+def _plltab_run(lib, pilot, Fs, launches, which="plltab_launch"):
+    import ctypes as C
+    w = 2 * 3.14159265358979323846 * float(np.float32(19e3) / np.float32(Fs))
+    Kp = np.float32(0.01) * np.float32(2.666)
+    Ki = np.float32(np.float32(0.01) * np.float32(0.01)) * np.float32(3.555)
+    th = np.zeros(pilot.size, np.float32)
+    st = np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32)              # PLLState, project.cpp:46-53
+    stats = (C.c_long * 2)(0, 0)
+    a = 0
+    for m in launches:
+        args = [C.c_void_p(pilot[a:].ctypes.data), int(m), C.c_void_p(st.ctypes.data), C.c_double(w), C.c_float(Kp), C.c_float(Ki),
+                C.c_void_p(th[a:].ctypes.data)]
+        if which == "plltab_launch": args.append(stats)
+        getattr(lib, which)(*args)
+        a += m
+    assert a == pilot.size
+    return th, st, (stats[0], stats[1])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_table_pll_host_build_reproduces_golden_nco(mode):
+    """predict -> table -> pick (csrc/dy4_plltab.h, built for the host) gives the reference's trigArg bit for bit:
+    cos(2*trigArg) equals the golden NCO row minted from the reference's own fmPLL, whatever the launch split."""
+    lib = _plltab_lib()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mode%d_stereo.npz" % mode))
+    Fs = {0: 240e3, 1: 288e3, 2: 240e3, 3: 384e3}[mode]
+    pilot = np.ascontiguousarray(g["pilot"]); n = pilot.size
+    ref_th, ref_st, _ = _plltab_run(lib, pilot, Fs, [n], "pllref_launch")
+    nco = np.empty(n, np.float32); nco[0] = 1.0
+    nco[1:] = np.cos((ref_th[:-1] * np.float32(2.0)).astype(np.float64)).astype(np.float32)      # filter.cpp:219-221
+    assert np.array_equal(nco.view(np.uint32), g["nco"].view(np.uint32))      # the in-file reference recurrence is the reference's
+    for launches in ([n], [n // 2, n - n // 2], [1, 2, 3, 5, n - 11], [7] * (n // 7) + ([n % 7] if n % 7 else [])):
+        th, st, stats = _plltab_run(lib, pilot, Fs, launches)
+        assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32)), launches[:4]
+        assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+
+
+def test_table_pll_host_build_long_stream_and_pick_rate(dy4, orc):
+    """24 blocks (past the chaotic onset, trigArg ulp 2^-12 .. 2^-7) in the bench's geometric sub-chunks: bit-identical
+    to the reference recurrence, and after start-up essentially every step is a pick (that is the speed-up)."""
+    lib = _plltab_lib()
+    nb = 24
+    iq = dy4.synth.make_stream(0, nb * 51200, 77)
+    pilot = np.ascontiguousarray(orc.pipeline(0, True, iq, want=("pilot",))["pilot"])
+    launches = [b * 5120 for b in (1, 2, 4, 8, 8, 1)]
+    ref_th, ref_st, _ = _plltab_run(lib, pilot, 240e3, launches, "pllref_launch")
+    th, st, (picks, direct) = _plltab_run(lib, pilot, 240e3, launches)
+    assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
+    assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+    assert direct < 0.01 * (picks + direct), (picks, direct)
+    # adversarial inputs: zeros, denormals, sign flips, a dropout — still bit-identical (more direct evaluations)
+    rng = np.random.default_rng(5)
+    bad = pilot[:40960].copy()
+    bad[1000:1100] = 0.0; bad[5000:5050] = 1e-42; bad[9000:9400] *= -1.0
+    bad[20000:22000] = rng.normal(0, 0.03, 2000).astype(np.float32)
+    ref_th, ref_st, _ = _plltab_run(lib, bad, 240e3, [5120] * 8, "pllref_launch")
+    th, st, _ = _plltab_run(lib, bad, 240e3, [5120] * 8)
+    assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
+    assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
