@@ -203,7 +203,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.nco, bytes));
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
-            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes));
+            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 2 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set

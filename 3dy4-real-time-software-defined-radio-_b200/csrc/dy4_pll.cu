@@ -225,7 +225,7 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const float* __re
     const float* x = in + (long long)s * in_stride;
     dy4_tabrow_t r;
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
-                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, 0, &r);
+                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r);
     float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
     o[0] = make_float4(r.A, r.invu, r.T0, r.T1);
     o[1] = make_float4(r.T2, r.c, r.eps, r.u);
@@ -236,6 +236,8 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const float* __re
 // so the loop never waits on global memory.
 constexpr int TAB_GROUPS = 16;     // ring size in groups of 4 samples (2 KB per lane)
 constexpr int TAB_AHEAD = 12;      // groups in flight
+constexpr int TAB_LANES = 16;      // most streams per warp (fixed shared-memory stride)
+constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -245,6 +247,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct TabRow { float4 a, b; };    // a = (A, invu, T0, T1), b = (T2, c, eps, u)
+
+// one copy of the direct evaluation, out of line: the loop body stays small
+__device__ __noinline__ float tab_direct(float th, float x_next) { return dy4_next_errorD((double)th, x_next); }
 
 // state_k -> state_{k+1}: picks trigArg_k (returned) and applies errorD_{k+1}
 __device__ __forceinline__ float tab_step(const TabRow& r, const float* __restrict__ x, int k, double T0, const PllConst& c,
@@ -263,9 +268,24 @@ __device__ __forceinline__ float tab_step(const TabRow& r, const float* __restri
     }
     // not certain: this step directly (dy4_pllmath.h), as k_pll does
     const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
-    const float eD = dy4_next_errorD((double)th, x[k + 1]);
-    dy4_pll_filter(eD, c.Kp, c.Ki, &integ, &phase);
+    dy4_pll_filter(tab_direct(th, x[k + 1]), c.Kp, c.Ki, &integ, &phase);
     return th;
+}
+
+// the same step with no branch: the pick and the three speculative updates run side by side, the select closes the
+// step.  Returns whether the pick was certain; if not, integ/phase/th are garbage and the caller redoes the group.
+__device__ __forceinline__ bool tab_step_spec(const TabRow& r, const PllConst& c, float& integ, float& phase, float& th)
+{
+    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, r.b.x));
+    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.z), i0));
+    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.w), i1));
+    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.b.x), i2));
+    float jf;
+    const bool ok = dy4_tab_pick(phase, r.a.x, r.a.y, r.b.z, &jf);
+    integ = jf < 0.0f ? i0 : (jf > 0.0f ? i2 : i1);
+    phase = jf < 0.0f ? p0 : (jf > 0.0f ? p2 : p1);
+    th = fmaf(jf, r.b.w, r.b.y);
+    return ok;
 }
 
 __global__ void __launch_bounds__(32)
@@ -273,7 +293,7 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
           double* __restrict__ theta, long long wide_stride, float* __restrict__ nco0, float* __restrict__ state,
           int n, int n_streams, PllConst c, int lanes)
 {
-    extern __shared__ float4 ring[];                 // [TAB_GROUPS][8][lanes]: lane-interleaved, conflict-free 16-byte accesses
+    __shared__ float4 ring[TAB_GROUPS * 8 * TAB_LANES];   // [group][row half][lane]: lane-interleaved, conflict-free 16-byte accesses
     const int lane = threadIdx.x;
     const int s = blockIdx.x * lanes + lane;
     if (lane >= lanes || s >= n_streams || n <= 0) return;
@@ -286,37 +306,57 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     double* y = theta + (long long)s * wide_stride;
     const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
     const int n_groups = (n_pick + 3) / 4;
+    // Start of a stream: while the loop acquires lock the detector crosses +-pi, where one ulp decides the sign of a
+    // 2*pi jump — nothing predicts that, so those samples are evaluated directly (as k_pll does) and the table starts
+    // after them.  k_pll_table leaves their rows empty.
+    int kd = 0;
+    if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
+    const int g0 = (kd + 3) / 4;
+    // the buffer is padded (dy4_pipeline.cu), so whole groups are fetched without per-row bounds
     auto issue = [&](int g) {
         if (g < n_groups) {
-            float4* dst = ring + (size_t)(g % TAB_GROUPS) * 8 * lanes + lane;
+            float4* dst = ring + (g % TAB_GROUPS) * (8 * TAB_LANES) + lane;
             const float4* src = rows + (long long)g * 8;
-            const int m = min(8, 2 * (n - 4 * g));   // rows exist for k < n
 #pragma unroll
-            for (int i = 0; i < 8; i++) if (i < m) cp_async16(dst + i * lanes, src + i);
+            for (int i = 0; i < 8; i++) cp_async16(dst + i * TAB_LANES, src + i);
         }
         cp_async_commit();
     };
     auto fetch = [&](int g, TabRow (&r)[4]) {
-        const float4* src = ring + (size_t)(g % TAB_GROUPS) * 8 * lanes + lane;
+        const float4* src = ring + (g % TAB_GROUPS) * (8 * TAB_LANES) + lane;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { r[i].a = src[(2 * i) * lanes]; r[i].b = src[(2 * i + 1) * lanes]; }
+        for (int i = 0; i < 4; i++) { r[i].a = src[(2 * i) * TAB_LANES]; r[i].b = src[(2 * i + 1) * TAB_LANES]; }
     };
-    for (int g = 0; g < TAB_AHEAD; g++) issue(g);
+    for (int g = 0; g < TAB_AHEAD; g++) issue(g0 + g);
     // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
     dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
+    for (int k = 0; k < kd; k++) {
+        const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
+        dy4_pll_filter(tab_direct(th, x[k + 1]), c.Kp, c.Ki, &integ, &phase);
+        y[k] = (double)th;
+    }
     TabRow ra[4], rb[4];
     cp_async_wait<TAB_AHEAD - 1>();
-    fetch(0, ra);
+    fetch(g0, ra);
     auto process = [&](int g, const TabRow (&cur)[4], TabRow (&nxt)[4]) {
         issue(g + TAB_AHEAD);
         cp_async_wait<TAB_AHEAD - 1>();              // groups <= g+1 have landed
         fetch(g + 1, nxt);                           // (a stale slot past the end: never used)
         const int k = 4 * g;
         if (k + 4 <= n_pick) {
-            const float t0 = tab_step(cur[0], x, k, T0, c, integ, phase);
-            const float t1 = tab_step(cur[1], x, k + 1, T0, c, integ, phase);
-            const float t2 = tab_step(cur[2], x, k + 2, T0, c, integ, phase);
-            const float t3 = tab_step(cur[3], x, k + 3, T0, c, integ, phase);
+            // four steps without a branch; if any pick was not certain the group is redone step by step
+            float si = integ, sp = phase, t0, t1, t2, t3;
+            bool ok = tab_step_spec(cur[0], c, si, sp, t0);
+            ok &= tab_step_spec(cur[1], c, si, sp, t1);
+            ok &= tab_step_spec(cur[2], c, si, sp, t2);
+            ok &= tab_step_spec(cur[3], c, si, sp, t3);
+            if (ok) { integ = si; phase = sp; }
+            else {
+                t0 = tab_step(cur[0], x, k, T0, c, integ, phase);
+                t1 = tab_step(cur[1], x, k + 1, T0, c, integ, phase);
+                t2 = tab_step(cur[2], x, k + 2, T0, c, integ, phase);
+                t3 = tab_step(cur[3], x, k + 3, T0, c, integ, phase);
+            }
             *reinterpret_cast<double2*>(y + k) = make_double2((double)t0, (double)t1);
             *reinterpret_cast<double2*>(y + k + 2) = make_double2((double)t2, (double)t3);
         } else {
@@ -324,7 +364,7 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
             for (int i = 0; i < 4; i++) if (k + i < n_pick) y[k + i] = (double)tab_step(cur[i], x, k + i, T0, c, integ, phase);
         }
     };
-    for (int g = 0; g < n_groups; g += 2) {          // two groups per trip: the row registers swap roles, no copies
+    for (int g = g0; g < n_groups; g += 2) {         // two groups per trip: the row registers swap roles, no copies
         process(g, ra, rb);
         if (g + 1 < n_groups) process(g + 1, rb, ra);
     }
@@ -401,9 +441,8 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.n, c);
             k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
-            lanes = std::max(1, std::min(lanes, 16));
-            const size_t smem = (size_t)TAB_GROUPS * 8 * lanes * sizeof(float4);
-            k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, smem, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, a.theta, a.wide_stride,
+            lanes = std::max(1, std::min(lanes, TAB_LANES));
+                        k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, a.theta, a.wide_stride,
                                                                          a.nco0, a.state, a.n, a.n_streams, c, lanes);
             g_dy4_launches += 3;
             cudaError_t e = cudaGetLastError();

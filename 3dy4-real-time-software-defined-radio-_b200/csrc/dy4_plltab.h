@@ -33,6 +33,10 @@
 #define DY4_D2F(a) ((float)(a))
 #endif
 
+// Samples of a stream evaluated directly before the table takes over: while the loop acquires lock the detector
+// crosses +-pi, where one ulp decides the sign of a 2*pi jump, and nothing predicts that.
+#define DY4_TAB_EARLY 1536
+
 // One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
 // 32 bytes, read as two 16-byte words.
 typedef struct {
@@ -69,6 +73,8 @@ DY4_HD double dy4_pred_step(float x, double th_prev, double wT, double Kp, doubl
     const double big = 6755399441055744.0;                       // 1.5*2^52: round to nearest integer
     const double n = (a * INV_2PI + big) - big;
     a = fma(-n, TWO_PI, a);                                      // into (-pi, pi]; accuracy ~1e-10 is plenty for a prediction
+    // x == 0: the reference's detector sees (1*fbI, +-0) (filter.cpp:192-193): 0 in the right half plane, +-pi in the left
+    if (x == 0.0f) a = (fabs(a) < 0.5 * PI_) ? 0.0 : (a > 0.0 ? PI_ : -PI_);
     *integ = fma(Ki, a, *integ);
     *phase = *phase + fma(Kp, a, *integ);
     return wT + *phase;

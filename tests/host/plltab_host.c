@@ -30,7 +30,7 @@ void plltab_launch(const float* x, int n, float* state, double w, float Kp, floa
     }
     /* 2. table */
     for (int k = 0; k < n; k++)
-        dy4_tab_make_row(th_hat[k], DY4_MUL(w, dy4_pll_count(T0, k + 1)), k + 1 < n ? x[k + 1] : 0.0f, k + 1 < n, 0, &rows[k]);
+        dy4_tab_make_row(th_hat[k], DY4_MUL(w, dy4_pll_count(T0, k + 1)), k + 1 < n ? x[k + 1] : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &rows[k]);
     /* 3. serial */
     float fbI = state[0], fbQ = state[1], integ = state[2], phase = state[3];
     {

@@ -143,7 +143,7 @@ def test_table_pll_host_build_long_stream_and_pick_rate(dy4, orc):
     th, st, (picks, direct) = _plltab_run(lib, pilot, 240e3, launches)
     assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
     assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
-    assert direct < 0.01 * (picks + direct), (picks, direct)
+    assert direct <= 1536 + 0.002 * (picks + direct), (picks, direct)       # DY4_TAB_EARLY start-up samples + rare guard-band cases
     # adversarial inputs: zeros, denormals, sign flips, a dropout — still bit-identical (more direct evaluations)
     rng = np.random.default_rng(5)
     bad = pilot[:40960].copy()
