@@ -206,7 +206,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
         }
     }
-    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 2 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set
+    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 4 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, then sample counter
     if (p->stereo && !p->s_pll) {
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -382,7 +382,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
     pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
     { Timer t(p, (parts & DY4_PLL_LOOP) ? DY4_K_PLL : DY4_K_PLL_AUX, st); CU(dy4_launch_pll_parts(pa, st, parts)); }
     return DY4_OK;

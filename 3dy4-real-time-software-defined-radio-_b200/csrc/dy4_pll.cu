@@ -227,16 +227,19 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const float* __re
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
                      k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r);
     float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
-    o[0] = make_float4(r.A, r.invu, r.T0, r.T1);
-    o[1] = make_float4(r.T2, r.c, r.eps, r.u);
+    o[0] = make_float4(r.t_lo, r.t_hi, r.T0, r.T1);
+    o[1] = make_float4(r.T2, r.c, r.u, r.m);
 }
 
 // 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
-// Table rows arrive through a per-lane shared-memory ring filled by cp.async TAB_AHEAD groups of four samples ahead,
-// so the loop never waits on global memory.
-constexpr int TAB_GROUPS = 16;     // ring size in groups of 4 samples (2 KB per lane)
-constexpr int TAB_AHEAD = 12;      // groups in flight
-constexpr int TAB_LANES = 16;      // most streams per warp (fixed shared-memory stride)
+// Table rows arrive through a per-lane shared-memory ring filled by cp.async three super-groups (48 samples) ahead,
+// so the loop never waits on global memory.  A super-group of 16 samples is straight-line code: per sample three
+// speculative loop-filter updates, two compares of phaseEst against the row's thresholds, selects — and ONE branch per
+// super-group on "every pick was certain"; if not, the super-group is redone step by step from its saved state.
+// Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
+constexpr int TAB_SG = 16;         // samples per super-group
+constexpr int TAB_SLOTS = 4;       // ring size in super-groups (8 KB per lane)
+constexpr int TAB_LANES = 8;       // most streams per warp (fixed shared-memory stride)
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
@@ -246,54 +249,43 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct TabRow { float4 a, b; };    // a = (A, invu, T0, T1), b = (T2, c, eps, u)
-
 // one copy of the direct evaluation, out of line: the loop body stays small
 __device__ __noinline__ float tab_direct(float th, float x_next) { return dy4_next_errorD((double)th, x_next); }
 
-// state_k -> state_{k+1}: picks trigArg_k (returned) and applies errorD_{k+1}
-__device__ __forceinline__ float tab_step(const TabRow& r, const float* __restrict__ x, int k, double T0, const PllConst& c,
-                                          float& integ, float& phase)
+// state_k -> state_{k+1} with no branch.  a = (t_lo, t_hi, T0, T1), b = (T2, c, u, m).  Returns whether the pick was
+// certain; if not, integ/phase are garbage and the caller redoes the super-group.
+__device__ __forceinline__ bool tab_step_spec(const float4 a, const float4 b, const PllConst& c, float& integ, float& phase)
 {
-    // three speculative loop-filter updates (float adds), beside the pick
-    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, r.b.x));
-    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.z), i0));
-    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.w), i1));
-    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.b.x), i2));
-    float jf;
-    if (dy4_tab_pick(phase, r.a.x, r.a.y, r.b.z, &jf)) {
-        integ = jf < 0.0f ? i0 : (jf > 0.0f ? i2 : i1);
-        phase = jf < 0.0f ? p0 : (jf > 0.0f ? p2 : p1);
-        return fmaf(jf, r.b.w, r.b.y);
-    }
-    // not certain: this step directly (dy4_pllmath.h), as k_pll does
-    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
-    dy4_pll_filter(tab_direct(th, x[k + 1]), c.Kp, c.Ki, &integ, &phase);
-    return th;
+    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, b.x));
+    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, a.z), i0));
+    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, a.w), i1));
+    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, b.x), i2));
+    const bool neg = phase < a.x, pos = phase > a.y;
+    const float d_lo = __fadd_rn(phase, -a.x), d_hi = __fadd_rn(phase, -a.y), um = __fadd_rn(b.z, -b.w);
+    const bool ok = (fabsf(d_lo) > b.w) && (fabsf(d_hi) > b.w) && (d_lo > -um) && (d_hi < um);
+    integ = neg ? i0 : (pos ? i2 : i1);
+    phase = neg ? p0 : (pos ? p2 : p1);
+    return ok;
 }
 
-// the same step with no branch: the pick and the three speculative updates run side by side, the select closes the
-// step.  Returns whether the pick was certain; if not, integ/phase/th are garbage and the caller redoes the group.
-__device__ __forceinline__ bool tab_step_spec(const TabRow& r, const PllConst& c, float& integ, float& phase, float& th)
+// the same step with the fallback: a pick if certain, else this step directly (dy4_pllmath.h), as k_pll does
+__device__ __noinline__ void tab_step_careful(const float4 a, const float4 b, const float* x_next, double T, const PllConst& c, float* integ_io, float* phase_io)
 {
-    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, r.a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, r.b.x));
-    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.z), i0));
-    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.a.w), i1));
-    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, r.b.x), i2));
-    float jf;
-    const bool ok = dy4_tab_pick(phase, r.a.x, r.a.y, r.b.z, &jf);
-    integ = jf < 0.0f ? i0 : (jf > 0.0f ? i2 : i1);
-    phase = jf < 0.0f ? p0 : (jf > 0.0f ? p2 : p1);
-    th = fmaf(jf, r.b.w, r.b.y);
-    return ok;
+    float integ = *integ_io, phase = *phase_io;
+    int j;
+    float eD;
+    if (dy4_tab_pick(phase, a.x, a.y, b.z, b.w, &j)) eD = j < 0 ? a.z : (j > 0 ? b.x : a.w);
+    else eD = tab_direct(dy4_pll_trigarg(c.w, T, phase), *x_next);      // the input sample is loaded only when it is needed
+    dy4_pll_filter(eD, c.Kp, c.Ki, &integ, &phase);
+    *integ_io = integ; *phase_io = phase;
 }
 
 __global__ void __launch_bounds__(32)
 k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
-          double* __restrict__ theta, long long wide_stride, float* __restrict__ nco0, float* __restrict__ state,
-          int n, int n_streams, PllConst c, int lanes)
+          float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
+          float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
 {
-    __shared__ float4 ring[TAB_GROUPS * 8 * TAB_LANES];   // [group][row half][lane]: lane-interleaved, conflict-free 16-byte accesses
+    __shared__ float4 ring[TAB_SLOTS * TAB_SG * 2 * TAB_LANES];   // [slot][row half][lane]: lane-interleaved, conflict-free 16-byte accesses
     const int lane = threadIdx.x;
     const int s = blockIdx.x * lanes + lane;
     if (lane >= lanes || s >= n_streams || n <= 0) return;
@@ -301,82 +293,98 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
     const double T0 = (double)st[4];
     nco0[s] = st[5];                                 // nco_state opens this launch's NCO row (filter.cpp:184)
+    tstart[s] = st[4];                               // k_nco_phase needs the sample counter this launch started from
     const float* x = in + (long long)s * in_stride;
     const float4* rows = tab + (long long)s * tab_stride;
-    double* y = theta + (long long)s * wide_stride;
+    float* y = phase_out + (long long)s * phase_stride;
     const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
-    const int n_groups = (n_pick + 3) / 4;
     // Start of a stream: while the loop acquires lock the detector crosses +-pi, where one ulp decides the sign of a
     // 2*pi jump — nothing predicts that, so those samples are evaluated directly (as k_pll does) and the table starts
     // after them.  k_pll_table leaves their rows empty.
     int kd = 0;
     if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
-    const int g0 = (kd + 3) / 4;
-    // the buffer is padded (dy4_pipeline.cu), so whole groups are fetched without per-row bounds
-    auto issue = [&](int g) {
-        if (g < n_groups) {
-            float4* dst = ring + (g % TAB_GROUPS) * (8 * TAB_LANES) + lane;
-            const float4* src = rows + (long long)g * 8;
+    const int n_sg = (n_pick - kd) / TAB_SG;         // whole super-groups after the direct part
+    auto issue = [&](int i) {                        // super-group i -> slot i % TAB_SLOTS (past the end: the last one again, unused)
+        const int ic = min(i, n_sg - 1);
+        float4* dst = ring + (i % TAB_SLOTS) * (TAB_SG * 2 * TAB_LANES) + lane;
+        const float4* src = rows + 2 * ((long long)kd + (long long)ic * TAB_SG);
 #pragma unroll
-            for (int i = 0; i < 8; i++) cp_async16(dst + i * TAB_LANES, src + i);
-        }
+        for (int r = 0; r < TAB_SG * 2; r++) cp_async16(dst + r * TAB_LANES, src + r);
         cp_async_commit();
     };
-    auto fetch = [&](int g, TabRow (&r)[4]) {
-        const float4* src = ring + (g % TAB_GROUPS) * (8 * TAB_LANES) + lane;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { r[i].a = src[(2 * i) * TAB_LANES]; r[i].b = src[(2 * i + 1) * TAB_LANES]; }
-    };
-    for (int g = 0; g < TAB_AHEAD; g++) issue(g0 + g);
+    if (n_sg > 0)
+        for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
     // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
     dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
-    for (int k = 0; k < kd; k++) {
-        const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
-        dy4_pll_filter(tab_direct(th, x[k + 1]), c.Kp, c.Ki, &integ, &phase);
-        y[k] = (double)th;
-    }
-    TabRow ra[4], rb[4];
-    cp_async_wait<TAB_AHEAD - 1>();
-    fetch(g0, ra);
-    auto process = [&](int g, const TabRow (&cur)[4], TabRow (&nxt)[4]) {
-        issue(g + TAB_AHEAD);
-        cp_async_wait<TAB_AHEAD - 1>();              // groups <= g+1 have landed
-        fetch(g + 1, nxt);                           // (a stale slot past the end: never used)
-        const int k = 4 * g;
-        if (k + 4 <= n_pick) {
-            // four steps without a branch; if any pick was not certain the group is redone step by step
-            float si = integ, sp = phase, t0, t1, t2, t3;
-            bool ok = tab_step_spec(cur[0], c, si, sp, t0);
-            ok &= tab_step_spec(cur[1], c, si, sp, t1);
-            ok &= tab_step_spec(cur[2], c, si, sp, t2);
-            ok &= tab_step_spec(cur[3], c, si, sp, t3);
-            if (ok) { integ = si; phase = sp; }
-            else {
-                t0 = tab_step(cur[0], x, k, T0, c, integ, phase);
-                t1 = tab_step(cur[1], x, k + 1, T0, c, integ, phase);
-                t2 = tab_step(cur[2], x, k + 2, T0, c, integ, phase);
-                t3 = tab_step(cur[3], x, k + 3, T0, c, integ, phase);
-            }
-            *reinterpret_cast<double2*>(y + k) = make_double2((double)t0, (double)t1);
-            *reinterpret_cast<double2*>(y + k + 2) = make_double2((double)t2, (double)t3);
-        } else {
+    {   // direct part, inputs loaded one group of four ahead of their use
+        float xn[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) if (k + i < n_pick) y[k + i] = (double)tab_step(cur[i], x, k + i, T0, c, integ, phase);
+        for (int r = 0; r < 4; r++) xn[r] = x[min(1 + r, n - 1)];
+        for (int k = 0; k < kd; k += 4) {
+            float xc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) { xc[r] = xn[r]; xn[r] = x[min(k + 5 + r, n - 1)]; }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (k + r < kd) {
+                    y[k + r] = phase;
+                    dy4_pll_filter(tab_direct(dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + r + 1), phase), xc[r]), c.Kp, c.Ki, &integ, &phase);
+                }
         }
-    };
-    for (int g = g0; g < n_groups; g += 2) {         // two groups per trip: the row registers swap roles, no copies
-        process(g, ra, rb);
-        if (g + 1 < n_groups) process(g + 1, rb, ra);
+    }
+    for (int i = 0; i < n_sg; i++) {
+        issue(i + TAB_SLOTS - 1);
+        cp_async_wait<TAB_SLOTS - 1>();              // super-group i has landed
+        const float4* src = ring + (i % TAB_SLOTS) * (TAB_SG * 2 * TAB_LANES) + lane;
+        const int k = kd + i * TAB_SG;
+        float si = integ, sp = phase;
+        float ph[TAB_SG];
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < TAB_SG; r++) {
+            ph[r] = sp;
+            ok &= tab_step_spec(src[(2 * r) * TAB_LANES], src[(2 * r + 1) * TAB_LANES], c, si, sp);
+        }
+        if (ok) {
+#pragma unroll
+            for (int r = 0; r < TAB_SG; r += 4) *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[r], ph[r + 1], ph[r + 2], ph[r + 3]);
+        } else {                                     // rare: redo from the saved state, step by step
+            si = integ; sp = phase;
+#pragma unroll 1
+            for (int r = 0; r < TAB_SG; r++) {
+                y[k + r] = sp;
+                tab_step_careful(src[(2 * r) * TAB_LANES], src[(2 * r + 1) * TAB_LANES], x + k + r + 1, dy4_pll_count(T0, k + r + 1), c, &si, &sp);
+            }
+        }
+        integ = si; phase = sp;
     }
     cp_async_wait<0>();
+    for (int k = kd + n_sg * TAB_SG; k < n_pick; k++) {         // tail: rows straight from global memory
+        y[k] = phase;
+        tab_step_careful(__ldg(rows + 2 * (long long)k), __ldg(rows + 2 * (long long)k + 1), x + k + 1, dy4_pll_count(T0, k + 1), c, &integ, &phase);
+    }
     // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
+    y[n - 1] = phase;
     const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
     dy4_nco_t o;
     dy4_sincos_nco_v((double)th, 0, &o, 0);
-    y[n - 1] = (double)th;
     st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
     st[4] = (float)dy4_pll_count(T0, n);
     st[5] = nco_value(th, c.ncoScale, c.phaseAdjust);          // nco_state for the next launch (filter.cpp:218-219)
+}
+
+// NCO row from the phaseEst row of k_pll_tab: trigArg[k-1] = RN_f(RN_d(w*T) + phase[k-1]) (filter.cpp:214), then as k_nco
+__global__ void __launch_bounds__(256)
+k_nco_phase(const float* __restrict__ phase, long long phase_stride, const float* __restrict__ nco0, const float* __restrict__ tstart,
+            float* __restrict__ nco, long long nco_stride, int n, PllConst c)
+{
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x;
+    if (k >= n) return;
+    float v;
+    if (k == 0) v = nco0[s];
+    else v = nco_value(dy4_pll_trigarg(c.w, dy4_pll_count((double)tstart[s], k), __ldg(phase + (long long)s * phase_stride + k - 1)), c.ncoScale, c.phaseAdjust);
+    nco[(long long)s * nco_stride + k] = v;
 }
 
 // NCO row from the phase row: nco[0] = carried nco_state, nco[k] = cos(trigArg[k-1]*ncoScale + phaseAdjust)
@@ -442,13 +450,18 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
             lanes = std::max(1, std::min(lanes, TAB_LANES));
-                        k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, a.theta, a.wide_stride,
-                                                                         a.nco0, a.state, a.n, a.n_streams, c, lanes);
+            k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, reinterpret_cast<float*>(a.theta), 2 * a.wide_stride,
+                                                                       a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
             g_dy4_launches += 3;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
-        parts &= DY4_PLL_NCO;
+        if (parts & DY4_PLL_NCO) {
+            dim3 grid(a.n_streams, (a.n + 255) / 256);
+            k_nco_phase<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.theta), 2 * a.wide_stride, a.nco0, a.tstart, a.nco, a.nco_stride, a.n, c);
+            g_dy4_launches++;
+        }
+        return cudaGetLastError();
     }
     if (parts & DY4_PLL_PREP) {
         dim3 gp(a.n_streams, ((a.n + 3) / 4 + 255) / 256);

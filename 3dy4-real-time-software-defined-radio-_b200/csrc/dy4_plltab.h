@@ -12,9 +12,9 @@
 //   1. k_pll_predict   time-parallel (segments with a warm-up), serial only in cheap double adds: predicted trigArg
 //   2. k_pll_table     fully parallel: for every sample the EXACT errorD of the next step for the three float grid
 //                      points around the prediction (the dy4_pllmath.h sincos + detector, unchanged arithmetic)
-//   3. k_pll_tab       the serial loop: per sample a float FMA + rounding picks the grid point the true trigArg
-//                      falls on, three speculative loop-filter updates (float adds) are selected from — ~20-40
-//                      cycles instead of ~445.  Whenever the pick is not certain (outside the three candidates, within
+//   3. k_pll_tab       the serial loop: per sample two float compares of phaseEst against precomputed thresholds pick
+//                      the grid point the true trigArg falls on, and three speculative loop-filter updates (float
+//                      adds) are selected from — tens of cycles instead of ~445.  Whenever the pick is not certain (outside the three candidates, within
 //                      a rounding-error guard band of a tie, binade edges, start-up) the thread evaluates that step
 //                      directly with dy4_pllmath.h, so the result is the reference's bit for bit by construction.
 //
@@ -38,15 +38,15 @@
 #define DY4_TAB_EARLY 1536
 
 // One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
-// 32 bytes, read as two 16-byte words.
+// 32 bytes, read as two 16-byte words.  With P = c - RN_d(w*T_k):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is
+// c - u, c, c + u  for  phase_k  in  (P-1.5u, P-.5u), (P-.5u, P+.5u), (P+.5u, P+1.5u).
 typedef struct {
-    float A;        // (RN_d(w*T_k) - c) / u : trigArg_k = c + round(phase_k/u + A) * u   (NaN: row not usable)
-    float invu;     // 1/u, a power of two
-    float T0, T1;   // errorD of step k+1 if trigArg_k = c - u, c
-    float T2;       //                                   c + u
-    float c;        // predicted trigArg_k rounded to float
-    float eps;      // guard band (in grid units) around a tie: rounding error budget of the pick
-    float u;        // grid spacing of c's binade
+    float t_lo, t_hi; // P - u/2, P + u/2 rounded to float (NaN: row not usable)
+    float T0, T1;     // errorD of step k+1 if trigArg_k = c - u, c
+    float T2;         //                                   c + u
+    float c;          // predicted trigArg_k rounded to float
+    float u;          // grid spacing of c's binade
+    float m;          // guard band around a threshold: rounding-error budget of the pick
 } dy4_tabrow_t;
 
 // float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
@@ -106,7 +106,7 @@ DY4_HD int dy4_f2i_bits(float v) { int b; memcpy(&b, &v, 4); return b; }
 DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 #endif
 
-// th_hat / th_hat_prev: predicted trigArg of this and of the previous sample; wT = RN_d(w*T_k);
+// th_hat: predicted trigArg of this sample; wT = RN_d(w*T_k);
 // x_next: input of step k+1 (has_next == 0 for the last sample of a launch: T unused).
 // `force_invalid`: rows the serial loop must evaluate directly whatever the prediction says.
 DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_tabrow_t* r)
@@ -115,14 +115,16 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     const int bits = dy4_f2i_bits(c);
     const int expo = (bits >> 23) & 0xff, mant = bits & 0x7fffff;
     // usable: positive normal float with both neighbours in the same binade and u in a sane range (2^-40 .. 2^40)
-    int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
+    const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
     const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
-    const float invu = dy4_i2f_bits((ok ? 254 - (expo - 23) : 127) << 23);
-    const float A = DY4_D2F(DY4_MUL(DY4_SUB(wT, (double)c), (double)invu));
-    if (!(fabsf(A) < 4194304.0f)) ok = 0;                       // |phase|/u beyond 2^22: the float pick would have no fraction bits left
-    r->c = c; r->u = u; r->invu = invu;
-    r->A = ok ? A : dy4_i2f_bits(0x7fc00000);
-    r->eps = DY4_FMULF(1.1920928955078125e-07f, DY4_FADDF(fabsf(A), 2.0f));   // 2^-23 (|A| + 2)
+    const double P = DY4_SUB((double)c, wT), hu = DY4_MUL(0.5, (double)u);
+    const float t_lo = DY4_D2F(DY4_SUB(P, hu)), t_hi = DY4_D2F(DY4_ADD(P, hu));
+    const float nan = dy4_i2f_bits(0x7fc00000);
+    r->c = c; r->u = u;
+    r->t_lo = ok ? t_lo : nan; r->t_hi = ok ? t_hi : nan;
+    // |t - exact| <= 2^-24|t| (half an ulp) + 2^-29 u from the reference's double add; the guard is twice the first
+    // term plus eight times the second (the float subtraction phase - t adds at most 2^-24 of the guard itself)
+    r->m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fmaxf(fabsf(t_lo), fabsf(t_hi))), DY4_FMULF(1.4901161193847656e-08f, u));
     r->T0 = r->T1 = r->T2 = 0.0f;
     if (ok && has_next) {
         r->T0 = dy4_next_errorD((double)DY4_FADDF(c, -u), x_next);
@@ -133,15 +135,12 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
 
 // ---- 3. the pick ----------------------------------------------------------------------------------------------------
 // Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *j in {-1,0,1} when it is certainly
-// c + j*u; 0 when the serial loop has to evaluate the step directly.
-// Error budget: |A - exact| <= 2^-24|A| + 2^-29, the fma rounds once (<= 2^-24*1.5), the reference's double add moves
-// the sum by <= 2^-29 u  =>  total < eps = 2^-23(|A|+2).  A NaN row fails every comparison.
-DY4_HD int dy4_tab_pick(float phase, float A, float invu, float eps, float* jf_out)
+// c + j*u: phase_k is farther than the guard band m from both thresholds and inside the outer ones.  0: the serial
+// loop has to evaluate the step directly.  A NaN row fails every comparison.
+DY4_HD int dy4_tab_pick(float phase, float t_lo, float t_hi, float u, float m, int* j)
 {
-    const float q = fmaf(phase, invu, A);
-    const float r = DY4_FADDF(q, 12582912.0f);                  // 1.5*2^23: nearest integer, ties to even
-    const float jf = DY4_FADDF(r, -12582912.0f);
-    const float d = DY4_FADDF(q, -jf);                          // exact
-    *jf_out = jf;
-    return (fabsf(d) < DY4_FADDF(0.5f, -eps)) && (fabsf(jf) <= 1.0f);
+    const float d_lo = DY4_FADDF(phase, -t_lo), d_hi = DY4_FADDF(phase, -t_hi);
+    const float um = DY4_FADDF(u, -m);
+    *j = (phase > t_hi) - (phase < t_lo);
+    return (fabsf(d_lo) > m) && (fabsf(d_hi) > m) && (d_lo > -um) && (d_hi < um);
 }

@@ -12,7 +12,7 @@
 #define WARM 1024
 
 /* One launch over n samples of one stream.  state: fbI fbQ integ phase trigOffset (as the reference's PLLState).
- * theta_out[n]: float trigArg after each sample.  stats[0] += picks, stats[1] += direct evaluations. */
+ * theta_out[n]: float trigArg after each sample.  stats[0] += picks, stats[1] += direct evaluations, stats[2] += wrong picks (must stay 0). */
 void plltab_launch(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out, long* stats)
 {
     dy4_tabrow_t* rows = (dy4_tabrow_t*)malloc(sizeof(dy4_tabrow_t) * (size_t)n);
@@ -39,13 +39,14 @@ void plltab_launch(const float* x, int n, float* state, double w, float Kp, floa
     }
     for (int k = 0; k + 1 < n; k++) {
         const dy4_tabrow_t* r = &rows[k];
-        float jf, eD, th;
-        if (dy4_tab_pick(phase, r->A, r->invu, r->eps, &jf)) {
-            eD = jf < 0.0f ? r->T0 : (jf > 0.0f ? r->T2 : r->T1);
-            th = fmaf(jf, r->u, r->c);
+        float eD;
+        int j;
+        const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);     /* what k_nco derives from the stored phase */
+        if (dy4_tab_pick(phase, r->t_lo, r->t_hi, r->u, r->m, &j)) {
+            eD = j < 0 ? r->T0 : (j > 0 ? r->T2 : r->T1);
+            if (th != fmaf((float)j, r->u, r->c)) stats[2]++;                     /* a certain pick that is wrong: must never happen */
             stats[0]++;
         } else {
-            th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);
             eD = dy4_next_errorD((double)th, x[k + 1]);
             stats[1]++;
         }

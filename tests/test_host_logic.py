@@ -101,7 +101,7 @@ def _plltab_run(lib, pilot, Fs, launches, which="plltab_launch"):
     Ki = np.float32(np.float32(0.01) * np.float32(0.01)) * np.float32(3.555)
     th = np.zeros(pilot.size, np.float32)
     st = np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32)              # PLLState, project.cpp:46-53
-    stats = (C.c_long * 2)(0, 0)
+    stats = (C.c_long * 3)(0, 0, 0)
     a = 0
     for m in launches:
         args = [C.c_void_p(pilot[a:].ctypes.data), int(m), C.c_void_p(st.ctypes.data), C.c_double(w), C.c_float(Kp), C.c_float(Ki),
@@ -110,6 +110,7 @@ def _plltab_run(lib, pilot, Fs, launches, which="plltab_launch"):
         getattr(lib, which)(*args)
         a += m
     assert a == pilot.size
+    assert stats[2] == 0, "a pick declared certain chose the wrong grid point"
     return th, st, (stats[0], stats[1])
 
 
