@@ -31,7 +31,7 @@ struct Dy4PllArgs {
     const float* in; long long in_stride;       // pilot
     double* inv; double* theta; long long wide_stride;  // scratch rows of doubles: 1/x per input sample; trigArg after each sample
     float* tstart = nullptr;                            // scratch [n_streams] (table-driven loop): sample counter at the start of the launch
-    float4* tab = nullptr; long long tab_stride = 0;    // optional [n_streams][tab_stride] 16-byte words, 2 per sample: selects the table-driven loop (dy4_plltab.h)
+    float4* tab = nullptr; long long tab_stride = 0;    // optional [n_streams][tab_stride] 16-byte words, 3 per sample: selects the table-driven loop (dy4_plltab.h)
     float* nco0;                                // scratch [n_streams]: NCO value that opens this launch's row
     float* nco; long long nco_stride;
     float* state;                               // [n_streams][8]: fbI fbQ integ phase trigOffset nco_state pad pad

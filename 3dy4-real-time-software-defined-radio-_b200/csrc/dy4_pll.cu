@@ -225,67 +225,94 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const float* __re
     const float* x = in + (long long)s * in_stride;
     dy4_tabrow_t r;
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
-                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r);
-    float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
-    o[0] = make_float4(r.t_lo, r.t_hi, r.T0, r.T1);
-    o[1] = make_float4(r.T2, r.c, r.u, r.m);
+                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, c.Kp, c.Ki, &r);
+    float4* o = tab + (long long)s * tab_stride + 3 * (long long)k;
+    o[0] = make_float4(r.t_lo, r.t_hi, r.P, r.hm);
+    o[1] = make_float4(r.a0, r.a1, r.a2, r.b0);
+    o[2] = make_float4(r.b1, r.b2, r.u, r.c);
 }
 
 // 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
-// Table rows arrive through a per-lane shared-memory ring filled by cp.async three super-groups (48 samples) ahead,
-// so the loop never waits on global memory.  A super-group of 16 samples is straight-line code: per sample three
-// speculative loop-filter updates, two compares of phaseEst against the row's thresholds, selects — and ONE branch per
-// super-group on "every pick was certain"; if not, the super-group is redone step by step from its saved state.
+// Measured on a B200 (tools/ubench_pick.cu): a dependent FADD 4.9 cycles, FSETP -> FSEL 8.9, the three-candidate step
+// below 21 without and 27 with its guard — and ~55 cycles for every BRANCH a lone warp executes.  So:
+//  * table rows arrive through a per-lane shared-memory ring, ONE bulk asynchronous copy (cp.async.bulk, completing on
+//    the lane's own mbarrier) per super-group of 32 samples, three super-groups ahead: no waiting on global memory and
+//    no issue slots spent on it;
+//  * a super-group is straight-line code: per sample three speculative loop-filter updates (float adds of the table's
+//    precomputed products), two compares of phaseEst against the row's thresholds, selects, and a four-instruction
+//    guard — with ONE branch per super-group on "every pick was certain"; if not, the super-group is redone step by
+//    step from its saved state (tab_redo, out of line).
 // Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
-constexpr int TAB_SG = 16;         // samples per super-group
-constexpr int TAB_SLOTS = 4;       // ring size in super-groups (8 KB per lane)
-constexpr int TAB_LANES = 8;       // most streams per warp (fixed shared-memory stride)
+constexpr int TAB_SG = 32;                         // samples per super-group
+constexpr int TAB_SLOTS = 4;                       // ring size in super-groups
+constexpr int TAB_LANES = 4;                       // most streams per warp
+constexpr int TAB_ROW_Q = 3;                       // 16-byte words per row
+constexpr int TAB_SG_BYTES = TAB_SG * TAB_ROW_Q * 16;
+constexpr int TAB_LANE_Q = TAB_SG * TAB_ROW_Q + 1; // lane stride in 16-byte words: +1 spreads the lanes over the banks
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+__device__ __forceinline__ unsigned tab_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tab_mbar_init(unsigned long long* bar)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tab_smem_u32(bar)));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// one copy of the direct evaluation, out of line: the loop body stays small
-__device__ __noinline__ float tab_direct(float th, float x_next) { return dy4_next_errorD((double)th, x_next); }
-
-// state_k -> state_{k+1} with no branch.  a = (t_lo, t_hi, T0, T1), b = (T2, c, u, m).  Returns whether the pick was
-// certain; if not, integ/phase are garbage and the caller redoes the super-group.
-__device__ __forceinline__ bool tab_step_spec(const float4 a, const float4 b, const PllConst& c, float& integ, float& phase)
+__device__ __forceinline__ void tab_bulk_load(void* dst, const void* src, unsigned long long* bar)
 {
-    const float i0 = __fadd_rn(integ, __fmul_rn(c.Ki, a.z)), i1 = __fadd_rn(integ, __fmul_rn(c.Ki, a.w)), i2 = __fadd_rn(integ, __fmul_rn(c.Ki, b.x));
-    const float p0 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, a.z), i0));
-    const float p1 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, a.w), i1));
-    const float p2 = __fadd_rn(phase, __fadd_rn(__fmul_rn(c.Kp, b.x), i2));
-    const bool neg = phase < a.x, pos = phase > a.y;
-    const float d_lo = __fadd_rn(phase, -a.x), d_hi = __fadd_rn(phase, -a.y), um = __fadd_rn(b.z, -b.w);
-    const bool ok = (fabsf(d_lo) > b.w) && (fabsf(d_hi) > b.w) && (d_lo > -um) && (d_hi < um);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tab_smem_u32(bar)), "n"(TAB_SG_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tab_smem_u32(dst)), "l"(src), "n"(TAB_SG_BYTES), "r"(tab_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool tab_mbar_try(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(tab_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// state_k -> state_{k+1} with no branch.  q0 = (t_lo, t_hi, P, hm), q1 = (a0, a1, a2, b0), q2 = (b1, b2, u, c).
+// `ok` stays true while every pick was certain; if not, integ/phase are garbage and the caller redoes the super-group.
+__device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, const float4 q2, float& integ, float& phase, bool& ok)
+{
+    const float i0 = __fadd_rn(integ, q1.x), i1 = __fadd_rn(integ, q1.y), i2 = __fadd_rn(integ, q1.z);
+    const float p0 = __fadd_rn(phase, __fadd_rn(q1.w, i0));
+    const float p1 = __fadd_rn(phase, __fadd_rn(q2.x, i1));
+    const float p2 = __fadd_rn(phase, __fadd_rn(q2.y, i2));
+    const bool neg = phase < q0.x, pos = phase > q0.y;
+    const float az = fabsf(__fadd_rn(phase, -q0.z));
+    const float v = fminf(az, fabsf(__fadd_rn(az, -q2.z)));
+    ok = ok && (v < q0.w);
     integ = neg ? i0 : (pos ? i2 : i1);
     phase = neg ? p0 : (pos ? p2 : p1);
-    return ok;
 }
 
-// the same step with the fallback: a pick if certain, else this step directly (dy4_pllmath.h), as k_pll does
-__device__ __noinline__ void tab_step_careful(const float4 a, const float4 b, const float* x_next, double T, const PllConst& c, float* integ_io, float* phase_io)
+// A super-group again, carefully: a pick where it is certain, else that step directly (dy4_pllmath.h), as k_pll does.
+// Out of line and looping: it runs for a fraction of a percent of the super-groups once the loop is in lock.
+__device__ __noinline__ void tab_redo(const float4* src, const float* x_next, float* y, double T0, int k, int count, double w, float Kp, float Ki,
+                                      float* integ_io, float* phase_io)
 {
     float integ = *integ_io, phase = *phase_io;
-    int j;
-    float eD;
-    if (dy4_tab_pick(phase, a.x, a.y, b.z, b.w, &j)) eD = j < 0 ? a.z : (j > 0 ? b.x : a.w);
-    else eD = tab_direct(dy4_pll_trigarg(c.w, T, phase), *x_next);      // the input sample is loaded only when it is needed
-    dy4_pll_filter(eD, c.Kp, c.Ki, &integ, &phase);
+#pragma unroll 1
+    for (int r = 0; r < count; r++) {
+        const float4 q0 = src[3 * r], q1 = src[3 * r + 1], q2 = src[3 * r + 2];
+        y[r] = phase;
+        int j;
+        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, q2.z, q0.w, &j))
+            dy4_pll_filter_ab(j < 0 ? q1.x : (j > 0 ? q1.z : q1.y), j < 0 ? q1.w : (j > 0 ? q2.y : q2.x), &integ, &phase);
+        else
+            dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + r + 1), phase), x_next[r]), Kp, Ki, &integ, &phase);
+    }
     *integ_io = integ; *phase_io = phase;
 }
 
+template <bool FENCE>
 __global__ void __launch_bounds__(32)
 k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
           float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
           float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
 {
-    __shared__ float4 ring[TAB_SLOTS * TAB_SG * 2 * TAB_LANES];   // [slot][row half][lane]: lane-interleaved, conflict-free 16-byte accesses
+    __shared__ __align__(16) float4 ring[TAB_SLOTS * TAB_LANES * TAB_LANE_Q];
+    __shared__ __align__(8) unsigned long long bars[TAB_SLOTS * TAB_LANES];
     const int lane = threadIdx.x;
     const int s = blockIdx.x * lanes + lane;
     if (lane >= lanes || s >= n_streams || n <= 0) return;
@@ -304,64 +331,60 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     int kd = 0;
     if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
     const int n_sg = (n_pick - kd) / TAB_SG;         // whole super-groups after the direct part
-    auto issue = [&](int i) {                        // super-group i -> slot i % TAB_SLOTS (past the end: the last one again, unused)
-        const int ic = min(i, n_sg - 1);
-        float4* dst = ring + (i % TAB_SLOTS) * (TAB_SG * 2 * TAB_LANES) + lane;
-        const float4* src = rows + 2 * ((long long)kd + (long long)ic * TAB_SG);
 #pragma unroll
-        for (int r = 0; r < TAB_SG * 2; r++) cp_async16(dst + r * TAB_LANES, src + r);
-        cp_async_commit();
+    for (int i = 0; i < TAB_SLOTS; i++) tab_mbar_init(&bars[i * TAB_LANES + lane]);   // each lane owns its barriers: no CTA-wide sync
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    auto issue = [&](int i) {                        // super-group i -> slot i % TAB_SLOTS
+        if (i < n_sg) {
+            const int slot = i % TAB_SLOTS;
+            tab_bulk_load(ring + (slot * TAB_LANES + lane) * TAB_LANE_Q, rows + TAB_ROW_Q * ((long long)kd + (long long)i * TAB_SG), &bars[slot * TAB_LANES + lane]);
+        }
     };
-    if (n_sg > 0)
-        for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
+    for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
     // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
     dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
-    {   // direct part, inputs loaded one group of four ahead of their use
-        float xn[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) xn[r] = x[min(1 + r, n - 1)];
-        for (int k = 0; k < kd; k += 4) {
-            float xc[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) { xc[r] = xn[r]; xn[r] = x[min(k + 5 + r, n - 1)]; }
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (k + r < kd) {
-                    y[k + r] = phase;
-                    dy4_pll_filter(tab_direct(dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + r + 1), phase), xc[r]), c.Kp, c.Ki, &integ, &phase);
-                }
+    {   // direct part (one inlined copy of the evaluation), inputs loaded four samples ahead of their use
+        float x0 = x[min(1, n - 1)], x1 = x[min(2, n - 1)], x2 = x[min(3, n - 1)], x3 = x[min(4, n - 1)];
+#pragma unroll 1
+        for (int k = 0; k < kd; k++) {
+            const float xc = x0;
+            x0 = x1; x1 = x2; x2 = x3; x3 = x[min(k + 5, n - 1)];
+            y[k] = phase;
+            dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase), xc), c.Kp, c.Ki, &integ, &phase);
         }
     }
+#pragma unroll 1
     for (int i = 0; i < n_sg; i++) {
+        const int slot = i % TAB_SLOTS;
+        // slot (i-1) % TAB_SLOTS was read in the previous trip: order those reads before the async write that refills it.
+        // (Every value read from it has been consumed by then — `ok` depends on all of them — so DY4_PLL_FENCE=0 drops
+        // the fence for an A/B measurement; the default keeps it.)
+        if (FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(i + TAB_SLOTS - 1);
-        cp_async_wait<TAB_SLOTS - 1>();              // super-group i has landed
-        const float4* src = ring + (i % TAB_SLOTS) * (TAB_SG * 2 * TAB_LANES) + lane;
+        unsigned long long* bar = &bars[slot * TAB_LANES + lane];
+        const unsigned parity = (unsigned)((i / TAB_SLOTS) & 1);
+        if (!tab_mbar_try(bar, parity)) { while (!tab_mbar_try(bar, parity)) { } }     // super-group i has landed (normally long ago)
+        const float4* src = ring + (slot * TAB_LANES + lane) * TAB_LANE_Q;
         const int k = kd + i * TAB_SG;
         float si = integ, sp = phase;
-        float ph[TAB_SG];
         bool ok = true;
 #pragma unroll
-        for (int r = 0; r < TAB_SG; r++) {
-            ph[r] = sp;
-            ok &= tab_step_spec(src[(2 * r) * TAB_LANES], src[(2 * r + 1) * TAB_LANES], c, si, sp);
-        }
-        if (ok) {
+        for (int r = 0; r < TAB_SG; r += 4) {
+            float ph[4];
 #pragma unroll
-            for (int r = 0; r < TAB_SG; r += 4) *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[r], ph[r + 1], ph[r + 2], ph[r + 3]);
-        } else {                                     // rare: redo from the saved state, step by step
-            si = integ; sp = phase;
-#pragma unroll 1
-            for (int r = 0; r < TAB_SG; r++) {
-                y[k + r] = sp;
-                tab_step_careful(src[(2 * r) * TAB_LANES], src[(2 * r + 1) * TAB_LANES], x + k + r + 1, dy4_pll_count(T0, k + r + 1), c, &si, &sp);
+            for (int q = 0; q < 4; q++) {
+                ph[q] = sp;
+                tab_step_spec(src[3 * (r + q)], src[3 * (r + q) + 1], src[3 * (r + q) + 2], si, sp, ok);
             }
+            *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[0], ph[1], ph[2], ph[3]);   // (rewritten by tab_redo if a pick was not certain)
         }
+        if (!ok) { si = integ; sp = phase; tab_redo(src, x + k + 1, y + k, T0, k, TAB_SG, c.w, c.Kp, c.Ki, &si, &sp); }
         integ = si; phase = sp;
     }
-    cp_async_wait<0>();
-    for (int k = kd + n_sg * TAB_SG; k < n_pick; k++) {         // tail: rows straight from global memory
-        y[k] = phase;
-        tab_step_careful(__ldg(rows + 2 * (long long)k), __ldg(rows + 2 * (long long)k + 1), x + k + 1, dy4_pll_count(T0, k + 1), c, &integ, &phase);
+    {   // tail: rows straight from global memory
+        const int k = kd + n_sg * TAB_SG;
+        if (k < n_pick) tab_redo(rows + TAB_ROW_Q * (long long)k, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
     }
     // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
     y[n - 1] = phase;
@@ -450,8 +473,11 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
             lanes = std::max(1, std::min(lanes, TAB_LANES));
-            k_pll_tab<<<(a.n_streams + lanes - 1) / lanes, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, reinterpret_cast<float*>(a.theta), 2 * a.wide_stride,
-                                                                       a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
+            static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);
+            const int grid = (a.n_streams + lanes - 1) / lanes;
+            float* ph = reinterpret_cast<float*>(a.theta);
+            if (fence) k_pll_tab<true><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
+            else k_pll_tab<false><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
             g_dy4_launches += 3;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;

@@ -38,25 +38,28 @@
 #define DY4_TAB_EARLY 1536
 
 // One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
-// 32 bytes, read as two 16-byte words.  With P = c - RN_d(w*T_k):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is
+// 48 bytes, read as three 16-byte words.  With P = c - RN_d(w*T_k):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is
 // c - u, c, c + u  for  phase_k  in  (P-1.5u, P-.5u), (P-.5u, P+.5u), (P+.5u, P+1.5u).
 typedef struct {
     float t_lo, t_hi; // P - u/2, P + u/2 rounded to float (NaN: row not usable)
-    float T0, T1;     // errorD of step k+1 if trigArg_k = c - u, c
-    float T2;         //                                   c + u
-    float c;          // predicted trigArg_k rounded to float
-    float u;          // grid spacing of c's binade
-    float m;          // guard band around a threshold: rounding-error budget of the pick
+    float P, hm;      // P as a float; hm = u/2 - m, m the guard band around a threshold (rounding-error budget of the pick)
+    float a0, a1, a2; // Ki*errorD of step k+1 if trigArg_k = c - u, c, c + u   (filter.cpp:207's product)
+    float b0, b1, b2; // Kp*errorD                                              (filter.cpp:210's product)
+    float u, c;       // grid spacing of c's binade; c = predicted trigArg_k rounded to float
 } dy4_tabrow_t;
 
 // float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
 DY4_HD double dy4_pll_count(double T0, int steps) { return fmin(T0 + (double)steps, 16777216.0); }
 
-// loop filter + phase accumulator, filter.cpp:207,210 (float, unfused, this order)
+// loop filter + phase accumulator, filter.cpp:207,210 (float, unfused, this order); a = Ki*errorD, b = Kp*errorD
+DY4_HD void dy4_pll_filter_ab(float a, float b, float* integ, float* phase)
+{
+    *integ = DY4_FADDF(*integ, a);
+    *phase = DY4_FADDF(*phase, DY4_FADDF(b, *integ));
+}
 DY4_HD void dy4_pll_filter(float eD, float Kp, float Ki, float* integ, float* phase)
 {
-    *integ = DY4_FADDF(*integ, DY4_FMULF(Ki, eD));
-    *phase = DY4_FADDF(*phase, DY4_FADDF(DY4_FMULF(Kp, eD), *integ));
+    dy4_pll_filter_ab(DY4_FMULF(Ki, eD), DY4_FMULF(Kp, eD), integ, phase);
 }
 
 // exact trigArg of filter.cpp:214 as a float value
@@ -109,7 +112,7 @@ DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 // th_hat: predicted trigArg of this sample; wT = RN_d(w*T_k);
 // x_next: input of step k+1 (has_next == 0 for the last sample of a launch: T unused).
 // `force_invalid`: rows the serial loop must evaluate directly whatever the prediction says.
-DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_tabrow_t* r)
+DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, float Kp, float Ki, dy4_tabrow_t* r)
 {
     const float c = DY4_D2F(th_hat);
     const int bits = dy4_f2i_bits(c);
@@ -118,29 +121,33 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
     const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
     const double P = DY4_SUB((double)c, wT), hu = DY4_MUL(0.5, (double)u);
-    const float t_lo = DY4_D2F(DY4_SUB(P, hu)), t_hi = DY4_D2F(DY4_ADD(P, hu));
+    const float t_lo = DY4_D2F(DY4_SUB(P, hu)), t_hi = DY4_D2F(DY4_ADD(P, hu)), Pf = DY4_D2F(P);
     const float nan = dy4_i2f_bits(0x7fc00000);
     r->c = c; r->u = u;
-    r->t_lo = ok ? t_lo : nan; r->t_hi = ok ? t_hi : nan;
-    // |t - exact| <= 2^-24|t| (half an ulp) + 2^-29 u from the reference's double add; the guard is twice the first
-    // term plus eight times the second (the float subtraction phase - t adds at most 2^-24 of the guard itself)
-    r->m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fmaxf(fabsf(t_lo), fabsf(t_hi))), DY4_FMULF(1.4901161193847656e-08f, u));
-    r->T0 = r->T1 = r->T2 = 0.0f;
+    r->t_lo = ok ? t_lo : nan; r->t_hi = ok ? t_hi : nan; r->P = ok ? Pf : nan;
+    // each of t_lo, t_hi, P is within 2^-24 of its magnitude (half an ulp) of the exact value, and the reference's double
+    // add moves the sum by at most 2^-29 u.  The guard band is FOUR half-ulps of the largest of them (the pick compares
+    // phase with t_lo/t_hi and measures its distance from P: two roundings) plus 2^-26 u.
+    const float m = DY4_FADDF(DY4_FMULF(2.384185791015625e-07f, fmaxf(fmaxf(fabsf(t_lo), fabsf(t_hi)), fabsf(Pf))), DY4_FMULF(1.4901161193847656e-08f, u));
+    r->hm = DY4_FADDF(DY4_FMULF(0.5f, u), -m);
+    r->a0 = r->a1 = r->a2 = r->b0 = r->b1 = r->b2 = 0.0f;
     if (ok && has_next) {
-        r->T0 = dy4_next_errorD((double)DY4_FADDF(c, -u), x_next);
-        r->T1 = dy4_next_errorD((double)c, x_next);
-        r->T2 = dy4_next_errorD((double)DY4_FADDF(c, u), x_next);
+        const float e0 = dy4_next_errorD((double)DY4_FADDF(c, -u), x_next);
+        const float e1 = dy4_next_errorD((double)c, x_next);
+        const float e2 = dy4_next_errorD((double)DY4_FADDF(c, u), x_next);
+        r->a0 = DY4_FMULF(Ki, e0); r->a1 = DY4_FMULF(Ki, e1); r->a2 = DY4_FMULF(Ki, e2);
+        r->b0 = DY4_FMULF(Kp, e0); r->b1 = DY4_FMULF(Kp, e1); r->b2 = DY4_FMULF(Kp, e2);
     }
 }
 
 // ---- 3. the pick ----------------------------------------------------------------------------------------------------
 // Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *j in {-1,0,1} when it is certainly
-// c + j*u: phase_k is farther than the guard band m from both thresholds and inside the outer ones.  0: the serial
-// loop has to evaluate the step directly.  A NaN row fails every comparison.
-DY4_HD int dy4_tab_pick(float phase, float t_lo, float t_hi, float u, float m, int* j)
+// c + j*u: |phase_k - P| lies inside [0, u/2 - m) or (u/2 + m, 3u/2 - m), i.e. min(|z|, ||z| - u|) < u/2 - m.
+// 0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
+DY4_HD int dy4_tab_pick(float phase, float t_lo, float t_hi, float P, float u, float hm, int* j)
 {
-    const float d_lo = DY4_FADDF(phase, -t_lo), d_hi = DY4_FADDF(phase, -t_hi);
-    const float um = DY4_FADDF(u, -m);
+    const float az = fabsf(DY4_FADDF(phase, -P));
+    const float v = fminf(az, fabsf(DY4_FADDF(az, -u)));
     *j = (phase > t_hi) - (phase < t_lo);
-    return (fabsf(d_lo) > m) && (fabsf(d_hi) > m) && (d_lo > -um) && (d_hi < um);
+    return v < hm;
 }

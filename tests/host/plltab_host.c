@@ -30,7 +30,7 @@ void plltab_launch(const float* x, int n, float* state, double w, float Kp, floa
     }
     /* 2. table */
     for (int k = 0; k < n; k++)
-        dy4_tab_make_row(th_hat[k], DY4_MUL(w, dy4_pll_count(T0, k + 1)), k + 1 < n ? x[k + 1] : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &rows[k]);
+        dy4_tab_make_row(th_hat[k], DY4_MUL(w, dy4_pll_count(T0, k + 1)), k + 1 < n ? x[k + 1] : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, Kp, Ki, &rows[k]);
     /* 3. serial */
     float fbI = state[0], fbQ = state[1], integ = state[2], phase = state[3];
     {
@@ -39,19 +39,17 @@ void plltab_launch(const float* x, int n, float* state, double w, float Kp, floa
     }
     for (int k = 0; k + 1 < n; k++) {
         const dy4_tabrow_t* r = &rows[k];
-        float eD;
         int j;
-        const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);     /* what k_nco derives from the stored phase */
-        if (dy4_tab_pick(phase, r->t_lo, r->t_hi, r->u, r->m, &j)) {
-            eD = j < 0 ? r->T0 : (j > 0 ? r->T2 : r->T1);
+        const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);     /* what k_nco_phase derives from the stored phase */
+        theta_out[k] = th;
+        if (dy4_tab_pick(phase, r->t_lo, r->t_hi, r->P, r->u, r->hm, &j)) {
             if (th != fmaf((float)j, r->u, r->c)) stats[2]++;                     /* a certain pick that is wrong: must never happen */
+            dy4_pll_filter_ab(j < 0 ? r->a0 : (j > 0 ? r->a2 : r->a1), j < 0 ? r->b0 : (j > 0 ? r->b2 : r->b1), &integ, &phase);
             stats[0]++;
         } else {
-            eD = dy4_next_errorD((double)th, x[k + 1]);
+            dy4_pll_filter(dy4_next_errorD((double)th, x[k + 1]), Kp, Ki, &integ, &phase);
             stats[1]++;
         }
-        theta_out[k] = th;
-        dy4_pll_filter(eD, Kp, Ki, &integ, &phase);
     }
     {
         const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, n), phase);
