@@ -54,6 +54,7 @@ struct dy4_pipeline {
     struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
     WorkSet ws[2];
     float* ws_nco0 = nullptr;
+    double* pred_state = nullptr;                    // table-driven PLL: the predictor's own state, [2][n_streams][8], then [2][n_streams] turns
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
     // RDS filtering front end (DY4_FLAG_RDS): its own stream beside the stereo PLL
     float *rds_f = nullptr, *rds_carrier = nullptr, *rds_nco_i = nullptr, *rds_nco_q = nullptr, *rds_lp = nullptr, *rds_out = nullptr;
@@ -68,6 +69,7 @@ struct dy4_pipeline {
     long long rds_blocks_since_drain = 0;
     cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
+    bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
     // host-facing staging
@@ -134,6 +136,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     CU(cudaMemsetAsync(p->iq_tail, 128, S * DY4_IQ_TAIL, st));            // byte 128 = 0.0f: zero RF history (project.cpp:242-243)
     CU(cudaMemsetAsync(p->if_tail, 0, 3 * S * DY4_IF_TAIL * sizeof(float), st));
     p->seq = 0;
+    p->pll_fresh = true;
     CU(cudaMemsetAsync(p->mix_tail, 0, S * DY4_MIX_TAIL * sizeof(float), st));
     std::vector<float> h(S * 8, 0.0f);
     for (size_t s = 0; s < S; s++) { h[s * 8 + 0] = 1.0f; h[s * 8 + 5] = 1.0f; }   // PLLState, project.cpp:46-53
@@ -206,7 +209,8 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             if (p->pll_table) CU(cudaMalloc(&w.tab, 12 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
         }
     }
-    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 4 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, then sample counter
+    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
+    if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, 2 * (size_t)p->n_streams * 9 * sizeof(double)));   // [2][S][8] predictor state + [2][S] turns
     if (p->stereo && !p->s_pll) {
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -250,6 +254,8 @@ struct SubChunk {                        // one sub-chunk of the job: where its 
     const uint8_t* iq; int nb;
     int16_t* pcm; float* audio; float* d_if;
     int set; float* if_tail_in; float* if_tail_out;
+    int fresh = 0;                       // table-driven PLL: leading samples of a fresh stream left to the direct loop
+    int pred_carry = 0;                  // table-driven PLL: the prediction continues from the previous sub-chunk's (not the first of a call)
 };
 
 float* if_tail_slot(dy4_pipeline* p, long long seq) { return p->if_tail + (size_t)(seq % 3) * p->n_streams * DY4_IF_TAIL; }
@@ -383,6 +389,11 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
     pa.tab = w.tab; pa.tab_stride = 3 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    if (w.tab) {
+        pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
+        pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;
+        pa.pred_carry = c.pred_carry; pa.fresh = c.fresh; pa.nco0b = p->ws_nco0 + (size_t)(4 + c.set) * p->n_streams;
+    }
     pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
     { Timer t(p, (parts & DY4_PLL_LOOP) ? DY4_K_PLL : DY4_K_PLL_AUX, st); CU(dy4_launch_pll_parts(pa, st, parts)); }
     return DY4_OK;
@@ -483,12 +494,21 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     int prev_b = 0, prev_i = 0;
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
         const int b = plan[i].first;
-        const SubChunk c = sub(b, plan[i].second, p->seq);
+        SubChunk c = sub(b, plan[i].second, p->seq);
+        // Table-driven PLL (dy4_pll.cu).  Sub-chunk 0 starts from the exact carried state; at the start of a stream —
+        // and of every multi-sub-chunk call, where the signal may have jumped — its first samples go through the direct
+        // loop while the PLL (re)acquires lock.  Sub-chunk 1 is predicted from the exact state too (its prediction waits
+        // for the loop of sub-chunk 0, on the PLL stream); from sub-chunk 2 on the prediction carries its own state and
+        // runs with the FIR kernels on the main stream, beside the serial loop of the sub-chunk before.
+        c.pred_carry = i < 2 ? 0 : (i == 2 ? 1 : 2);
+        c.fresh = (i == 0 && (p->pll_fresh || plan.size() > 1)) ? 1536 : 0;       // DY4_TAB_EARLY (dy4_plltab.h)
+        p->pll_fresh = false;
+        const bool prep_on_pll = p->pll_table && i == 1;
         if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
         // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
         if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
-        if ((rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
+        if (!prep_on_pll && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
             CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
@@ -497,7 +517,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
         CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
-        if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_LOOP))) return rc;
+        if ((rc = run_pll(p, c, p->s_pll, prep_on_pll ? (DY4_PLL_PREP | DY4_PLL_LOOP) : DY4_PLL_LOOP))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
         if (have_prev) {
             CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
@@ -514,6 +534,22 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
     }
     if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
+    if (p->pred_state && std::getenv("DY4_DEBUG_PRED")) {          // development aid: predictor state vs PLL state of stream 0
+        CU(cudaDeviceSynchronize());
+        double h[8]; float f[8];
+        CU(cudaMemcpy(h, p->pred_state, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(h + 4, p->pred_state + (size_t)p->n_streams * 8, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(f, p->pll_state, 8 * sizeof(float), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "pred[0] %g %.9g %g %g | pred[1] %g %.9g %g %g | pll integ %g phase %.9g T %g | seq %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7],
+                f[2], f[3], f[4], (long long)p->seq);
+        for (int set = 0; set < 2; set++) {
+            double th[4]; float row[24];
+            CU(cudaMemcpy(th, p->ws[set].theta + 2000, sizeof(th), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(row, p->ws[set].tab + 3 * 2000, sizeof(row), cudaMemcpyDeviceToHost));
+            fprintf(stderr, " set %d th_hat[2000..] %.6f %.6f | row2000: t_lo %.7g t_hi %.7g P %.7g hm %g a %g %g %g b %g %g %g u %g c %.6f | row2001 t_lo %.7g c %.6f\n", set, th[0], th[1],
+                    row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7], row[8], row[9], row[10], row[11], row[12], row[23]);
+        }
+    }
     return DY4_OK;
 }
 
@@ -604,7 +640,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
-    cudaFree(p->ws_nco0);
+    cudaFree(p->ws_nco0); cudaFree(p->pred_state);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); }
@@ -865,6 +901,7 @@ extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
 
 extern "C" int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf)
 {
+    if (p) p->pll_fresh = false;                     // whatever the restored streams are, they are not at sample 0 by construction
     if (!p || !host_buf) return DY4_ERR_ARG;
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());

@@ -181,9 +181,17 @@ constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop f
 
 // 1. predicted trigArg of every sample (double) -> theta row.  One thread per (stream, segment); the first WARM samples
 // of a launch start from the exact carried state, later segments from that state as a guess plus the warm-up.
+// `pred_in` / `pred_out`: [n_streams][8] doubles (integ, phase, sample counter after / before the launch, turns) — the
+// predictor's own state at the start / end of the launch.  carry == 0: the launch starts from the exact carried PLL
+// state (the loop of the previous launch has finished).  carry != 0: from where the previous launch's prediction ended,
+// so that prediction and table of sub-chunk c+1 do not wait for the serial loop of sub-chunk c (dy4_pipeline.cu).
+// The loop locks to the pilot modulo 2*pi, and after a loss of lock the predictor may settle a whole number of turns
+// away from the true phaseEst — a table built there never matches.  So every serial launch reports how many turns its
+// prediction was off (`need`, k_pll_tab), and with carry == 2 the launch two later shifts its start by that much.
 __global__ void __launch_bounds__(128)
-k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __restrict__ state,
-              double* __restrict__ th_hat, long long wide_stride, int n, PllConst c)
+k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __restrict__ state, const double* __restrict__ pred_in,
+              double* __restrict__ pred_out, const double* __restrict__ need, int carry, double* __restrict__ th_hat, long long wide_stride,
+              int n, PllConst c)
 {
     const int s = blockIdx.x;
     const int s0 = (blockIdx.y * blockDim.x + threadIdx.x) * PRED_SEG;
@@ -191,8 +199,15 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
     const float* st = state + (long long)s * 8;
     const float* x = in + (long long)s * in_stride;
     double* y = th_hat + (long long)s * wide_stride;
-    const double T0 = (double)st[4], Kp = (double)c.Kp, Ki = (double)c.Ki;
-    double integ = (double)st[2], phase = (double)st[3];
+    const double Kp = (double)c.Kp, Ki = (double)c.Ki;
+    double integ, phase, T0, turns = 0.0;
+    if (carry) {
+        integ = pred_in[8 * s]; phase = pred_in[8 * s + 1]; T0 = pred_in[8 * s + 2]; turns = pred_in[8 * s + 4];
+        if (carry == 2) {
+            const double d = need[s] - turns;
+            if (fabs(d) < 1e6) { phase = fma(d, 6.28318530717958647692, phase); turns = need[s]; }
+        }
+    } else { integ = (double)st[2]; phase = (double)st[3]; T0 = (double)st[4]; }
     const int kw = max(0, s0 - PRED_WARM), k1 = min(n, s0 + PRED_SEG);
     double th_prev = c.w * dy4_pll_count(T0, kw) + phase;
     int k = kw;
@@ -211,17 +226,21 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
         th_prev = dy4_pred_step(__ldg(x + k), th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase);
         if (k >= s0) y[k] = th_prev;
     }
+    if (k1 == n) {                                                  // the thread of the last segment: state for the next launch
+        pred_out[8 * s] = integ; pred_out[8 * s + 1] = phase; pred_out[8 * s + 2] = dy4_pll_count(T0, n); pred_out[8 * s + 3] = T0;
+        pred_out[8 * s + 4] = turns;
+    }
 }
 
 // 2. one table row per sample: the exact errorD of the next step for the three float grid points around the prediction
 __global__ void __launch_bounds__(128)
-k_pll_table(const float* __restrict__ in, long long in_stride, const float* __restrict__ state,
+k_pll_table(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
             const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
 {
     const int s = blockIdx.x;
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const double T0 = (double)state[(long long)s * 8 + 4];
+    const double T0 = pred_out[8 * s + 3];                          // sample counter at the start of this launch (k_pll_predict)
     const float* x = in + (long long)s * in_stride;
     dy4_tabrow_t r;
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
@@ -309,7 +328,7 @@ template <bool FENCE>
 __global__ void __launch_bounds__(32)
 k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
           float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
-          float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
+          const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
 {
     __shared__ __align__(16) float4 ring[TAB_SLOTS * TAB_LANES * TAB_LANE_Q];
     __shared__ __align__(8) unsigned long long bars[TAB_SLOTS * TAB_LANES];
@@ -343,16 +362,37 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     };
     for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
     // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
-    dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
-    {   // direct part (one inlined copy of the evaluation), inputs loaded four samples ahead of their use
-        float x0 = x[min(1, n - 1)], x1 = x[min(2, n - 1)], x2 = x[min(3, n - 1)], x3 = x[min(4, n - 1)];
+    if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
+    else {
+        // direct part: the steps of k_pll (pll_step_fast: straight-line groups of four whose independent work overlaps
+        // the dependent chain, ~450 cycles per sample), samples 0 .. kd; it ends holding state_kd
+        PllRegs r = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
+        dy4_nco_t o;
+        o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
+        pll_advance<1, false>(detector_libm(x[0], r.fbI, r.fbQ), r, c, o, n > 1 && x[1] < 0.0f);
+        auto xat = [&](int i) { return x[min(i, n - 1)]; };
+        float v0 = xat(1), v1 = xat(2), v2 = xat(3), v3 = xat(4), v4 = xat(5);
+        int k = 0;                                               // r holds the state after sample k
 #pragma unroll 1
-        for (int k = 0; k < kd; k++) {
-            const float xc = x0;
-            x0 = x1; x1 = x2; x2 = x3; x3 = x[min(k + 5, n - 1)];
-            y[k] = phase;
-            dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase), xc), c.Kp, c.Ki, &integ, &phase);
+        for (; k + 4 <= kd; k += 4) {
+            const float c0 = v0, c1 = v1, c2 = v2, c3 = v3, c4 = v4;
+            v0 = c4; v1 = xat(k + 6); v2 = xat(k + 7); v3 = xat(k + 8); v4 = xat(k + 9);
+            float q0, q1, q2, q3;
+            if (fast_ok(c0) && fast_ok(c1) && fast_ok(c2) && fast_ok(c3)) {
+                q0 = r.phase; pll_step_fast<1, false>(c0, dy4_recip(c0), c1, r, c, o);
+                q1 = r.phase; pll_step_fast<1, false>(c1, dy4_recip(c1), c2, r, c, o);
+                q2 = r.phase; pll_step_fast<1, false>(c2, dy4_recip(c2), c3, r, c, o);
+                q3 = r.phase; pll_step_fast<1, false>(c3, dy4_recip(c3), c4, r, c, o);
+            } else {
+                q0 = r.phase; pll_step_any<false>(c0, c1, r, c, o, true);
+                q1 = r.phase; pll_step_any<false>(c1, c2, r, c, o, true);
+                q2 = r.phase; pll_step_any<false>(c2, c3, r, c, o, true);
+                q3 = r.phase; pll_step_any<false>(c3, c4, r, c, o, true);
+            }
+            *reinterpret_cast<float4*>(y + k) = make_float4(q0, q1, q2, q3);
         }
+        for (; k < kd; k++) { y[k] = r.phase; pll_step_any<false>(xat(k + 1), xat(k + 2), r, c, o, true); }
+        integ = r.integ; phase = r.phase;
     }
 #pragma unroll 1
     for (int i = 0; i < n_sg; i++) {
@@ -394,6 +434,8 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
     st[4] = (float)dy4_pll_count(T0, n);
     st[5] = nco_value(th, c.ncoScale, c.phaseAdjust);          // nco_state for the next launch (filter.cpp:218-219)
+    // how many whole turns the prediction of this launch ended away from the true phaseEst (see k_pll_predict)
+    need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
 }
 
 // NCO row from the phaseEst row of k_pll_tab: trigArg[k-1] = RN_f(RN_d(w*T) + phase[k-1]) (filter.cpp:214), then as k_nco
@@ -466,25 +508,53 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
     static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
     // Table-driven loop (dy4_plltab.h) when the caller provides the row buffer: predict -> table -> serial pick.
     static const int tab_lanes_env = std::getenv("DY4_PLL_LANES") ? atoi(std::getenv("DY4_PLL_LANES")) : 0;
+    if (a.tab && a.fresh > 0 && a.n > a.fresh + 64) {
+        // First launch of a stream.  While the loop acquires lock the detector crosses +-pi, where one ulp decides the
+        // sign of a 2*pi jump: the predictor cannot know on which turn phaseEst settles, and a table built around the
+        // wrong turn never matches.  So the first `fresh` samples run through the direct loop (k_pll), and prediction,
+        // table and picks start from the exact state it leaves, on the rest of the launch.
+        const int E = a.fresh;                               // a multiple of 4: every row offset stays 16-byte aligned
+        Dy4PllArgs A = a, B = a;
+        A.tab = nullptr; A.n = E; A.fresh = 0;
+        B.in = a.in + E; B.nco = a.nco + E; B.theta = a.theta + E; B.inv = a.inv + E; B.n = a.n - E; B.fresh = 0; B.pred_carry = 0;
+        B.nco0 = a.nco0b;
+        cudaError_t e = cudaSuccess;
+        if (parts & DY4_PLL_PREP) e = dy4_launch_pll_parts(A, st, DY4_PLL_PREP);
+        if (e == cudaSuccess && (parts & DY4_PLL_LOOP)) {
+            e = dy4_launch_pll_parts(A, st, DY4_PLL_LOOP);
+            if (e == cudaSuccess) e = dy4_launch_pll_parts(B, st, DY4_PLL_PREP | DY4_PLL_LOOP);
+        }
+        if (e == cudaSuccess && (parts & DY4_PLL_NCO)) {
+            e = dy4_launch_pll_parts(A, st, DY4_PLL_NCO);
+            if (e == cudaSuccess) e = dy4_launch_pll_parts(B, st, DY4_PLL_NCO);
+        }
+        return e;
+    }
     if (a.tab) {
-        if (parts & DY4_PLL_LOOP) {
+        if (parts & DY4_PLL_PREP) {                          // time-parallel: may run beside the serial loop of the previous launch
             const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
-            k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.n, c);
-            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.pred_in, a.pred_out, a.need, a.pred_carry,
+                                                                                 a.theta, a.wide_stride, a.n, c);
+            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            g_dy4_launches += 2;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        if (parts & DY4_PLL_LOOP) {
             int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
             lanes = std::max(1, std::min(lanes, TAB_LANES));
             static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);
             const int grid = (a.n_streams + lanes - 1) / lanes;
-            float* ph = reinterpret_cast<float*>(a.theta);
-            if (fence) k_pll_tab<true><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
-            else k_pll_tab<false><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.state, a.n, a.n_streams, c, lanes);
-            g_dy4_launches += 3;
+            float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
+            if (fence) k_pll_tab<true><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes);
+            else k_pll_tab<false><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes);
+            g_dy4_launches++;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
         if (parts & DY4_PLL_NCO) {
             dim3 grid(a.n_streams, (a.n + 255) / 256);
-            k_nco_phase<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.theta), 2 * a.wide_stride, a.nco0, a.tstart, a.nco, a.nco_stride, a.n, c);
+            k_nco_phase<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.inv), 2 * a.wide_stride, a.nco0, a.tstart, a.nco, a.nco_stride, a.n, c);
             g_dy4_launches++;
         }
         return cudaGetLastError();

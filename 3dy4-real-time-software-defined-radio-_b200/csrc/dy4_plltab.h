@@ -125,10 +125,10 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     const float nan = dy4_i2f_bits(0x7fc00000);
     r->c = c; r->u = u;
     r->t_lo = ok ? t_lo : nan; r->t_hi = ok ? t_hi : nan; r->P = ok ? Pf : nan;
-    // each of t_lo, t_hi, P is within 2^-24 of its magnitude (half an ulp) of the exact value, and the reference's double
-    // add moves the sum by at most 2^-29 u.  The guard band is FOUR half-ulps of the largest of them (the pick compares
-    // phase with t_lo/t_hi and measures its distance from P: two roundings) plus 2^-26 u.
-    const float m = DY4_FADDF(DY4_FMULF(2.384185791015625e-07f, fmaxf(fmaxf(fabsf(t_lo), fabsf(t_hi)), fabsf(Pf))), DY4_FMULF(1.4901161193847656e-08f, u));
+    // Each of t_lo, t_hi, P is within 2^-24 of its magnitude (half an ulp) of the exact value, and the reference's double
+    // add moves the sum by at most 2^-29 u.  The pick compares phase with t_lo / t_hi and measures its distance from P,
+    // so two of those roundings can add up: the guard band is 2.5 half-ulps of the largest of the three plus 2^-26 u.
+    const float m = DY4_FADDF(DY4_FMULF(1.4901161193847656e-07f, fmaxf(fmaxf(fabsf(t_lo), fabsf(t_hi)), fabsf(Pf))), DY4_FMULF(1.4901161193847656e-08f, u));
     r->hm = DY4_FADDF(DY4_FMULF(0.5f, u), -m);
     r->a0 = r->a1 = r->a2 = r->b0 = r->b1 = r->b2 = 0.0f;
     if (ok && has_next) {

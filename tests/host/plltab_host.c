@@ -13,20 +13,31 @@
 
 /* One launch over n samples of one stream.  state: fbI fbQ integ phase trigOffset (as the reference's PLLState).
  * theta_out[n]: float trigArg after each sample.  stats[0] += picks, stats[1] += direct evaluations, stats[2] += wrong picks (must stay 0). */
+void plltab_launch_carry(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out, long* stats, double* pred, int carry);
 void plltab_launch(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out, long* stats)
+{
+    double pred[4];
+    plltab_launch_carry(x, n, state, w, Kp, Ki, theta_out, stats, pred, 0);
+}
+
+/* pred: the predictor's own state (integ, phase, sample counter, -) carried from launch to launch as k_pll_predict does:
+ * with carry != 0 the prediction starts from it instead of the exact PLL state. */
+void plltab_launch_carry(const float* x, int n, float* state, double w, float Kp, float Ki, float* theta_out, long* stats, double* pred, int carry)
 {
     dy4_tabrow_t* rows = (dy4_tabrow_t*)malloc(sizeof(dy4_tabrow_t) * (size_t)n);
     double* th_hat = (double*)malloc(sizeof(double) * (size_t)n);
-    const double T0 = (double)state[4];
+    const double T0 = carry ? pred[2] : (double)state[4];
+    const double g_integ = carry ? pred[0] : (double)state[2], g_phase = carry ? pred[1] : (double)state[3];
     /* 1. predict: segment i covers [i*SEG, (i+1)*SEG), warm-up from the launch-start state */
     for (int s0 = 0; s0 < n; s0 += SEG) {
         int kw = s0 - WARM; if (kw < 0) kw = 0;
-        double integ = (double)state[2], phase = (double)state[3];
+        double integ = g_integ, phase = g_phase;
         double th_prev = w * dy4_pll_count(T0, kw) + phase;       /* trigArg of step kw-1 (guess unless kw == 0) */
         for (int k = kw; k < s0 + SEG && k < n; k++) {
             th_prev = dy4_pred_step(x[k], th_prev, DY4_MUL(w, dy4_pll_count(T0, k + 1)), (double)Kp, (double)Ki, &integ, &phase);
             if (k >= s0) th_hat[k] = th_prev;
         }
+        if (s0 + SEG >= n) { pred[0] = integ; pred[1] = phase; pred[2] = dy4_pll_count(T0, n); pred[3] = T0; }
     }
     /* 2. table */
     for (int k = 0; k < n; k++)
