@@ -162,7 +162,7 @@ def workload_config():
         "mode": MODE, "stereo": bool(STEREO), "rds": RDS, "streams_per_gpu": STREAMS_PER_GPU, "blocks_per_stream": BLOCKS_PER_STREAM,
         "input_bytes_per_gpu": STREAMS_PER_GPU * BLOCKS_PER_STREAM * {0: 102400, 1: 81920, 2: 160000, 3: 128000}[MODE],
         "l2": "inputs are larger than the 126 MB L2 (see input_bytes_per_gpu); no flush needed",
-        "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32, f64 libm in the PLL); "
+        "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32; the PLL's f64 libm results reproduced exactly); "
                       "audio resamplers fused f32 (PCM within 1 LSB)",
         "parallelism": "streams partitioned across GPUs, one process per GPU, no collective on the data path",
     }
@@ -285,13 +285,16 @@ def run_gpu_arm(args):
     # algorithmic bytes / MACs per IQ pair, SURVEY.md §8(d) and DESIGN.md §5
     rd = float(m.rf_decim)                           # IQ pairs per IF sample
     ad = rd * m.audio_decim / m.audio_upsample       # IQ pairs per audio sample
+    PLL_TABLE = bool(STEREO) and S <= int(os.environ.get("DY4_PLL_TABLE_MAX", "4096"))     # dy4_pipeline.cu: ensure_workspace
     alg = {
         "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
         "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
-        "pll": {"bytes": 20 / rd, "mac": 0.0},           # pilot 4 + reciprocal 8 in, phase row 8 out per IF sample
+        # direct loop: pilot 4 + reciprocal 8 in, phase row 8 out per IF sample; table-driven loop: 48-byte table row in, phaseEst 4 out
+        "pll": {"bytes": (52 if PLL_TABLE else 20) / rd, "mac": 0.0},
         "audio": {"bytes": (12 if STEREO else 4) / rd + 4 / ad, "mac": (2 if STEREO else 1) * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
-        "pll_aux": {"bytes": 24 / rd, "mac": 0.0},       # reciprocals (4 in, 8 out) and NCO row (8 in, 4 out) per IF sample
+        # direct: reciprocals (4 in, 8 out) and NCO row (8 in, 4 out); table-driven: prediction (4 in, 8 out), table (12 in, 48 out), NCO (4 in, 4 out)
+        "pll_aux": {"bytes": (80 if PLL_TABLE else 24) / rd, "mac": 0.0},
         # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
         "rds_bpf": {"bytes": 16 / rd, "mac": 2 * 101 / rd},
         "rds_pll": {"bytes": 28 / rd, "mac": 0.0},
@@ -344,7 +347,11 @@ def run_gpu_arm(args):
         pll_info = {"share_of_step": pll["share"], "avg_launch_ms": pll["avg_ms"], "ms_per_step": round(pll_ms_per_step, 3),
                     "ns_per_sample_per_stream": round(pll_ms_per_step * 1e6 / n_if, 2),
                     "stream_samples_per_s": round(S * n_if / (pll_ms_per_step * 1e-3), 0),
-                    "note": "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
+                    "loop": "table-driven (predict -> exact three-candidate table -> serial picks; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
+                    "note": ("serial recurrence per stream, one thread per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
+                             "pll_aux), the serial loop is float adds, compares and selects - bound by the latency of that dependent chain and by branch "
+                             "cost of a lone warp, not by FLOPs or bytes") if PLL_TABLE else
+                            "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
 
     # ---- CPU baseline: the reference's own code on the host cores, bounded sample (N=1 only) ----------------
     cpu = None

@@ -4,5 +4,5 @@ print("value %.1f Msamples/s  ms/step %.2f  e2e %.1f  launches %d clocks %s" % (
 for k, v in d["kernels"].items():
     print("  %-9s %s" % (k, v))
 print("  pll:", d["pll"])
-print("  roofline:", {k: d["roofline"][k] for k in ("achieved", "frac", "issue_frac", "share_of_step")})
+print("  roofline:", {k: d["roofline"][k] for k in ("achieved", "frac", "issue_frac", "share_of_step") if k in d["roofline"]})
 if d.get("cpu_baseline"): print("  cpu:", d["cpu_baseline"])
