@@ -174,7 +174,10 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     // Table-driven PLL (dy4_plltab.h, 48 bytes of table per IF sample) while the stream count leaves the serial loop
     // latency-bound; with many streams the direct loop's FP64 work is already throughput-bound and the table's 3x
     // evaluations would only add to it.  DY4_PLL_TABLE_MAX=0 selects the direct loop always.
-    int tab_max = 4096;
+    // Measured: 4 096 streams 99.5 -> 127 G samples/s with the table, 8 192 streams 160 -> 124 without / with.
+    // With the RDS branch beside it (its own FP64 carrier PLL and FIRs on another stream) the table's extra FP64 work
+    // costs more than it saves at 4 096 streams (69.9 -> 63.8), so the switch-over is lower there.
+    int tab_max = (p->flags & DY4_FLAG_RDS) ? 1024 : 4096;
     if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
     p->pll_table = p->stereo && p->n_streams <= tab_max;
     const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 40 : 16) : 1);
@@ -542,13 +545,6 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         CU(cudaMemcpy(f, p->pll_state, 8 * sizeof(float), cudaMemcpyDeviceToHost));
         fprintf(stderr, "pred[0] %g %.9g %g %g | pred[1] %g %.9g %g %g | pll integ %g phase %.9g T %g | seq %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7],
                 f[2], f[3], f[4], (long long)p->seq);
-        for (int set = 0; set < 2; set++) {
-            double th[4]; float row[24];
-            CU(cudaMemcpy(th, p->ws[set].theta + 2000, sizeof(th), cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(row, p->ws[set].tab + 3 * 2000, sizeof(row), cudaMemcpyDeviceToHost));
-            fprintf(stderr, " set %d th_hat[2000..] %.6f %.6f | row2000: t_lo %.7g t_hi %.7g P %.7g hm %g a %g %g %g b %g %g %g u %g c %.6f | row2001 t_lo %.7g c %.6f\n", set, th[0], th[1],
-                    row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7], row[8], row[9], row[10], row[11], row[12], row[23]);
-        }
     }
     return DY4_OK;
 }

@@ -285,7 +285,7 @@ def run_gpu_arm(args):
     # algorithmic bytes / MACs per IQ pair, SURVEY.md §8(d) and DESIGN.md §5
     rd = float(m.rf_decim)                           # IQ pairs per IF sample
     ad = rd * m.audio_decim / m.audio_upsample       # IQ pairs per audio sample
-    PLL_TABLE = bool(STEREO) and S <= int(os.environ.get("DY4_PLL_TABLE_MAX", "4096"))     # dy4_pipeline.cu: ensure_workspace
+    PLL_TABLE = bool(STEREO) and S <= int(os.environ.get("DY4_PLL_TABLE_MAX", "1024" if RDS else "4096"))     # dy4_pipeline.cu: ensure_workspace
     alg = {
         "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
         "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
