@@ -328,3 +328,38 @@ def test_streaming_command_line(dy4, mode, stereo, per_call):
     assert got.size == want.size and np.array_equal(got, want)
     bad = subprocess.run([exe, "7", "stereo"], input=b"", capture_output=True, timeout=60)
     assert bad.returncode == 1 and b"Wrong mode" in bad.stderr
+
+
+# ---------------------------------------------------------------- table-driven PLL through the software pipeline
+@pytest.mark.gpu
+def test_table_pll_multi_subchunk_calls_with_signal_jump(dy4, checker, monkeypatch):
+    """16-block calls are cut into five sub-chunks, so the prediction carries its own state (and its turn correction)
+    from the third one on; feeding the same 16 blocks AGAIN continues the streams across a phase jump of the pilot
+    (the loop re-acquires lock).  Results must equal the reference run over the concatenated input, bit for bit, and
+    the direct loop (DY4_PLL_TABLE_MAX=0) must give the same."""
+    import torch
+    mode, S, nb = 0, 3, 16
+    m = dy4.mode_params(mode)
+    iq = dy4.synth.make_batch(mode, S, nb * m.block_size // 2, base_seed=41)
+    d = torch.from_numpy(iq).cuda()
+    both = np.concatenate([iq, iq], axis=1)
+    ref = [checker.pipeline(mode, 1, both[s]) for s in range(S)]
+
+    def run():
+        p = dy4.Pipeline(mode, 1, S, exact_audio=True)          # no debug_rows: the real sub-chunk plan
+        try:
+            outs = [p.process(d, want=("pcm", "audio", "if")) for _ in range(2)]
+            torch.cuda.synchronize()
+            return {k: torch.cat([o[k] for o in outs], 1).cpu().numpy() for k in outs[0]}
+        finally:
+            p.close()
+
+    tab = run()
+    for s in range(S):
+        assert np.array_equal(bits(tab["if"][s]), bits(ref[s]["if"]))
+        assert np.array_equal(bits(tab["audio"][s]), bits(ref[s]["audio"])), "stream %d" % s
+        assert np.array_equal(tab["pcm"][s], ref[s]["pcm"])
+    monkeypatch.setenv("DY4_PLL_TABLE_MAX", "0")
+    direct = run()
+    for k in tab:
+        assert np.array_equal(direct[k], tab[k]), k
