@@ -71,7 +71,7 @@ struct dy4_pipeline {
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
-    cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr;
+    cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr, ev_prep1 = nullptr;
     // host-facing staging
     uint8_t* d_stage = nullptr; int16_t* d_pcm_stage = nullptr; float* d_audio_stage = nullptr;
     int stage_blocks = 0; bool stage_audio = false;
@@ -221,6 +221,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaEventCreateWithFlags(&p->ev_pll[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&p->ev_prep1, cudaEventDisableTiming));
     }
     if (p->flags & DY4_FLAG_RDS) {
         cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta);
@@ -511,6 +512,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
         if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
+        if (p->pll_table && i == 2) CU(cudaStreamWaitEvent(st, p->ev_prep1, 0));
         if (!prep_on_pll && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
@@ -520,7 +522,13 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
         CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
-        if ((rc = run_pll(p, c, p->s_pll, prep_on_pll ? (DY4_PLL_PREP | DY4_PLL_LOOP) : DY4_PLL_LOOP))) return rc;
+        if (prep_on_pll) {
+            // prediction + table of sub-chunk 1 from the exact state loop(0) leaves; the prediction of sub-chunk 2 (main
+            // stream) continues from this one's state, so it waits for it
+            if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_PREP))) return rc;
+            CU(cudaEventRecord(p->ev_prep1, p->s_pll));
+        }
+        if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_LOOP))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
         if (have_prev) {
             CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
@@ -640,6 +648,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); }
+        if (p->ev_prep1) cudaEventDestroy(p->ev_prep1);
         cudaEventDestroy(p->ev_in);
     }
     cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);

@@ -349,6 +349,10 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     // after them.  k_pll_table leaves their rows empty.
     int kd = 0;
     if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
+    // A pick certifies "trigArg = RN_f(RN_d(w*T) + phaseEst) is this grid point" for the sample counter T the TABLE was
+    // built with: it must be this stream's own counter.  It always is when the launches are ordered as dy4_pipeline.cu
+    // orders them; if it ever is not, nothing of the table is used.
+    if (pred[8 * s + 3] != T0) kd = n_pick;
     const int n_sg = (n_pick - kd) / TAB_SG;         // whole super-groups after the direct part
 #pragma unroll
     for (int i = 0; i < TAB_SLOTS; i++) tab_mbar_init(&bars[i * TAB_LANES + lane]);   // each lane owns its barriers: no CTA-wide sync
