@@ -262,12 +262,9 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const double* __r
 //    guard — with ONE branch per super-group on "every pick was certain"; if not, the super-group is redone step by
 //    step from its saved state (tab_redo, out of line).
 // Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
-constexpr int TAB_SG = 32;                         // samples per super-group
-constexpr int TAB_SLOTS = 4;                       // ring size in super-groups
 constexpr int TAB_LANES = 4;                       // most streams per warp
 constexpr int TAB_ROW_Q = 3;                       // 16-byte words per row
-constexpr int TAB_SG_BYTES = TAB_SG * TAB_ROW_Q * 16;
-constexpr int TAB_LANE_Q = TAB_SG * TAB_ROW_Q + 1; // lane stride in 16-byte words: +1 spreads the lanes over the banks
+// template parameters of k_pll_tab: TAB_SG samples per super-group (32; 64 for the A/B knob DY4_PLL_SG), TAB_SLOTS ring slots
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
 __device__ __forceinline__ unsigned tab_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -275,11 +272,12 @@ __device__ __forceinline__ void tab_mbar_init(unsigned long long* bar)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tab_smem_u32(bar)));
 }
+template <int BYTES>
 __device__ __forceinline__ void tab_bulk_load(void* dst, const void* src, unsigned long long* bar)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tab_smem_u32(bar)), "n"(TAB_SG_BYTES) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tab_smem_u32(bar)), "n"(BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(tab_smem_u32(dst)), "l"(src), "n"(TAB_SG_BYTES), "r"(tab_smem_u32(bar)) : "memory");
+                 ::"r"(tab_smem_u32(dst)), "l"(src), "n"(BYTES), "r"(tab_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool tab_mbar_try(unsigned long long* bar, unsigned parity)
 {
@@ -324,12 +322,14 @@ __device__ __noinline__ void tab_redo(const float4* src, const float* x_next, fl
     *integ_io = integ; *phase_io = phase;
 }
 
-template <bool FENCE>
+template <bool FENCE, int TAB_SG, int TAB_SLOTS>
 __global__ void __launch_bounds__(32)
 k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
           float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
           const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
 {
+    constexpr int TAB_SG_BYTES = TAB_SG * TAB_ROW_Q * 16;
+    constexpr int TAB_LANE_Q = TAB_SG * TAB_ROW_Q + 1;   // lane stride in 16-byte words: +1 spreads the lanes over the banks
     __shared__ __align__(16) float4 ring[TAB_SLOTS * TAB_LANES * TAB_LANE_Q];
     __shared__ __align__(8) unsigned long long bars[TAB_SLOTS * TAB_LANES];
     const int lane = threadIdx.x;
@@ -361,7 +361,7 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     auto issue = [&](int i) {                        // super-group i -> slot i % TAB_SLOTS
         if (i < n_sg) {
             const int slot = i % TAB_SLOTS;
-            tab_bulk_load(ring + (slot * TAB_LANES + lane) * TAB_LANE_Q, rows + TAB_ROW_Q * ((long long)kd + (long long)i * TAB_SG), &bars[slot * TAB_LANES + lane]);
+            tab_bulk_load<TAB_SG_BYTES>(ring + (slot * TAB_LANES + lane) * TAB_LANE_Q, rows + TAB_ROW_Q * ((long long)kd + (long long)i * TAB_SG), &bars[slot * TAB_LANES + lane]);
         }
     };
     for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
@@ -539,7 +539,10 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
             k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.pred_in, a.pred_out, a.need, a.pred_carry,
                                                                                  a.theta, a.wide_stride, a.n, c);
-            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            // DY4_PLL_TABLE_SMEM (bytes of unused dynamic shared memory per CTA) caps the resident CTAs of the table kernel: fewer
+            // warps contending with the serial loops it runs beside (A/B knob)
+            static const int tab_smem = std::getenv("DY4_PLL_TABLE_SMEM") ? atoi(std::getenv("DY4_PLL_TABLE_SMEM")) : 0;
+            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, tab_smem, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             g_dy4_launches += 2;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
@@ -550,8 +553,12 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);
             const int grid = (a.n_streams + lanes - 1) / lanes;
             float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
-            if (fence) k_pll_tab<true><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes);
-            else k_pll_tab<false><<<grid, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes);
+            static const int sg = std::getenv("DY4_PLL_SG") ? atoi(std::getenv("DY4_PLL_SG")) : 32;
+#define DY4_TAB_ARGS a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes
+            if (sg == 64) k_pll_tab<true, 64, 3><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            else if (fence) k_pll_tab<true, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            else k_pll_tab<false, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+#undef DY4_TAB_ARGS
             g_dy4_launches++;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
