@@ -171,7 +171,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
 {
     size_t budget = 8ull << 30;
     if (const char* e = std::getenv("DY4_WS_BYTES")) budget = std::strtoull(e, nullptr, 10);
-    // Table-driven PLL (dy4_plltab.h, 48 bytes of table per IF sample) while the stream count leaves the serial loop
+    // Table-driven PLL (dy4_plltab.h, 32 bytes of table per IF sample) while the stream count leaves the serial loop
     // latency-bound; with many streams the direct loop's FP64 work is already throughput-bound and the table's 3x
     // evaluations would only add to it.  DY4_PLL_TABLE_MAX=0 selects the direct loop always.
     // Measured: 4 096 streams 99.5 -> 127 G samples/s with the table, 8 192 streams 160 -> 124 without / with.
@@ -180,7 +180,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     int tab_max = (p->flags & DY4_FLAG_RDS) ? 1024 : 4096;
     if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
     p->pll_table = p->stereo && p->n_streams <= tab_max;
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 40 : 16) : 1);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 32 : 16) : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
     const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
@@ -209,7 +209,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.nco, bytes));
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
-            if (p->pll_table) CU(cudaMalloc(&w.tab, 12 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
+            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
@@ -392,7 +392,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.tab_stride = 3 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
     if (w.tab) {
         pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
         pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;

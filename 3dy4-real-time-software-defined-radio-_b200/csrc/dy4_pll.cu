@@ -232,7 +232,7 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
     }
 }
 
-// 2. one table row per sample: the exact errorD of the next step for the three float grid points around the prediction
+// 2. one table row per sample: the exact errorD of the next step for the two float grid points the prediction lies between
 __global__ void __launch_bounds__(128)
 k_pll_table(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
             const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
@@ -245,10 +245,9 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const double* __r
     dy4_tabrow_t r;
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
                      k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, c.Kp, c.Ki, &r);
-    float4* o = tab + (long long)s * tab_stride + 3 * (long long)k;
-    o[0] = make_float4(r.t_lo, r.t_hi, r.P, r.hm);
-    o[1] = make_float4(r.a0, r.a1, r.a2, r.b0);
-    o[2] = make_float4(r.b1, r.b2, r.u, r.c);
+    float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
+    o[0] = make_float4(r.d, r.Q, r.m, r.um);
+    o[1] = make_float4(r.a_c, r.a_n, r.b_c, r.b_n);
 }
 
 // 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
@@ -263,7 +262,7 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const double* __r
 //    step from its saved state (tab_redo, out of line).
 // Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
 constexpr int TAB_LANES = 4;                       // most streams per warp
-constexpr int TAB_ROW_Q = 3;                       // 16-byte words per row
+constexpr int TAB_ROW_Q = 2;                       // 16-byte words per row
 // template parameters of k_pll_tab: TAB_SG samples per super-group (32; 64 for the A/B knob DY4_PLL_SG), TAB_SLOTS ring slots
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
@@ -287,20 +286,19 @@ __device__ __forceinline__ bool tab_mbar_try(unsigned long long* bar, unsigned p
     return ok != 0;
 }
 
-// state_k -> state_{k+1} with no branch.  q0 = (t_lo, t_hi, P, hm), q1 = (a0, a1, a2, b0), q2 = (b1, b2, u, c).
+// state_k -> state_{k+1} with no branch.  q0 = (d, Q, m, um), q1 = (a_c, a_n, b_c, b_n).
 // `ok` stays true while every pick was certain; if not, integ/phase are garbage and the caller redoes the super-group.
-__device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, const float4 q2, float& integ, float& phase, bool& ok)
+__device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, float& integ, float& phase, bool& ok)
 {
-    const float i0 = __fadd_rn(integ, q1.x), i1 = __fadd_rn(integ, q1.y), i2 = __fadd_rn(integ, q1.z);
-    const float p0 = __fadd_rn(phase, __fadd_rn(q1.w, i0));
-    const float p1 = __fadd_rn(phase, __fadd_rn(q2.x, i1));
-    const float p2 = __fadd_rn(phase, __fadd_rn(q2.y, i2));
-    const bool neg = phase < q0.x, pos = phase > q0.y;
-    const float az = fabsf(__fadd_rn(phase, -q0.z));
-    const float v = fminf(az, fabsf(__fadd_rn(az, -q2.z)));
-    ok = ok && (v < q0.w);
-    integ = neg ? i0 : (pos ? i2 : i1);
-    phase = neg ? p0 : (pos ? p2 : p1);
+    const float i_c = __fadd_rn(integ, q1.x), i_n = __fadd_rn(integ, q1.y);
+    const float p_c = __fadd_rn(phase, __fadd_rn(q1.z, i_c));
+    const float p_n = __fadd_rn(phase, __fadd_rn(q1.w, i_n));
+    const float w = fmaf(phase, q0.x, -q0.y);
+    const float aw = fabsf(w);
+    ok = ok && (aw > q0.z) && (aw < q0.w);
+    const bool far = w > 0.0f;
+    integ = far ? i_n : i_c;
+    phase = far ? p_n : p_c;
 }
 
 // A super-group again, carefully: a pick where it is certain, else that step directly (dy4_pllmath.h), as k_pll does.
@@ -311,11 +309,11 @@ __device__ __noinline__ void tab_redo(const float4* src, const float* x_next, fl
     float integ = *integ_io, phase = *phase_io;
 #pragma unroll 1
     for (int r = 0; r < count; r++) {
-        const float4 q0 = src[3 * r], q1 = src[3 * r + 1], q2 = src[3 * r + 2];
+        const float4 q0 = src[2 * r], q1 = src[2 * r + 1];
         y[r] = phase;
-        int j;
-        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, q2.z, q0.w, &j))
-            dy4_pll_filter_ab(j < 0 ? q1.x : (j > 0 ? q1.z : q1.y), j < 0 ? q1.w : (j > 0 ? q2.y : q2.x), &integ, &phase);
+        int far;
+        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, q0.w, &far))
+            dy4_pll_filter_ab(far ? q1.y : q1.x, far ? q1.w : q1.z, &integ, &phase);
         else
             dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + r + 1), phase), x_next[r]), Kp, Ki, &integ, &phase);
     }
@@ -419,7 +417,7 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 ph[q] = sp;
-                tab_step_spec(src[3 * (r + q)], src[3 * (r + q) + 1], src[3 * (r + q) + 2], si, sp, ok);
+                tab_step_spec(src[2 * (r + q)], src[2 * (r + q) + 1], si, sp, ok);
             }
             *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[0], ph[1], ph[2], ph[3]);   // (rewritten by tab_redo if a pick was not certain)
         }
@@ -555,7 +553,7 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
             static const int sg = std::getenv("DY4_PLL_SG") ? atoi(std::getenv("DY4_PLL_SG")) : 32;
 #define DY4_TAB_ARGS a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes
-            if (sg == 64) k_pll_tab<true, 64, 3><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            if (sg == 64) k_pll_tab<true, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
             else if (fence) k_pll_tab<true, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
             else k_pll_tab<false, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
 #undef DY4_TAB_ARGS

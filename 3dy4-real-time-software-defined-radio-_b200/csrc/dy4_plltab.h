@@ -38,14 +38,16 @@
 #define DY4_TAB_EARLY 1536
 
 // One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
-// 48 bytes, read as three 16-byte words.  With P = c - RN_d(w*T_k):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is
-// c - u, c, c + u  for  phase_k  in  (P-1.5u, P-.5u), (P-.5u, P+.5u), (P+.5u, P+1.5u).
+// 32 bytes (the first eight fields), read as two 16-byte words.  The prediction th_hat lies between the float c = RN_f(th_hat)
+// and its neighbour n = c + d*u (d = +-1 towards th_hat), and so — almost always — does the true trigArg.  With
+// P = c - RN_d(w*T_k) and  w = d*phase_k - (d*P + u/2):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is c for w in (-u, 0)
+// and n for w in (0, u).
 typedef struct {
-    float t_lo, t_hi; // P - u/2, P + u/2 rounded to float (NaN: row not usable)
-    float P, hm;      // P as a float; hm = u/2 - m, m the guard band around a threshold (rounding-error budget of the pick)
-    float a0, a1, a2; // Ki*errorD of step k+1 if trigArg_k = c - u, c, c + u   (filter.cpp:207's product)
-    float b0, b1, b2; // Kp*errorD                                              (filter.cpp:210's product)
-    float u, c;       // grid spacing of c's binade; c = predicted trigArg_k rounded to float
+    float d, Q;       // direction of the neighbour (+-1); Q = d*P + u/2 rounded to float (NaN: row not usable)
+    float m, um;      // m: guard band around the threshold (rounding-error budget of the pick); um = u - m
+    float a_c, a_n;   // Ki*errorD of step k+1 if trigArg_k = c, n   (filter.cpp:207's product)
+    float b_c, b_n;   // Kp*errorD                                   (filter.cpp:210's product)
+    float c, u;       // (not stored on the device) predicted trigArg_k rounded to float, grid spacing of its binade
 } dy4_tabrow_t;
 
 // float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
@@ -110,7 +112,7 @@ DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 #endif
 
 // th_hat: predicted trigArg of this sample; wT = RN_d(w*T_k);
-// x_next: input of step k+1 (has_next == 0 for the last sample of a launch: T unused).
+// x_next: input of step k+1 (has_next == 0 for the last sample of a launch: products unused).
 // `force_invalid`: rows the serial loop must evaluate directly whatever the prediction says.
 DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, float Kp, float Ki, dy4_tabrow_t* r)
 {
@@ -120,34 +122,32 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     // usable: positive normal float with both neighbours in the same binade and u in a sane range (2^-40 .. 2^40)
     const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
     const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
-    const double P = DY4_SUB((double)c, wT), hu = DY4_MUL(0.5, (double)u);
-    const float t_lo = DY4_D2F(DY4_SUB(P, hu)), t_hi = DY4_D2F(DY4_ADD(P, hu)), Pf = DY4_D2F(P);
-    const float nan = dy4_i2f_bits(0x7fc00000);
-    r->c = c; r->u = u;
-    r->t_lo = ok ? t_lo : nan; r->t_hi = ok ? t_hi : nan; r->P = ok ? Pf : nan;
-    // Each of t_lo, t_hi, P is within 2^-24 of its magnitude (half an ulp) of the exact value, and the reference's double
-    // add moves the sum by at most 2^-29 u.  The pick compares phase with t_lo / t_hi and measures its distance from P,
-    // so two of those roundings can add up: the guard band is 2.5 half-ulps of the largest of the three plus 2^-26 u.
-    const float m = DY4_FADDF(DY4_FMULF(1.4901161193847656e-07f, fmaxf(fmaxf(fabsf(t_lo), fabsf(t_hi)), fabsf(Pf))), DY4_FMULF(1.4901161193847656e-08f, u));
-    r->hm = DY4_FADDF(DY4_FMULF(0.5f, u), -m);
-    r->a0 = r->a1 = r->a2 = r->b0 = r->b1 = r->b2 = 0.0f;
+    const float d = (th_hat >= (double)c) ? 1.0f : -1.0f;
+    const double P = DY4_SUB((double)c, wT);
+    const float Q = DY4_D2F(DY4_ADD(DY4_MUL((double)d, P), DY4_MUL(0.5, (double)u)));
+    r->c = c; r->u = u; r->d = d;
+    r->Q = ok ? Q : dy4_i2f_bits(0x7fc00000);
+    // Q is within 2^-24|Q| (half an ulp) of the exact threshold, the pick's fma rounds once more (2^-24|w|, |w| < u) and the
+    // reference's double add moves the sum by at most 2^-29 u: the guard band is two half-ulps of Q plus 2^-26 u.
+    r->m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fabsf(Q)), DY4_FMULF(1.4901161193847656e-08f, u));
+    r->um = DY4_FADDF(u, -r->m);
+    r->a_c = r->a_n = r->b_c = r->b_n = 0.0f;
     if (ok && has_next) {
-        const float e0 = dy4_next_errorD((double)DY4_FADDF(c, -u), x_next);
-        const float e1 = dy4_next_errorD((double)c, x_next);
-        const float e2 = dy4_next_errorD((double)DY4_FADDF(c, u), x_next);
-        r->a0 = DY4_FMULF(Ki, e0); r->a1 = DY4_FMULF(Ki, e1); r->a2 = DY4_FMULF(Ki, e2);
-        r->b0 = DY4_FMULF(Kp, e0); r->b1 = DY4_FMULF(Kp, e1); r->b2 = DY4_FMULF(Kp, e2);
+        const float e_c = dy4_next_errorD((double)c, x_next);
+        const float e_n = dy4_next_errorD((double)fmaf(d, u, c), x_next);
+        r->a_c = DY4_FMULF(Ki, e_c); r->a_n = DY4_FMULF(Ki, e_n);
+        r->b_c = DY4_FMULF(Kp, e_c); r->b_n = DY4_FMULF(Kp, e_n);
     }
 }
 
 // ---- 3. the pick ----------------------------------------------------------------------------------------------------
-// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *j in {-1,0,1} when it is certainly
-// c + j*u: |phase_k - P| lies inside [0, u/2 - m) or (u/2 + m, 3u/2 - m), i.e. min(|z|, ||z| - u|) < u/2 - m.
-// 0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
-DY4_HD int dy4_tab_pick(float phase, float t_lo, float t_hi, float P, float u, float hm, int* j)
+// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *far (0: c, 1: the neighbour n) when that is
+// certain: w = d*phase - Q is farther than m from 0 (the threshold between the two) and closer than u - m (their far
+// ends).  0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
+DY4_HD int dy4_tab_pick(float phase, float d, float Q, float m, float um, int* far)
 {
-    const float az = fabsf(DY4_FADDF(phase, -P));
-    const float v = fminf(az, fabsf(DY4_FADDF(az, -u)));
-    *j = (phase > t_hi) - (phase < t_lo);
-    return v < hm;
+    const float w = fmaf(phase, d, -Q);
+    const float aw = fabsf(w);
+    *far = w > 0.0f;
+    return (aw > m) && (aw < um);
 }

@@ -289,12 +289,12 @@ def run_gpu_arm(args):
     alg = {
         "frontend": {"bytes": 2.0 + 4 / rd, "mac": 2 * 101 / rd},
         "twin_bpf": {"bytes": 4 / rd + 8 / rd, "mac": 2 * 101 / rd},
-        # direct loop: pilot 4 + reciprocal 8 in, phase row 8 out per IF sample; table-driven loop: 48-byte table row in, phaseEst 4 out
-        "pll": {"bytes": (52 if PLL_TABLE else 20) / rd, "mac": 0.0},
+        # direct loop: pilot 4 + reciprocal 8 in, phase row 8 out per IF sample; table-driven loop: 32-byte table row in, phaseEst 4 out
+        "pll": {"bytes": (36 if PLL_TABLE else 20) / rd, "mac": 0.0},
         "audio": {"bytes": (12 if STEREO else 4) / rd + 4 / ad, "mac": (2 if STEREO else 1) * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
-        # direct: reciprocals (4 in, 8 out) and NCO row (8 in, 4 out); table-driven: prediction (4 in, 8 out), table (12 in, 48 out), NCO (4 in, 4 out)
-        "pll_aux": {"bytes": (80 if PLL_TABLE else 24) / rd, "mac": 0.0},
+        # direct: reciprocals (4 in, 8 out) and NCO row (8 in, 4 out); table-driven: prediction (4 in, 8 out), table (12 in, 32 out), NCO (4 in, 4 out)
+        "pll_aux": {"bytes": (64 if PLL_TABLE else 24) / rd, "mac": 0.0},
         # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
         "rds_bpf": {"bytes": 16 / rd, "mac": 2 * 101 / rd},
         "rds_pll": {"bytes": 28 / rd, "mac": 0.0},
@@ -347,7 +347,7 @@ def run_gpu_arm(args):
         pll_info = {"share_of_step": pll["share"], "avg_launch_ms": pll["avg_ms"], "ms_per_step": round(pll_ms_per_step, 3),
                     "ns_per_sample_per_stream": round(pll_ms_per_step * 1e6 / n_if, 2),
                     "stream_samples_per_s": round(S * n_if / (pll_ms_per_step * 1e-3), 0),
-                    "loop": "table-driven (predict -> exact three-candidate table -> serial picks; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
+                    "loop": "table-driven (predict -> exact two-candidate table -> serial picks; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
                     "note": ("serial recurrence per stream, one thread per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
                              "pll_aux), the serial loop is float adds, compares and selects - bound by the latency of that dependent chain and by branch "
                              "cost of a lone warp, not by FLOPs or bytes") if PLL_TABLE else

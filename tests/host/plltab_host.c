@@ -50,12 +50,12 @@ void plltab_launch_carry(const float* x, int n, float* state, double w, float Kp
     }
     for (int k = 0; k + 1 < n; k++) {
         const dy4_tabrow_t* r = &rows[k];
-        int j;
+        int far;
         const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);     /* what k_nco_phase derives from the stored phase */
         theta_out[k] = th;
-        if (dy4_tab_pick(phase, r->t_lo, r->t_hi, r->P, r->u, r->hm, &j)) {
-            if (th != fmaf((float)j, r->u, r->c)) stats[2]++;                     /* a certain pick that is wrong: must never happen */
-            dy4_pll_filter_ab(j < 0 ? r->a0 : (j > 0 ? r->a2 : r->a1), j < 0 ? r->b0 : (j > 0 ? r->b2 : r->b1), &integ, &phase);
+        if (dy4_tab_pick(phase, r->d, r->Q, r->m, r->um, &far)) {
+            if (th != (far ? fmaf(r->d, r->u, r->c) : r->c)) stats[2]++;           /* a certain pick that is wrong: must never happen */
+            dy4_pll_filter_ab(far ? r->a_n : r->a_c, far ? r->b_n : r->b_c, &integ, &phase);
             stats[0]++;
         } else {
             dy4_pll_filter(dy4_next_errorD((double)th, x[k + 1]), Kp, Ki, &integ, &phase);
