@@ -246,8 +246,8 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const double* __r
     dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
                      k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, c.Kp, c.Ki, &r);
     float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
-    o[0] = make_float4(r.d, r.Q, r.m, r.um);
-    o[1] = make_float4(r.a_c, r.a_n, r.b_c, r.b_n);
+    o[0] = make_float4(r.t, r.hu, r.hm, 0.0f);
+    o[1] = make_float4(r.a_lo, r.a_hi, r.b_lo, r.b_hi);
 }
 
 // 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
@@ -286,19 +286,20 @@ __device__ __forceinline__ bool tab_mbar_try(unsigned long long* bar, unsigned p
     return ok != 0;
 }
 
-// state_k -> state_{k+1} with no branch.  q0 = (d, Q, m, um), q1 = (a_c, a_n, b_c, b_n).
+// state_k -> state_{k+1} with no branch.  q0 = (t, u/2, hm, -), q1 = (a_lo, a_hi, b_lo, b_hi).
 // `ok` stays true while every pick was certain; if not, integ/phase are garbage and the caller redoes the super-group.
+// On the serial chain: one compare of phaseEst with the threshold and one select (8.9 cycles, tools/ubench_pick.cu);
+// the two speculative updates and the three-instruction guard run beside it.
 __device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, float& integ, float& phase, bool& ok)
 {
-    const float i_c = __fadd_rn(integ, q1.x), i_n = __fadd_rn(integ, q1.y);
-    const float p_c = __fadd_rn(phase, __fadd_rn(q1.z, i_c));
-    const float p_n = __fadd_rn(phase, __fadd_rn(q1.w, i_n));
-    const float w = fmaf(phase, q0.x, -q0.y);
-    const float aw = fabsf(w);
-    ok = ok && (aw > q0.z) && (aw < q0.w);
-    const bool far = w > 0.0f;
-    integ = far ? i_n : i_c;
-    phase = far ? p_n : p_c;
+    const float i_lo = __fadd_rn(integ, q1.x), i_hi = __fadd_rn(integ, q1.y);
+    const float p_lo = __fadd_rn(phase, __fadd_rn(q1.z, i_lo));
+    const float p_hi = __fadd_rn(phase, __fadd_rn(q1.w, i_hi));
+    const bool up = phase > q0.x;
+    const float v = __fadd_rn(fabsf(__fadd_rn(phase, -q0.x)), -q0.y);
+    ok = ok && (fabsf(v) < q0.z);
+    integ = up ? i_hi : i_lo;
+    phase = up ? p_hi : p_lo;
 }
 
 // A super-group again, carefully: a pick where it is certain, else that step directly (dy4_pllmath.h), as k_pll does.
@@ -311,9 +312,9 @@ __device__ __noinline__ void tab_redo(const float4* src, const float* x_next, fl
     for (int r = 0; r < count; r++) {
         const float4 q0 = src[2 * r], q1 = src[2 * r + 1];
         y[r] = phase;
-        int far;
-        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, q0.w, &far))
-            dy4_pll_filter_ab(far ? q1.y : q1.x, far ? q1.w : q1.z, &integ, &phase);
+        int up;
+        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, &up))
+            dy4_pll_filter_ab(up ? q1.y : q1.x, up ? q1.w : q1.z, &integ, &phase);
         else
             dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + r + 1), phase), x_next[r]), Kp, Ki, &integ, &phase);
     }
@@ -551,11 +552,12 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);
             const int grid = (a.n_streams + lanes - 1) / lanes;
             float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
-            static const int sg = std::getenv("DY4_PLL_SG") ? atoi(std::getenv("DY4_PLL_SG")) : 32;
+            static const int sg = std::getenv("DY4_PLL_SG") ? atoi(std::getenv("DY4_PLL_SG")) : 64;
 #define DY4_TAB_ARGS a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes
-            if (sg == 64) k_pll_tab<true, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-            else if (fence) k_pll_tab<true, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-            else k_pll_tab<false, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            if (sg == 32) k_pll_tab<true, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            else if (sg == 128) k_pll_tab<true, 128, 2><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            else if (fence) k_pll_tab<true, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
+            else k_pll_tab<false, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
 #undef DY4_TAB_ARGS
             g_dy4_launches++;
             cudaError_t e = cudaGetLastError();

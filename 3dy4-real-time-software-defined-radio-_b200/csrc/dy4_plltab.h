@@ -38,16 +38,15 @@
 #define DY4_TAB_EARLY 1536
 
 // One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
-// 32 bytes (the first eight fields), read as two 16-byte words.  The prediction th_hat lies between the float c = RN_f(th_hat)
-// and its neighbour n = c + d*u (d = +-1 towards th_hat), and so — almost always — does the true trigArg.  With
-// P = c - RN_d(w*T_k) and  w = d*phase_k - (d*P + u/2):  trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is c for w in (-u, 0)
-// and n for w in (0, u).
+// 32 bytes (the first eight fields), read as two 16-byte words.  The prediction th_hat lies between two neighbouring floats
+// lo < hi = lo + u, and so — almost always — does the true trigArg.  With t = (lo - RN_d(w*T_k)) + u/2:
+// trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is lo for phase_k in (t - u, t) and hi for phase_k in (t, t + u).
 typedef struct {
-    float d, Q;       // direction of the neighbour (+-1); Q = d*P + u/2 rounded to float (NaN: row not usable)
-    float m, um;      // m: guard band around the threshold (rounding-error budget of the pick); um = u - m
-    float a_c, a_n;   // Ki*errorD of step k+1 if trigArg_k = c, n   (filter.cpp:207's product)
-    float b_c, b_n;   // Kp*errorD                                   (filter.cpp:210's product)
-    float c, u;       // (not stored on the device) predicted trigArg_k rounded to float, grid spacing of its binade
+    float t, hu;      // the threshold rounded to float (NaN: row not usable); u/2
+    float hm, pad;    // hm = u/2 - m, m the guard band (rounding-error budget of the pick): certain iff | |phase - t| - u/2 | < hm
+    float a_lo, a_hi; // Ki*errorD of step k+1 if trigArg_k = lo, hi   (filter.cpp:207's product)
+    float b_lo, b_hi; // Kp*errorD                                     (filter.cpp:210's product)
+    float lo, u;      // (not stored on the device) the lower candidate, grid spacing of its binade
 } dy4_tabrow_t;
 
 // float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
@@ -122,32 +121,32 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     // usable: positive normal float with both neighbours in the same binade and u in a sane range (2^-40 .. 2^40)
     const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
     const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
-    const float d = (th_hat >= (double)c) ? 1.0f : -1.0f;
-    const double P = DY4_SUB((double)c, wT);
-    const float Q = DY4_D2F(DY4_ADD(DY4_MUL((double)d, P), DY4_MUL(0.5, (double)u)));
-    r->c = c; r->u = u; r->d = d;
-    r->Q = ok ? Q : dy4_i2f_bits(0x7fc00000);
-    // Q is within 2^-24|Q| (half an ulp) of the exact threshold, the pick's fma rounds once more (2^-24|w|, |w| < u) and the
-    // reference's double add moves the sum by at most 2^-29 u: the guard band is two half-ulps of Q plus 2^-26 u.
-    r->m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fabsf(Q)), DY4_FMULF(1.4901161193847656e-08f, u));
-    r->um = DY4_FADDF(u, -r->m);
-    r->a_c = r->a_n = r->b_c = r->b_n = 0.0f;
+    const float lo = (th_hat >= (double)c) ? c : DY4_FADDF(c, -u), hi = DY4_FADDF(lo, u);
+    const double hu = DY4_MUL(0.5, (double)u);
+    const float t = DY4_D2F(DY4_ADD(DY4_SUB((double)lo, wT), hu));
+    r->lo = lo; r->u = u; r->hu = DY4_D2F(hu); r->pad = 0.0f;
+    r->t = ok ? t : dy4_i2f_bits(0x7fc00000);
+    // t is within 2^-24|t| (half an ulp) of the exact threshold; the pick's two float subtractions add at most 2^-24 u, the
+    // reference's double add 2^-29 u: the guard band is two half-ulps of t plus 2^-23 u.
+    const float m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fabsf(t)), DY4_FMULF(1.1920928955078125e-07f, u));
+    r->hm = DY4_FADDF(r->hu, -m);
+    r->a_lo = r->a_hi = r->b_lo = r->b_hi = 0.0f;
     if (ok && has_next) {
-        const float e_c = dy4_next_errorD((double)c, x_next);
-        const float e_n = dy4_next_errorD((double)fmaf(d, u, c), x_next);
-        r->a_c = DY4_FMULF(Ki, e_c); r->a_n = DY4_FMULF(Ki, e_n);
-        r->b_c = DY4_FMULF(Kp, e_c); r->b_n = DY4_FMULF(Kp, e_n);
+        const float e_lo = dy4_next_errorD((double)lo, x_next);
+        const float e_hi = dy4_next_errorD((double)hi, x_next);
+        r->a_lo = DY4_FMULF(Ki, e_lo); r->a_hi = DY4_FMULF(Ki, e_hi);
+        r->b_lo = DY4_FMULF(Kp, e_lo); r->b_hi = DY4_FMULF(Kp, e_hi);
     }
 }
 
 // ---- 3. the pick ----------------------------------------------------------------------------------------------------
-// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *far (0: c, 1: the neighbour n) when that is
-// certain: w = d*phase - Q is farther than m from 0 (the threshold between the two) and closer than u - m (their far
-// ends).  0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
-DY4_HD int dy4_tab_pick(float phase, float d, float Q, float m, float um, int* far)
+// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *up (0: lo, 1: hi) when that is certain:
+// phase is farther than m from the threshold t between the two and closer than u - m (their far ends), i.e.
+// | |phase - t| - u/2 | < u/2 - m.  0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
+DY4_HD int dy4_tab_pick(float phase, float t, float hu, float hm, int* up)
 {
-    const float w = fmaf(phase, d, -Q);
-    const float aw = fabsf(w);
-    *far = w > 0.0f;
-    return (aw > m) && (aw < um);
+    const float w = DY4_FADDF(phase, -t);
+    const float v = DY4_FADDF(fabsf(w), -hu);
+    *up = phase > t;
+    return fabsf(v) < hm;
 }

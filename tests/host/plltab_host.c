@@ -50,12 +50,12 @@ void plltab_launch_carry(const float* x, int n, float* state, double w, float Kp
     }
     for (int k = 0; k + 1 < n; k++) {
         const dy4_tabrow_t* r = &rows[k];
-        int far;
+        int up;
         const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);     /* what k_nco_phase derives from the stored phase */
         theta_out[k] = th;
-        if (dy4_tab_pick(phase, r->d, r->Q, r->m, r->um, &far)) {
-            if (th != (far ? fmaf(r->d, r->u, r->c) : r->c)) stats[2]++;           /* a certain pick that is wrong: must never happen */
-            dy4_pll_filter_ab(far ? r->a_n : r->a_c, far ? r->b_n : r->b_c, &integ, &phase);
+        if (dy4_tab_pick(phase, r->t, r->hu, r->hm, &up)) {
+            if (th != (up ? r->lo + r->u : r->lo)) stats[2]++;                     /* a certain pick that is wrong: must never happen */
+            dy4_pll_filter_ab(up ? r->a_hi : r->a_lo, up ? r->b_hi : r->b_lo, &integ, &phase);
             stats[0]++;
         } else {
             dy4_pll_filter(dy4_next_errorD((double)th, x[k + 1]), Kp, Ki, &integ, &phase);
