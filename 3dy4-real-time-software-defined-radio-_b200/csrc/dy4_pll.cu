@@ -251,19 +251,19 @@ k_pll_table(const float* __restrict__ in, long long in_stride, const double* __r
 }
 
 // 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
-// Measured on a B200 (tools/ubench_pick.cu): a dependent FADD 4.9 cycles, FSETP -> FSEL 8.9, the three-candidate step
-// below 21 without and 27 with its guard — and ~55 cycles for every BRANCH a lone warp executes.  So:
+// Measured on a B200 (tools/ubench_pick.cu): a dependent FADD 4.9 cycles, FSETP -> FSEL 8.9 (both at half issue rate) —
+// and ~55 cycles for every BRANCH a lone warp executes.  So:
 //  * table rows arrive through a per-lane shared-memory ring, ONE bulk asynchronous copy (cp.async.bulk, completing on
-//    the lane's own mbarrier) per super-group of 32 samples, three super-groups ahead: no waiting on global memory and
+//    the lane's own mbarrier) per super-group of 64 samples, three super-groups ahead: no waiting on global memory and
 //    no issue slots spent on it;
-//  * a super-group is straight-line code: per sample three speculative loop-filter updates (float adds of the table's
-//    precomputed products), two compares of phaseEst against the row's thresholds, selects, and a four-instruction
+//  * a super-group is straight-line code: per sample two speculative loop-filter updates (float adds of the table's
+//    precomputed products), ONE compare of phaseEst with the row's threshold, two selects, and a three-instruction
 //    guard — with ONE branch per super-group on "every pick was certain"; if not, the super-group is redone step by
 //    step from its saved state (tab_redo, out of line).
 // Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
 constexpr int TAB_LANES = 4;                       // most streams per warp
 constexpr int TAB_ROW_Q = 2;                       // 16-byte words per row
-// template parameters of k_pll_tab: TAB_SG samples per super-group (32; 64 for the A/B knob DY4_PLL_SG), TAB_SLOTS ring slots
+// template parameters of k_pll_tab: TAB_SG samples per super-group (64; 32 / 128 through the A/B knob DY4_PLL_SG), TAB_SLOTS ring slots
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
 __device__ __forceinline__ unsigned tab_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

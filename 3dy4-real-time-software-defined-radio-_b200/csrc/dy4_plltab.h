@@ -10,16 +10,17 @@
 //
 // So the work is split three ways (dy4_pll.cu):
 //   1. k_pll_predict   time-parallel (segments with a warm-up), serial only in cheap double adds: predicted trigArg
-//   2. k_pll_table     fully parallel: for every sample the EXACT errorD of the next step for the three float grid
-//                      points around the prediction (the dy4_pllmath.h sincos + detector, unchanged arithmetic)
-//   3. k_pll_tab       the serial loop: per sample two float compares of phaseEst against precomputed thresholds pick
-//                      the grid point the true trigArg falls on, and three speculative loop-filter updates (float
-//                      adds) are selected from — tens of cycles instead of ~445.  Whenever the pick is not certain (outside the three candidates, within
-//                      a rounding-error guard band of a tie, binade edges, start-up) the thread evaluates that step
-//                      directly with dy4_pllmath.h, so the result is the reference's bit for bit by construction.
+//   2. k_pll_table     fully parallel: for every sample the EXACT errorD of the next step for the two neighbouring floats
+//                      the prediction lies between (the dy4_pllmath.h sincos + detector, unchanged arithmetic)
+//   3. k_pll_tab       the serial loop: per sample ONE float compare of phaseEst with a precomputed threshold picks the
+//                      grid point the true trigArg falls on, and two speculative loop-filter updates (float adds) are
+//                      selected from — tens of cycles instead of ~445.  Whenever the pick is not certain (outside the
+//                      two candidates, within a rounding-error guard band of the threshold, binade edges, start-up) the
+//                      thread evaluates that step directly with dy4_pllmath.h, so the result is the reference's bit for
+//                      bit by construction.
 //
-// Everything here is a fixed sequence of IEEE operations compiled for host and device; tools/plltab_check.c runs the
-// three parts on the host against the reference recurrence with glibc.
+// Everything here is a fixed sequence of IEEE operations compiled for host and device; tests/host/plltab_host.c runs the
+// three parts on the host against the reference recurrence with glibc (tests/test_host_logic.py).
 #pragma once
 #include "dy4_pllmath.h"
 
