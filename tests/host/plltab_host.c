@@ -88,3 +88,44 @@ void pllref_launch(const float* x, int n, float* state, double w, float Kp, floa
     }
     state[0] = fbI; state[1] = fbQ; state[2] = integ; state[3] = phase; state[4] = T;
 }
+
+/* Randomised check of the pick's certificate (dy4_tab_pick): for random sample counters, loop phases and predictions, and
+ * for phaseEst values placed within a few ulps of every boundary the row defines (the threshold t, the far ends t -+ u) as
+ * well as at random, a pick declared certain must name exactly RN_f(RN_d(w*T) + phaseEst).
+ * out[0] += cases, out[1] += certain picks, out[2] += certain-but-wrong picks (must stay 0), out[3] += uncertain. */
+static unsigned long long fz_state;
+static unsigned long long fz_next(void) { fz_state ^= fz_state << 13; fz_state ^= fz_state >> 7; fz_state ^= fz_state << 17; return fz_state; }
+static double fz_uni(void) { return (double)(fz_next() >> 11) * (1.0 / 9007199254740992.0); }
+
+void plltab_fuzz(long n, unsigned long long seed, double w, long* out)
+{
+    fz_state = seed * 0x9E3779B97F4A7C15ull + 88172645463325252ull;
+    for (long it = 0; it < n; it++) {
+        const double T = floor(fz_uni() * fz_uni() * 16000000.0) + 1.0;                  /* more weight on small counters (small u) */
+        const float phase0 = (float)((fz_uni() - 0.5) * (it % 5 == 0 ? 200.0 : 8.0));
+        const double wT = DY4_MUL(w, T);
+        const float th_true = dy4_pll_trigarg(w, T, phase0);
+        const float u = nextafterf(th_true, INFINITY) - th_true;
+        const double th_hat = (double)th_true + (fz_uni() - 0.5) * 2.6 * (double)u;      /* prediction within +-1.3 grid points */
+        dy4_tabrow_t r;
+        dy4_tab_make_row(th_hat, wT, 0.01f, 0, 0, 0.02666f, 0.0003555f, &r);
+        if (r.t != r.t) continue;                                                         /* unusable row (binade edge) */
+        for (int probe = 0; probe < 40; probe++) {
+            float ph;
+            const int kind = probe % 4;
+            const float base = kind == 0 ? r.t : kind == 1 ? r.t - r.u : kind == 2 ? r.t + r.u : phase0;
+            ph = base;
+            const int steps = (int)(fz_next() % 17) - 8;                                  /* -8 .. +8 ulps around the boundary */
+            for (int s = 0; s < (steps < 0 ? -steps : steps); s++) ph = nextafterf(ph, steps < 0 ? -INFINITY : INFINITY);
+            if (kind == 3) ph = (float)((double)phase0 + (fz_uni() - 0.5) * 3.0 * (double)r.u);
+            int up;
+            out[0]++;
+            if (dy4_tab_pick(ph, r.t, r.hu, r.hm, &up)) {
+                const float want = dy4_pll_trigarg(w, T, ph);
+                const float got = up ? r.lo + r.u : r.lo;
+                out[1]++;
+                if (want != got) out[2]++;
+            } else out[3]++;
+        }
+    }
+}

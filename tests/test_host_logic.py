@@ -154,3 +154,18 @@ def test_table_pll_host_build_long_stream_and_pick_rate(dy4, orc):
     th, st, _ = _plltab_run(lib, bad, 240e3, [5120] * 8)
     assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
     assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+
+
+def test_table_pll_pick_certificate_randomised():
+    """The exactness of the table-driven PLL rests on one claim: a pick declared certain names exactly
+    RN_f(RN_d(w*T) + phaseEst).  4 M probes, most of them within 8 ulps of a boundary of the row: no certain pick is wrong,
+    and away from the boundaries picks ARE certain (the guard band is not so wide that it hides the claim)."""
+    import ctypes as C
+    lib = _plltab_lib()
+    for Fs in (240e3, 288e3, 384e3):
+        w = 2 * 3.14159265358979323846 * float(np.float32(19e3) / np.float32(Fs))
+        out = (C.c_long * 4)(0, 0, 0, 0)
+        lib.plltab_fuzz(C.c_long(35000), C.c_ulonglong(int(Fs)), C.c_double(w), out)
+        cases, certain, wrong, uncertain = list(out)
+        assert cases > 1_000_000 and wrong == 0, (cases, certain, wrong, uncertain)
+        assert certain > 0.3 * cases, (cases, certain)
