@@ -304,10 +304,11 @@ __device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, 
 
 // A super-group again, carefully: a pick where it is certain, else that step directly (dy4_pllmath.h), as k_pll does.
 // Out of line and looping: it runs for a fraction of a percent of the super-groups once the loop is in lock.
-__device__ __noinline__ void tab_redo(const float4* src, const float* x_next, float* y, double T0, int k, int count, double w, float Kp, float Ki,
-                                      float* integ_io, float* phase_io)
+__device__ __noinline__ int tab_redo(const float4* src, const float* x_next, float* y, double T0, int k, int count, double w, float Kp, float Ki,
+                                     float* integ_io, float* phase_io)
 {
     float integ = *integ_io, phase = *phase_io;
+    int n_direct = 0;
 #pragma unroll 1
     for (int r = 0; r < count; r++) {
         const float4 q0 = src[2 * r], q1 = src[2 * r + 1];
@@ -315,10 +316,48 @@ __device__ __noinline__ void tab_redo(const float4* src, const float* x_next, fl
         int up;
         if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, &up))
             dy4_pll_filter_ab(up ? q1.y : q1.x, up ? q1.w : q1.z, &integ, &phase);
-        else
+        else {
             dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + r + 1), phase), x_next[r]), Kp, Ki, &integ, &phase);
+            n_direct++;
+        }
     }
     *integ_io = integ; *phase_io = phase;
+    return n_direct;                                          // steps that had to be evaluated directly
+}
+
+// Samples k0+1 .. k1 through the steps of the direct loop (pll_step_fast: straight-line groups of four whose independent
+// work overlaps the dependent chain, ~450 cycles per sample).  *rp / *op hold the state after sample k0 on entry, after
+// sample k1 on return; y[k] = phaseEst after sample k for k in [k0, k1).
+__device__ __noinline__ void tab_direct_span(const float* __restrict__ x, float* __restrict__ y, int n, int k0, int k1, PllRegs* rp, dy4_nco_t* op,
+                                             double w, float Kp, float Ki)
+{
+    PllConst c; c.w = w; c.Kp = Kp; c.Ki = Ki; c.ncoScale = 0.0f; c.phaseAdjust = 0.0f;
+    PllRegs r = *rp;
+    dy4_nco_t o = *op;
+    auto xat = [&](int i) { return x[min(i, n - 1)]; };
+    int k = k0;                                              // r holds the state after sample k
+    for (; k < k1 && (k & 3); k++) { y[k] = r.phase; pll_step_any<false>(xat(k + 1), xat(k + 2), r, c, o, true); }
+    float v0 = xat(k + 1), v1 = xat(k + 2), v2 = xat(k + 3), v3 = xat(k + 4), v4 = xat(k + 5);
+#pragma unroll 1
+    for (; k + 4 <= k1; k += 4) {
+        const float c0 = v0, c1 = v1, c2 = v2, c3 = v3, c4 = v4;
+        v0 = c4; v1 = xat(k + 6); v2 = xat(k + 7); v3 = xat(k + 8); v4 = xat(k + 9);
+        float q0, q1, q2, q3;
+        if (fast_ok(c0) && fast_ok(c1) && fast_ok(c2) && fast_ok(c3)) {
+            q0 = r.phase; pll_step_fast<1, false>(c0, dy4_recip(c0), c1, r, c, o);
+            q1 = r.phase; pll_step_fast<1, false>(c1, dy4_recip(c1), c2, r, c, o);
+            q2 = r.phase; pll_step_fast<1, false>(c2, dy4_recip(c2), c3, r, c, o);
+            q3 = r.phase; pll_step_fast<1, false>(c3, dy4_recip(c3), c4, r, c, o);
+        } else {
+            q0 = r.phase; pll_step_any<false>(c0, c1, r, c, o, true);
+            q1 = r.phase; pll_step_any<false>(c1, c2, r, c, o, true);
+            q2 = r.phase; pll_step_any<false>(c2, c3, r, c, o, true);
+            q3 = r.phase; pll_step_any<false>(c3, c4, r, c, o, true);
+        }
+        *reinterpret_cast<float4*>(y + k) = make_float4(q0, q1, q2, q3);
+    }
+    for (; k < k1; k++) { y[k] = r.phase; pll_step_any<false>(xat(k + 1), xat(k + 2), r, c, o, true); }
+    *rp = r; *op = o;
 }
 
 template <bool FENCE, int TAB_SG, int TAB_SLOTS>
@@ -367,36 +406,16 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
     if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
     else {
-        // direct part: the steps of k_pll (pll_step_fast: straight-line groups of four whose independent work overlaps
-        // the dependent chain, ~450 cycles per sample), samples 0 .. kd; it ends holding state_kd
+        // direct part (tab_direct_span), samples 0 .. kd; it ends holding state_kd
         PllRegs r = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
         dy4_nco_t o;
         o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
         pll_advance<1, false>(detector_libm(x[0], r.fbI, r.fbQ), r, c, o, n > 1 && x[1] < 0.0f);
-        auto xat = [&](int i) { return x[min(i, n - 1)]; };
-        float v0 = xat(1), v1 = xat(2), v2 = xat(3), v3 = xat(4), v4 = xat(5);
-        int k = 0;                                               // r holds the state after sample k
-#pragma unroll 1
-        for (; k + 4 <= kd; k += 4) {
-            const float c0 = v0, c1 = v1, c2 = v2, c3 = v3, c4 = v4;
-            v0 = c4; v1 = xat(k + 6); v2 = xat(k + 7); v3 = xat(k + 8); v4 = xat(k + 9);
-            float q0, q1, q2, q3;
-            if (fast_ok(c0) && fast_ok(c1) && fast_ok(c2) && fast_ok(c3)) {
-                q0 = r.phase; pll_step_fast<1, false>(c0, dy4_recip(c0), c1, r, c, o);
-                q1 = r.phase; pll_step_fast<1, false>(c1, dy4_recip(c1), c2, r, c, o);
-                q2 = r.phase; pll_step_fast<1, false>(c2, dy4_recip(c2), c3, r, c, o);
-                q3 = r.phase; pll_step_fast<1, false>(c3, dy4_recip(c3), c4, r, c, o);
-            } else {
-                q0 = r.phase; pll_step_any<false>(c0, c1, r, c, o, true);
-                q1 = r.phase; pll_step_any<false>(c1, c2, r, c, o, true);
-                q2 = r.phase; pll_step_any<false>(c2, c3, r, c, o, true);
-                q3 = r.phase; pll_step_any<false>(c3, c4, r, c, o, true);
-            }
-            *reinterpret_cast<float4*>(y + k) = make_float4(q0, q1, q2, q3);
-        }
-        for (; k < kd; k++) { y[k] = r.phase; pll_step_any<false>(xat(k + 1), xat(k + 2), r, c, o, true); }
+        tab_direct_span(x, y, n, 0, kd, &r, &o, c.w, c.Kp, c.Ki);
         integ = r.integ; phase = r.phase;
     }
+    int directs = 0, sg_done = n_sg;
+    bool bailed = false;
 #pragma unroll 1
     for (int i = 0; i < n_sg; i++) {
         const int slot = i % TAB_SLOTS;
@@ -422,12 +441,28 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
             }
             *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[0], ph[1], ph[2], ph[3]);   // (rewritten by tab_redo if a pick was not certain)
         }
-        if (!ok) { si = integ; sp = phase; tab_redo(src, x + k + 1, y + k, T0, k, TAB_SG, c.w, c.Kp, c.Ki, &si, &sp); }
+        if (!ok) {
+            si = integ; sp = phase;
+            directs += tab_redo(src, x + k + 1, y + k, T0, k, TAB_SG, c.w, c.Kp, c.Ki, &si, &sp);
+            // A stream whose loop is not in lock (no pilot, noise) misses all the time, and a direct evaluation inside the
+            // redo costs four times a step of the direct loop: once more than a quarter of the samples so far had to be
+            // evaluated directly, the rest of this launch goes through the direct loop.
+            if (i >= 2 && 4 * directs > (i + 1) * TAB_SG) { integ = si; phase = sp; sg_done = i + 1; bailed = true; break; }
+        }
         integ = si; phase = sp;
     }
-    {   // tail: rows straight from global memory
-        const int k = kd + n_sg * TAB_SG;
-        if (k < n_pick) tab_redo(rows + TAB_ROW_Q * (long long)k, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
+    {
+        const int k = kd + sg_done * TAB_SG;
+        if (bailed && k < n_pick) {                              // the rest directly, from state_k
+            const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
+            dy4_nco_t o;
+            dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
+            PllRegs r = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
+            tab_direct_span(x, y, n, k, n_pick, &r, &o, c.w, c.Kp, c.Ki);
+            integ = r.integ; phase = r.phase;
+        } else if (k < n_pick) {                                 // tail: rows straight from global memory
+            tab_redo(rows + TAB_ROW_Q * (long long)k, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
+        }
     }
     // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
     y[n - 1] = phase;

@@ -363,3 +363,34 @@ def test_table_pll_multi_subchunk_calls_with_signal_jump(dy4, checker, monkeypat
     direct = run()
     for k in tab:
         assert np.array_equal(direct[k], tab[k]), k
+
+
+def test_table_pll_streams_that_never_lock(dy4, checker):
+    """Input without a pilot (uniform noise bytes; an FM carrier with mono audio only): the PLL never locks, the
+    prediction is useless, every super-group is redone and the loop falls back to direct evaluation — the results are
+    still the reference's, bit for bit."""
+    import torch
+    mode, nb = 0, 10
+    m = dy4.mode_params(mode)
+    n_pairs = nb * m.block_size // 2
+    rng = np.random.default_rng(11)
+    noise = rng.integers(0, 256, size=2 * n_pairs, dtype=np.uint8)
+    t = np.arange(n_pairs) / 2.4e6
+    ph = 2 * np.pi * 75e3 * np.cumsum(0.5 * np.sin(2 * np.pi * 1e3 * t)) / 2.4e6          # mono programme, no 19 kHz pilot
+    mono = np.empty(2 * n_pairs, np.uint8)
+    mono[0::2] = np.clip(np.rint(100 * np.cos(ph) + 128), 0, 255)
+    mono[1::2] = np.clip(np.rint(100 * np.sin(ph) + 128), 0, 255)
+    iq = np.stack([noise, mono, dy4.synth.make_stream(mode, n_pairs, 65)])
+    p = dy4.Pipeline(mode, 1, 3, exact_audio=True)
+    try:
+        outs = [p.process(torch.from_numpy(iq).cuda(), want=("pcm", "audio", "if")) for _ in range(2)]
+        torch.cuda.synchronize()
+        got = {k: torch.cat([o[k] for o in outs], 1).cpu().numpy() for k in outs[0]}
+    finally:
+        p.close()
+    both = np.concatenate([iq, iq], axis=1)
+    for s in range(3):
+        ref = checker.pipeline(mode, 1, both[s])
+        assert np.array_equal(bits(got["if"][s]), bits(ref["if"])), s
+        assert np.array_equal(bits(got["audio"][s]), bits(ref["audio"])), s
+        assert np.array_equal(got["pcm"][s], ref["pcm"]), s
