@@ -460,8 +460,20 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
             PllRegs r = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
             tab_direct_span(x, y, n, k, n_pick, &r, &o, c.w, c.Kp, c.Ki);
             integ = r.integ; phase = r.phase;
-        } else if (k < n_pick) {                                 // tail: rows straight from global memory
-            tab_redo(rows + TAB_ROW_Q * (long long)k, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
+        } else if (k < n_pick) {
+            // tail (fewer than TAB_SG samples): its rows are first copied into ring slot 0 with all loads in flight at once —
+            // read one by one from global memory inside the step loop they would cost a DRAM latency per sample
+            float4* dst = ring + lane * TAB_LANE_Q;
+            const float4* src = rows + TAB_ROW_Q * (long long)k;
+            const int nq = TAB_ROW_Q * (n_pick - k);
+            for (int q = 0; q < nq; q += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __ldg(src + min(q + j, nq - 1));
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (q + j < nq) dst[q + j] = v[j];
+            }
+            tab_redo(dst, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
         }
     }
     // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
