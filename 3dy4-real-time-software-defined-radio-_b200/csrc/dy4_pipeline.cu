@@ -69,6 +69,7 @@ struct dy4_pipeline {
     long long rds_blocks_since_drain = 0;
     cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
+    bool pll_spec = true;                            // ... with 16-byte rows and the speculative serial loop (k_pll_spec)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr, ev_prep1 = nullptr;
@@ -180,6 +181,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     int tab_max = (p->flags & DY4_FLAG_RDS) ? 1024 : 4096;
     if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
     p->pll_table = p->stereo && p->n_streams <= tab_max;
+    if (const char* e = std::getenv("DY4_PLL_SPEC")) p->pll_spec = atoi(e) != 0;
     const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 32 : 16) : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
@@ -209,7 +211,8 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.nco, bytes));
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
-            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 64 * sizeof(float4)));   // padded: the serial loop prefetches whole groups of four rows
+            // padded: the serial loop copies whole chunks of 64 rows
+            if (p->pll_table) CU(cudaMalloc(&w.tab, (p->pll_spec ? 4 : 8) * bytes + 256 * sizeof(float4)));
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
@@ -392,7 +395,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    pa.tab = w.tab; pa.spec = p->pll_spec ? 1 : 0; pa.tab_stride = (p->pll_spec ? 1 : 2) * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
     if (w.tab) {
         pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
         pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;

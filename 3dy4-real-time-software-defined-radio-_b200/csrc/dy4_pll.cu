@@ -488,6 +488,454 @@ k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __res
     need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
 }
 
+// ====================================================================================================================
+// Speculative serial loop (dy4_plltab.h §2b): 16-byte rows (predicted candidate, other candidate, double threshold).
+// One WARP per stream.  The dependent chain of a step is three float adds of the predicted candidate's products — no
+// compare, no select: the predictor names the right candidate ~96 % of the time.  All 32 lanes run the same chain;
+// G steps are straight-line code, every step parks (integ, phaseEst) in shared memory, and afterwards lane i certifies
+// step i (dy4_spec_check, in double, off the chain).  A ballot finds the first step that is not certainly the predicted
+// candidate: the loop resumes THERE, from the parked state, with that step forced to the other candidate (certified the
+// same way); if neither candidate is certain the step is evaluated directly (dy4_pllmath.h), so the result is the
+// reference's by construction, as in k_pll_tab.  Rows arrive by one bulk asynchronous copy per 64 samples into a ring
+// of 4 slots; the lanes turn each landed chunk into the chain's operands (Ki*e, Kp*e of both candidates) in one pass.
+// ====================================================================================================================
+constexpr int SPEC_SG = 128;                         // rows per bulk copy
+constexpr int SPEC_SLOTS = 4;
+constexpr int SPEC_R = SPEC_SG * SPEC_SLOTS;         // ring size in rows
+
+__global__ void __launch_bounds__(128)
+k_pll_table16(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
+              const double* __restrict__ th_hat, long long wide_stride, dy4_row16_t* __restrict__ tab, long long tab_stride, int n, PllConst c)
+{
+    const int s = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double T0 = pred_out[8 * s + 3];                          // sample counter at the start of this launch (k_pll_predict)
+    const float* x = in + (long long)s * in_stride;
+    dy4_row16_t r;
+    dy4_tab_make_row16(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
+                       k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r, nullptr, nullptr);
+    float4 v;
+    v.x = __int_as_float(__double2loint(r.t)); v.y = __int_as_float(__double2hiint(r.t)); v.z = r.e_p; v.w = r.e_o;
+    reinterpret_cast<float4*>(tab + (long long)s * tab_stride)[k] = v;
+}
+
+// One step at row k, carefully: dy4_spec_check (double) for the predicted, then the other candidate; if neither is
+// certain the step is evaluated directly (filter.cpp:192-214 through dy4_pllmath.h).  Returns (integ, phase); *direct = 1
+// if it came to that.  Out of line: it runs where the float certificate of the loop is too coarse (the first ~0.1 s of
+// a stream), at binade edges of trigArg, and where the loop is not in lock.
+__device__ __noinline__ float2 spec_slow_step(double t, float e_p, float e_o, const float* __restrict__ x, int n, int k, double T0, double w, float Kp, float Ki,
+                                              float integ, float phase, int* direct)
+{
+    float eD;
+    *direct = 0;
+    if (dy4_spec_check(phase, t, 0)) eD = e_p;
+    else if (dy4_spec_check(phase, t, 1)) eD = e_o;
+    else {
+        eD = dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase), x[min(k + 1, n - 1)]);
+        *direct = 1;
+    }
+    dy4_pll_filter(eD, Kp, Ki, &integ, &phase);
+    return make_float2(integ, phase);
+}
+
+__device__ int g_spec_stats[4];      // rows, groups run, flips, direct steps (development counters, DY4_PLL_STATS=1)
+
+// Per-warp state of the speculative loop.  `r`: first row not yet run (rows before it are run, the last group of them
+// possibly not yet certified); (integ, phase): state before row r.  The group [pr, pr + pn) is run but not certified.
+struct SpecLoop {
+    int r, forced;                   // forced: row r must take the OTHER candidate (it was certainly not the predicted one)
+    int pr, pn, pforced;             // pending group: first row, rows, whether its first step took the other candidate
+    float integ, phase;
+};
+
+// One trip: certify the pending group (its states are in cap_prev) while the chain of the next group runs from the
+// state the pending group ended in.  ab: the chain's operands (Ki e, Kp e) of rows r .. r+G-1, already in registers;
+// abn receives those of rows r+G .. r+2G-1 for the next trip.  Returns the number of certain steps of the pending group
+// (== L.pn: all of them; the caller then makes the new group the pending one).
+template <int G>
+__device__ __forceinline__ int spec_trip(const SpecLoop& L, const float4* __restrict__ conv, const float4* __restrict__ chk,
+                                         const float2* __restrict__ cap_prev, float2* __restrict__ cap_cur, const float2 (&ab)[G], float2 (&abn)[G],
+                                         float* __restrict__ y_prev, int lane, float& si, float& sp)
+{
+    // certificate of the pending group, lane i for step i (float form; dy4_spec_fast_row)
+    const float myph = cap_prev[min(lane, G)].y;
+    const float4 q = chk[(L.pr + lane) & (SPEC_R - 1)];
+    const float tc = (lane == 0 && L.pforced) ? q.z : q.x;
+    const bool good = (lane >= L.pn) | (dy4_spec_fast_check(myph, tc, q.y) != 0);
+    // operands of the group after this one (optimistic: this group will be found certain)
+    const float4* cvn = conv + ((L.r + G) & (SPEC_R - 1));
+#pragma unroll
+    for (int i = 0; i < G; i++) abn[i] = *reinterpret_cast<const float2*>(cvn + i);
+    // the chain: three dependent float adds per step (filter.cpp:207,210), state parked before every step
+    si = L.integ; sp = L.phase;
+#pragma unroll
+    for (int i = 0; i < G; i++) {
+        cap_cur[i] = make_float2(si, sp);
+        si = __fadd_rn(si, ab[i].x);
+        sp = __fadd_rn(sp, __fadd_rn(ab[i].y, si));
+    }
+    cap_cur[G] = make_float2(si, sp);
+    const unsigned bad = ~__ballot_sync(0xffffffffu, good);
+    const int j = bad ? __ffs(bad) - 1 : L.pn;
+    if (lane < j) y_prev[lane] = myph;                 // phaseEst after each certain sample (k_nco_phase turns it into the NCO row)
+    return j;
+}
+
+template <int G>
+__global__ void __launch_bounds__(32)
+k_pll_spec(const float* __restrict__ in, long long in_stride, const dy4_row16_t* __restrict__ tab, long long tab_stride,
+           float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
+           const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int* __restrict__ stats, int n, int n_streams, PllConst c)
+{
+    static_assert(G >= 4 && G <= 32 && 3 * G <= SPEC_SG, "one lane certifies one step; three groups must fit a chunk");
+    __shared__ __align__(16) dy4_row16_t raw[SPEC_R];
+    __shared__ __align__(16) float4 conv[SPEC_R + 32];            // (Ki e_p, Kp e_p, Ki e_o, Kp e_o); the last 32 mirror the first 32
+    __shared__ __align__(16) float4 chk[SPEC_R];                  // (tc_p, hm, tc_o, -), dy4_spec_fast_row
+    __shared__ __align__(8) float2 cap0[G + 1], cap1[G + 1];      // (integ, phaseEst) before every step of a group, double-buffered
+    __shared__ __align__(8) unsigned long long bars[SPEC_SLOTS];
+    const int lane = threadIdx.x;
+    const int s = blockIdx.x;
+    if (s >= n_streams || n <= 0) return;
+    float* st = state + (long long)s * 8;
+    float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
+    const double T0 = (double)st[4];
+    const float nco_carry = st[5];
+    const float* x = in + (long long)s * in_stride;
+    const dy4_row16_t* rows = tab + (long long)s * tab_stride;
+    float* y = phase_out + (long long)s * phase_stride;
+    const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
+    int kd = 0;                                      // leading samples evaluated directly (see k_pll_tab)
+    if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
+    if (pred[8 * s + 3] != T0) kd = n_pick;          // a table built for another sample counter: nothing of it is used
+    const int n_rows = n_pick - kd;
+    const int n_chunks = (n_rows + SPEC_SG - 1) / SPEC_SG;
+    auto issue = [&](int cc) {                       // chunk cc -> slot cc % SPEC_SLOTS (lane 0)
+        const int slot = cc % SPEC_SLOTS;
+        tab_bulk_load<SPEC_SG * 16>(raw + slot * SPEC_SG, rows + (long long)kd + (long long)cc * SPEC_SG, &bars[slot]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < SPEC_SLOTS; i++) tab_mbar_init(&bars[i]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < SPEC_SLOTS && i < n_chunks; i++) issue(i);
+    }
+    __syncwarp();
+    // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
+    if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
+    else {
+        PllRegs rg = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
+        dy4_nco_t o;
+        o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
+        pll_advance<1, false>(detector_libm(x[0], rg.fbI, rg.fbQ), rg, c, o, n > 1 && x[1] < 0.0f);
+        tab_direct_span(x, y, n, 0, kd, &rg, &o, c.w, c.Kp, c.Ki);
+        integ = rg.integ; phase = rg.phase;
+    }
+    int conv_chunks = 0, directs = 0, trips = 0, flips = 0;
+    bool bailed = false;
+    // rows up to `upto` (exclusive) must be in conv / chk: turn the chunks that have landed into the loop's operands
+    // and keep two more chunks in flight.  Chunk cc-2 is consumed by then: the oldest row the loop can come back to is
+    // the pending group's first, r - G, and conversion of chunk cc is asked for when r + 2G > cc*SG, i.e. r - G > (cc-1)*SG.
+    auto cover = [&](int upto) {
+        while (conv_chunks < n_chunks && conv_chunks * SPEC_SG < upto) {
+            const int cc = conv_chunks, slot = cc % SPEC_SLOTS;
+            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
+            while (!tab_mbar_try(&bars[slot], parity)) { }
+#pragma unroll
+            for (int p = 0; p < SPEC_SG / 32; p++) {
+                const int idx = slot * SPEC_SG + p * 32 + lane;
+                const dy4_row16_t row = raw[idx];
+                const float4 q = make_float4(__fmul_rn(c.Ki, row.e_p), __fmul_rn(c.Kp, row.e_p), __fmul_rn(c.Ki, row.e_o), __fmul_rn(c.Kp, row.e_o));
+                conv[idx] = q;
+                if (idx < 32) conv[SPEC_R + idx] = q;
+                float4 v;
+                dy4_spec_fast_row(row.t, &v.x, &v.y, &v.z);
+                v.w = 0.0f;
+                chk[idx] = v;
+            }
+            conv_chunks++;
+            __syncwarp();
+            if (cc >= 2 && cc + 2 < n_chunks && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(cc + 2);
+            }
+        }
+    };
+    SpecLoop L;
+    L.r = 0; L.forced = 0; L.pr = 0; L.pn = 0; L.pforced = 0; L.integ = integ; L.phase = phase;
+    float2 ab0[G], ab1[G];
+    // (re)start at row L.r from (L.integ, L.phase): nothing pending, operands of rows r .. r+G-1 into ab0
+    auto restart = [&]() {
+        cover(L.r + 2 * G);
+        L.pn = 0; L.pr = L.r; L.pforced = 0;
+        const float4* cv = conv + (L.r & (SPEC_R - 1));
+        const float4 q0 = cv[0];
+        ab0[0] = L.forced ? make_float2(q0.z, q0.w) : make_float2(q0.x, q0.y);
+#pragma unroll
+        for (int i = 1; i < G; i++) ab0[i] = *reinterpret_cast<const float2*>(cv + i);
+    };
+    // the pending group failed at its step j (< L.pn): resume there
+    auto recover = [&](int j, const float2* cap_prev) {
+        const int k = L.pr + j;                                  // row that is not certainly the predicted candidate
+        const float2 sj = cap_prev[j];
+        if (j == 0 && L.pforced) {                               // ... and not certainly the other one either (float certificate)
+            const dy4_row16_t row = raw[k & (SPEC_R - 1)];
+            int direct;
+            const float2 nx = spec_slow_step(row.t, row.e_p, row.e_o, x, n, kd + k, T0, c.w, c.Kp, c.Ki, sj.x, sj.y, &direct);
+            if (lane == 0) y[kd + k] = sj.y;
+            L.integ = nx.x; L.phase = nx.y; L.r = k + 1; L.forced = 0;
+            directs += direct;
+        } else {
+            // a row with no usable threshold (NaN) goes straight to the careful step
+            L.integ = sj.x; L.phase = sj.y; L.r = k; L.forced = 1;
+            flips++;
+        }
+    };
+    restart();
+#pragma unroll 1
+    while (L.r < n_rows || L.pn > 0) {
+        float si, sp;
+        int j;
+        // ---- even trip: pending states in cap1, this group's into cap0, operands ab0 -> prefetch ab1
+        cover(L.r + 2 * G);
+        j = spec_trip<G>(L, conv, chk, cap1, cap0, ab0, ab1, y + kd + L.pr, lane, si, sp);
+        trips++;
+        if (j < L.pn) {
+            recover(j, cap1);
+            if (L.r >= 2 * SPEC_SG && 4 * directs > L.r) { bailed = true; L.pn = 0; break; }
+            restart();
+            continue;
+        }
+        {
+            const int nv = max(0, min(G, n_rows - L.r));
+            L.pr = L.r; L.pn = nv; L.pforced = L.forced; L.forced = 0;
+            if (nv < G) { const float2 e = cap0[nv]; si = e.x; sp = e.y; }   // the launch's last rows: state after the last valid one
+            L.r += nv; L.integ = si; L.phase = sp;
+        }
+        // ---- odd trip: roles of the buffers swapped
+        cover(L.r + 2 * G);
+        j = spec_trip<G>(L, conv, chk, cap0, cap1, ab1, ab0, y + kd + L.pr, lane, si, sp);
+        trips++;
+        if (j < L.pn) {
+            recover(j, cap0);
+            if (L.r >= 2 * SPEC_SG && 4 * directs > L.r) { bailed = true; L.pn = 0; break; }
+            restart();
+            continue;
+        }
+        {
+            const int nv = max(0, min(G, n_rows - L.r));
+            L.pr = L.r; L.pn = nv; L.pforced = L.forced; L.forced = 0;
+            if (nv < G) { const float2 e = cap1[nv]; si = e.x; sp = e.y; }
+            L.r += nv; L.integ = si; L.phase = sp;
+        }
+    }
+    integ = L.integ; phase = L.phase;
+    // no bulk copy may be in flight when the CTA retires: wait for every chunk that was issued and not consumed
+    {
+        const int issued = min(n_chunks, max(SPEC_SLOTS, conv_chunks + 2));
+        for (int cc = conv_chunks; cc < issued; cc++) {
+            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
+            while (!tab_mbar_try(&bars[cc % SPEC_SLOTS], parity)) { }
+        }
+    }
+    if (bailed && kd + L.r < n_pick) {                                        // the rest directly, from state_k
+        const int k = kd + L.r;
+        const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
+        dy4_nco_t o;
+        dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
+        PllRegs rg = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
+        tab_direct_span(x, y, n, k, n_pick, &rg, &o, c.w, c.Kp, c.Ki);
+        integ = rg.integ; phase = rg.phase;
+    }
+    // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
+    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
+    dy4_nco_t o;
+    dy4_sincos_nco_v((double)th, 0, &o, 0);
+    const float nco_next = nco_value(th, c.ncoScale, c.phaseAdjust);          // nco_state for the next launch (filter.cpp:218-219)
+    if (lane == 0) {
+        y[n - 1] = phase;
+        nco0[s] = nco_carry;                         // nco_state opens this launch's NCO row (filter.cpp:184)
+        tstart[s] = (float)T0;                       // k_nco_phase needs the sample counter this launch started from
+        st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
+        st[4] = (float)dy4_pll_count(T0, n);
+        st[5] = nco_next;
+        // how many whole turns the prediction of this launch ended away from the true phaseEst (see k_pll_predict)
+        need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
+        if (stats) { atomicAdd(stats + 0, n_rows); atomicAdd(stats + 1, trips); atomicAdd(stats + 2, flips); atomicAdd(stats + 3, directs); }
+    }
+}
+
+// Variant B of the speculative loop: the group is certified right after its own chain (nothing runs ahead on an
+// uncertified state, so a flip wastes only the steps behind it).  Lane i catches phaseEst before step i in a register
+// on the way (one LOP3 with a lane mask per step), so the certificate is one subtract, one compare and a vote after the
+// last step; (integ, phaseEst) of every step are also parked in shared memory for the resume.
+template <int G>
+__global__ void __launch_bounds__(32)
+k_pll_spec2(const float* __restrict__ in, long long in_stride, const dy4_row16_t* __restrict__ tab, long long tab_stride,
+            float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
+            const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int* __restrict__ stats, int n, int n_streams, PllConst c)
+{
+    static_assert(G >= 4 && G <= 32 && 3 * G <= SPEC_SG, "one lane certifies one step");
+    __shared__ __align__(16) dy4_row16_t raw[SPEC_R];
+    __shared__ __align__(16) float4 conv[SPEC_R + 32];
+    __shared__ __align__(16) float4 chk[SPEC_R];
+    __shared__ __align__(16) float2 cap[G + 2];
+    __shared__ __align__(8) unsigned long long bars[SPEC_SLOTS];
+    const int lane = threadIdx.x;
+    const int s = blockIdx.x;
+    if (s >= n_streams || n <= 0) return;
+    float* st = state + (long long)s * 8;
+    float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
+    const double T0 = (double)st[4];
+    const float nco_carry = st[5];
+    const float* x = in + (long long)s * in_stride;
+    const dy4_row16_t* rows = tab + (long long)s * tab_stride;
+    float* y = phase_out + (long long)s * phase_stride;
+    const int n_pick = n - 1;
+    int kd = 0;
+    if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
+    if (pred[8 * s + 3] != T0) kd = n_pick;
+    const int n_rows = n_pick - kd;
+    const int n_chunks = (n_rows + SPEC_SG - 1) / SPEC_SG;
+    auto issue = [&](int cc) {
+        const int slot = cc % SPEC_SLOTS;
+        tab_bulk_load<SPEC_SG * 16>(raw + slot * SPEC_SG, rows + (long long)kd + (long long)cc * SPEC_SG, &bars[slot]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < SPEC_SLOTS; i++) tab_mbar_init(&bars[i]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < SPEC_SLOTS && i < n_chunks; i++) issue(i);
+    }
+    __syncwarp();
+    if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
+    else {
+        PllRegs rg = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
+        dy4_nco_t o;
+        o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
+        pll_advance<1, false>(detector_libm(x[0], rg.fbI, rg.fbQ), rg, c, o, n > 1 && x[1] < 0.0f);
+        tab_direct_span(x, y, n, 0, kd, &rg, &o, c.w, c.Kp, c.Ki);
+        integ = rg.integ; phase = rg.phase;
+    }
+    int conv_chunks = 0, directs = 0, trips = 0, flips = 0;
+    bool bailed = false;
+    auto cover = [&](int upto) {
+        while (conv_chunks < n_chunks && conv_chunks * SPEC_SG < upto) {
+            const int cc = conv_chunks, slot = cc % SPEC_SLOTS;
+            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
+            while (!tab_mbar_try(&bars[slot], parity)) { }
+#pragma unroll
+            for (int p = 0; p < SPEC_SG / 32; p++) {
+                const int idx = slot * SPEC_SG + p * 32 + lane;
+                const dy4_row16_t row = raw[idx];
+                const float4 q = make_float4(__fmul_rn(c.Ki, row.e_p), __fmul_rn(c.Kp, row.e_p), __fmul_rn(c.Ki, row.e_o), __fmul_rn(c.Kp, row.e_o));
+                conv[idx] = q;
+                if (idx < 32) conv[SPEC_R + idx] = q;
+                float4 v;
+                dy4_spec_fast_row(row.t, &v.x, &v.y, &v.z);
+                v.w = 0.0f;
+                chk[idx] = v;
+            }
+            conv_chunks++;
+            __syncwarp();
+            if (cc >= 2 && cc + 2 < n_chunks && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(cc + 2);
+            }
+        }
+    };
+    unsigned mask[G];                                 // lane i: all ones in mask[i]
+#pragma unroll
+    for (int i = 0; i < G; i++) { const unsigned m = lane == i ? 0xffffffffu : 0u; asm volatile("mov.b32 %0, %1;" : "=r"(mask[i]) : "r"(m)); }
+    int r = 0, forced = 0;
+    float2 ab[G], abn[G];
+    auto load_ops = [&](float2 (&dst)[G], int row, int f) {
+        const float4* cv = conv + (row & (SPEC_R - 1));
+        const float4 q0 = cv[0];
+        dst[0] = f ? make_float2(q0.z, q0.w) : make_float2(q0.x, q0.y);
+#pragma unroll
+        for (int i = 1; i < G; i++) dst[i] = *reinterpret_cast<const float2*>(cv + i);
+    };
+    cover(2 * G);
+    load_ops(ab, 0, 0);
+#pragma unroll 1
+    while (r < n_rows) {
+        cover(r + 2 * G);
+        const int nv = min(G, n_rows - r);
+        const float4 q = chk[(r + lane) & (SPEC_R - 1)];
+        const float tc = (lane == 0 && forced) ? q.z : q.x;
+        load_ops(abn, r + G, 0);                      // operands of the next group, should this one hold
+        float si = integ, sp = phase;
+        unsigned mine = 0;
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            cap[i] = make_float2(si, sp);
+            mine |= __float_as_uint(sp) & mask[i];
+            si = __fadd_rn(si, ab[i].x);
+            sp = __fadd_rn(sp, __fadd_rn(ab[i].y, si));
+        }
+        cap[G] = make_float2(si, sp);
+        const float myph = __uint_as_float(mine);
+        const bool good = (lane >= nv) | (dy4_spec_fast_check(myph, tc, q.y) != 0);
+        const unsigned bad = ~__ballot_sync(0xffffffffu, good);
+        const int j = bad ? __ffs(bad) - 1 : nv;
+        if (lane < j) y[kd + r + lane] = myph;
+        trips++;
+        if (j == G) {                                 // the whole group is certain: straight on
+            r += G; integ = si; phase = sp; forced = 0;
+#pragma unroll
+            for (int i = 0; i < G; i++) ab[i] = abn[i];
+            continue;
+        }
+        const float2 sj = cap[j];
+        if (j == nv) { r += nv; integ = sj.x; phase = sj.y; break; }       // the launch's last rows
+        const int k = r + j;
+        if (j == 0 && forced) {
+            const dy4_row16_t row = raw[k & (SPEC_R - 1)];
+            int direct;
+            const float2 nx = spec_slow_step(row.t, row.e_p, row.e_o, x, n, kd + k, T0, c.w, c.Kp, c.Ki, sj.x, sj.y, &direct);
+            if (lane == 0) y[kd + k] = sj.y;
+            integ = nx.x; phase = nx.y; r = k + 1; forced = 0;
+            directs += direct;
+            if (r >= 2 * SPEC_SG && 4 * directs > r) { bailed = true; break; }
+        } else { integ = sj.x; phase = sj.y; r = k; forced = 1; flips++; }
+        cover(r + 2 * G);
+        load_ops(ab, r, forced);
+    }
+    {
+        const int issued = min(n_chunks, max(SPEC_SLOTS, conv_chunks + 2));
+        for (int cc = conv_chunks; cc < issued; cc++) {
+            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
+            while (!tab_mbar_try(&bars[cc % SPEC_SLOTS], parity)) { }
+        }
+    }
+    if (bailed && kd + r < n_pick) {
+        const int k = kd + r;
+        const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
+        dy4_nco_t o;
+        dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
+        PllRegs rg = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
+        tab_direct_span(x, y, n, k, n_pick, &rg, &o, c.w, c.Kp, c.Ki);
+        integ = rg.integ; phase = rg.phase;
+    }
+    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
+    dy4_nco_t o;
+    dy4_sincos_nco_v((double)th, 0, &o, 0);
+    const float nco_next = nco_value(th, c.ncoScale, c.phaseAdjust);
+    if (lane == 0) {
+        y[n - 1] = phase;
+        nco0[s] = nco_carry;
+        tstart[s] = (float)T0;
+        st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
+        st[4] = (float)dy4_pll_count(T0, n);
+        st[5] = nco_next;
+        need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
+        if (stats) { atomicAdd(stats + 0, n_rows); atomicAdd(stats + 1, trips); atomicAdd(stats + 2, flips); atomicAdd(stats + 3, directs); }
+    }
+}
+
 // NCO row from the phaseEst row of k_pll_tab: trigArg[k-1] = RN_f(RN_d(w*T) + phase[k-1]) (filter.cpp:214), then as k_nco
 __global__ void __launch_bounds__(256)
 k_nco_phase(const float* __restrict__ phase, long long phase_stride, const float* __restrict__ nco0, const float* __restrict__ tstart,
@@ -537,7 +985,19 @@ k_pll_prep(const float* __restrict__ in, long long in_stride, double* __restrict
     }
 }
 
+bool g_spec_stats_on = std::getenv("DY4_PLL_STATS") != nullptr;
+
 }  // namespace
+
+// development counters of the speculative loop: rows, iterations, flips, direct steps since the last call
+extern "C" int dy4_debug_pll_stats(long long* out4)
+{
+    int h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(h, g_spec_stats, sizeof(h)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_spec_stats, z, sizeof(z));
+    for (int i = 0; i < 4; i++) out4[i] = h[i];
+    return 0;
+}
 
 cudaError_t dy4_launch_pll(const Dy4PllArgs& a, cudaStream_t st) { return dy4_launch_pll_parts(a, st, DY4_PLL_PREP | DY4_PLL_LOOP | DY4_PLL_NCO); }
 
@@ -588,12 +1048,38 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             // DY4_PLL_TABLE_SMEM (bytes of unused dynamic shared memory per CTA) caps the resident CTAs of the table kernel: fewer
             // warps contending with the serial loops it runs beside (A/B knob)
             static const int tab_smem = std::getenv("DY4_PLL_TABLE_SMEM") ? atoi(std::getenv("DY4_PLL_TABLE_SMEM")) : 0;
-            k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, tab_smem, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            if (a.spec) k_pll_table16<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride,
+                                                                                              reinterpret_cast<dy4_row16_t*>(a.tab), a.tab_stride, a.n, c);
+            else k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, tab_smem, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             g_dy4_launches += 2;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
-        if (parts & DY4_PLL_LOOP) {
+        if ((parts & DY4_PLL_LOOP) && a.spec) {
+            float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
+            static const int g = std::getenv("DY4_PLL_G") ? atoi(std::getenv("DY4_PLL_G")) : 16;
+            int* stats = nullptr;
+            if (g_spec_stats_on) cudaGetSymbolAddress(reinterpret_cast<void**>(&stats), g_spec_stats);
+#define DY4_SPEC_ARGS a.in, a.in_stride, reinterpret_cast<const dy4_row16_t*>(a.tab), a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, stats, a.n, a.n_streams, c
+            static const int variant = std::getenv("DY4_PLL_VARIANT") ? atoi(std::getenv("DY4_PLL_VARIANT")) : 2;
+            if (variant == 1) {
+                if (g <= 8) k_pll_spec<8><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 12) k_pll_spec<12><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 16) k_pll_spec<16><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 24) k_pll_spec<24><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else k_pll_spec<32><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+            } else {
+                if (g <= 8) k_pll_spec2<8><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 12) k_pll_spec2<12><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 16) k_pll_spec2<16><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else if (g <= 24) k_pll_spec2<24><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+                else k_pll_spec2<32><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
+            }
+#undef DY4_SPEC_ARGS
+            g_dy4_launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        } else if (parts & DY4_PLL_LOOP) {
             int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
             lanes = std::max(1, std::min(lanes, TAB_LANES));
             static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);

@@ -140,6 +140,80 @@ DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_nex
     }
 }
 
+// ---- 2b. the 16-byte row of the speculative loop (k_pll_spec) -------------------------------------------------------
+// The same two candidates, stored as (predicted, other) instead of (lo, hi): the serial loop ADDS the predicted
+// candidate's products unconditionally — its dependent chain is three float adds per sample, no compare, no select —
+// and certifies afterwards, off the chain, that phaseEst really was inside the predicted candidate's cell.
+//   t    double: threshold between lo and hi in the phaseEst domain, t = (lo - RN_d(w*T)) + u/2, with the low 9 mantissa
+//        bits replaced by  bit 0: the predicted candidate is hi;  bits 1..8: biased float exponent of u.  NaN: row unusable.
+//   e_p, e_o   errorD of the next step if trigArg is the predicted / the other candidate (filter.cpp:200)
+// A double threshold makes the certificate's error budget 2^-26 u + 2^-40 |t| (see dy4_spec_check): with a float
+// threshold (dy4_tabrow_t) the half-ulp of t alone is 0.6 % of u early in a stream.
+typedef struct { double t; float e_p, e_o; } dy4_row16_t;
+
+#if defined(__CUDA_ARCH__)
+DY4_HD unsigned long long dy4_d2u_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+DY4_HD double dy4_u2d_bits(unsigned long long v) { return __longlong_as_double((long long)v); }
+#else
+DY4_HD unsigned long long dy4_d2u_bits(double v) { unsigned long long b; memcpy(&b, &v, 8); return b; }
+DY4_HD double dy4_u2d_bits(unsigned long long v) { double f; memcpy(&f, &v, 8); return f; }
+#endif
+
+// Arguments as dy4_tab_make_row.  *lo_out / *u_out (host checks only, may be NULL): the lower candidate and the grid spacing.
+DY4_HD void dy4_tab_make_row16(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_row16_t* r, float* lo_out, float* u_out)
+{
+    const float c = DY4_D2F(th_hat);
+    const int bits = dy4_f2i_bits(c);
+    const int expo = (bits >> 23) & 0xff, mant = bits & 0x7fffff;
+    const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
+    const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
+    const int pred_hi = !(th_hat >= (double)c);                    // c is the candidate nearest to the prediction
+    const float lo = pred_hi ? DY4_FADDF(c, -u) : c, hi = DY4_FADDF(lo, u);
+    const double t = DY4_ADD(DY4_SUB((double)lo, wT), DY4_MUL(0.5, (double)u));
+    const unsigned long long tb = (dy4_d2u_bits(t) & ~0x1ffull) | (unsigned long long)pred_hi | ((unsigned long long)(expo - 23) << 1);
+    r->t = ok ? dy4_u2d_bits(tb) : dy4_u2d_bits(0x7ff8000000000000ull);
+    r->e_p = r->e_o = 0.0f;
+    if (lo_out) *lo_out = lo;
+    if (u_out) *u_out = u;
+    if (ok && has_next) {
+        r->e_p = dy4_next_errorD((double)(pred_hi ? hi : lo), x_next);
+        r->e_o = dy4_next_errorD((double)(pred_hi ? lo : hi), x_next);
+    }
+}
+
+// Is trigArg = RN_f(RN_d(w*T) + phase) CERTAINLY the predicted candidate of this row (other == 0) / the other one (other == 1)?
+// With d = phase - t:  hi iff d in (0, u), lo iff d in (-u, 0); certain when d keeps a distance m from the ends, where
+// m = 2^-26 u + 2^-40 |t| bounds everything that is not exact on the way: the 9 borrowed mantissa bits of t (2^-43 |t|),
+// the two double roundings in t (2^-52 |t|), this subtraction (2^-53 |d|) and the reference's own RN_d (2^-29 u).
+// A NaN row fails both comparisons.
+DY4_HD int dy4_spec_check(float phase, double t, int other)
+{
+    const unsigned long long b = dy4_d2u_bits(t);
+    const int side_hi = (int)(b & 1) ^ other;
+    const double u = dy4_u2d_bits((((b >> 1) & 0xff) + 896ull) << 52);      // 2^(e - 127) as a double: e - 127 + 1023
+    const double d = DY4_SUB((double)phase, t);
+    const double dd = side_hi ? d : -d;
+    const double m = DY4_ADD(DY4_MUL(1.490116119384765625e-08, u), DY4_MUL(9.094947017729282379e-13, fabs(t)));
+    return dd > m && dd < DY4_SUB(u, m);
+}
+
+// The loop's fast certificate, in float, for whole groups at once: the cell's centre tc = t -+ u/2 rounded to float and
+// a half-width hm = u/2 - m_f with m_f = 2^-22 (|t| + u), which covers the float rounding of t (2^-24 |t|), of tc
+// (2^-24 (|t| + u/2)) and of the loop's own subtraction (2^-24 u) on top of dy4_spec_check's budget, twice over.
+// |phase - tc| < hm  =>  dy4_spec_check holds.  Where it fails the loop falls back on dy4_spec_check itself.
+// q = (tc of the predicted candidate, hm, tc of the other candidate); a NaN row gives NaN everywhere (never certain).
+DY4_HD void dy4_spec_fast_row(double t, float* tc_p, float* hm, float* tc_o)
+{
+    const unsigned long long b = dy4_d2u_bits(t);
+    const float u = dy4_i2f_bits((int)((b >> 1) & 0xff) << 23);
+    const float tf = DY4_D2F(t), hu = DY4_FMULF(0.5f, u);
+    const float up = DY4_FADDF(tf, hu), dn = DY4_FADDF(tf, -hu);
+    *tc_p = (b & 1) ? up : dn;
+    *tc_o = (b & 1) ? dn : up;
+    *hm = DY4_FADDF(hu, -DY4_FMULF(2.384185791015625e-07f, DY4_FADDF(fabsf(tf), u)));
+}
+DY4_HD int dy4_spec_fast_check(float phase, float tc, float hm) { return fabsf(DY4_FADDF(phase, -tc)) < hm; }
+
 // ---- 3. the pick ----------------------------------------------------------------------------------------------------
 // Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *up (0: lo, 1: hi) when that is certain:
 // phase is farther than m from the threshold t between the two and closer than u - m (their far ends), i.e.

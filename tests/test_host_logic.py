@@ -101,16 +101,17 @@ def _plltab_run(lib, pilot, Fs, launches, which="plltab_launch"):
     Ki = np.float32(np.float32(0.01) * np.float32(0.01)) * np.float32(3.555)
     th = np.zeros(pilot.size, np.float32)
     st = np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32)              # PLLState, project.cpp:46-53
-    stats = (C.c_long * 3)(0, 0, 0)
+    stats = (C.c_long * 6)(0, 0, 0, 0, 0, 0)
     a = 0
     for m in launches:
         args = [C.c_void_p(pilot[a:].ctypes.data), int(m), C.c_void_p(st.ctypes.data), C.c_double(w), C.c_float(Kp), C.c_float(Ki),
                 C.c_void_p(th[a:].ctypes.data)]
-        if which == "plltab_launch": args.append(stats)
+        if which in ("plltab_launch", "pllspec_launch"): args.append(stats)
         getattr(lib, which)(*args)
         a += m
     assert a == pilot.size
     assert stats[2] == 0, "a pick declared certain chose the wrong grid point"
+    if which == "pllspec_launch": return th, st, tuple(stats)
     return th, st, (stats[0], stats[1])
 
 
@@ -169,3 +170,66 @@ def test_table_pll_pick_certificate_randomised():
         cases, certain, wrong, uncertain = list(out)
         assert cases > 1_000_000 and wrong == 0, (cases, certain, wrong, uncertain)
         assert certain > 0.3 * cases, (cases, certain)
+
+
+# ---- speculative loop (k_pll_spec): 16-byte rows, predicted candidate added unconditionally, certified afterwards ------
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("G", [8, 16, 32])
+def test_spec_pll_host_build_reproduces_golden_nco(mode, G):
+    """The control flow of k_pll_spec (groups of G steps on the predicted candidate, float certificate per step, resume at
+    the first uncertain step with the other candidate, careful step otherwise), built for the host: the reference's trigArg
+    bit for bit, whatever the launch split and the group size."""
+    lib = _plltab_lib()
+    lib.pllspec_set_G(G)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mode%d_stereo.npz" % mode))
+    Fs = {0: 240e3, 1: 288e3, 2: 240e3, 3: 384e3}[mode]
+    pilot = np.ascontiguousarray(g["pilot"]); n = pilot.size
+    ref_th, ref_st, _ = _plltab_run(lib, pilot, Fs, [n], "pllref_launch")
+    for launches in ([n], [n // 2, n - n // 2], [1, 2, 3, 5, n - 11], [37] * (n // 37) + ([n % 37] if n % 37 else [])):
+        th, st, stats = _plltab_run(lib, pilot, Fs, launches, "pllspec_launch")
+        assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32)), launches[:4]
+        assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+
+
+def test_spec_pll_host_build_long_stream_and_flip_rate(dy4, orc):
+    """24 blocks in the bench's sub-chunks: bit-identical; after start-up a few percent of the steps flip to the other
+    candidate and essentially none needs a direct evaluation (that is the speed-up).  Then adversarial inputs."""
+    lib = _plltab_lib()
+    lib.pllspec_set_G(16)
+    nb = 24
+    iq = dy4.synth.make_stream(0, nb * 51200, 77)
+    pilot = np.ascontiguousarray(orc.pipeline(0, True, iq, want=("pilot",))["pilot"])
+    launches = [b * 5120 for b in (1, 2, 4, 8, 8, 1)]
+    ref_th, ref_st, _ = _plltab_run(lib, pilot, 240e3, launches, "pllref_launch")
+    th, st, (fast, direct, wrong, groups, flips, careful) = _plltab_run(lib, pilot, 240e3, launches, "pllspec_launch")
+    assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
+    assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+    n = pilot.size
+    assert direct <= 1536 + 0.002 * n, (fast, direct, careful)
+    assert flips < 0.08 * n, (flips, n)
+    assert careful < 0.02 * n, (careful, n)
+    print("spec loop: %d samples, %d groups of 16 (%.1f samples per group), flips %.2f%%, careful %.3f%%, direct %d"
+          % (n, groups, n / groups, 100.0 * flips / n, 100.0 * careful / n, direct))
+    rng = np.random.default_rng(5)
+    bad = pilot[:40960].copy()
+    bad[1000:1100] = 0.0; bad[5000:5050] = 1e-42; bad[9000:9400] *= -1.0
+    bad[20000:22000] = rng.normal(0, 0.03, 2000).astype(np.float32)
+    ref_th, ref_st, _ = _plltab_run(lib, bad, 240e3, [5120] * 8, "pllref_launch")
+    th, st, _ = _plltab_run(lib, bad, 240e3, [5120] * 8, "pllspec_launch")
+    assert np.array_equal(th.view(np.uint32), ref_th.view(np.uint32))
+    assert np.array_equal(st[:5].view(np.uint32), ref_st[:5].view(np.uint32))
+
+
+def test_spec_pll_certificates_randomised():
+    """Both certificates of the speculative loop (float: dy4_spec_fast_check; double: dy4_spec_check), probed within 8 float
+    ulps of every cell boundary of both candidates: nothing certified is wrong, the float certificate implies the double
+    one, and the double one leaves (almost) no gap at the boundaries."""
+    import ctypes as C
+    lib = _plltab_lib()
+    for Fs in (240e3, 288e3, 384e3):
+        w = 2 * 3.14159265358979323846 * float(np.float32(19e3) / np.float32(Fs))
+        out = (C.c_long * 5)(0, 0, 0, 0, 0)
+        lib.pllspec_fuzz(C.c_long(35000), C.c_ulonglong(int(Fs)), C.c_double(w), out)
+        probes, fc, dc, wrong, fc_not_dc = list(out)
+        assert probes > 2_000_000 and wrong == 0 and fc_not_dc == 0, list(out)
+        assert dc > fc > 0.1 * probes, list(out)
