@@ -69,7 +69,6 @@ struct dy4_pipeline {
     long long rds_blocks_since_drain = 0;
     cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
-    bool pll_spec = true;                            // ... with 16-byte rows and the speculative serial loop (k_pll_spec)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr, ev_prep1 = nullptr;
@@ -181,7 +180,6 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     int tab_max = (p->flags & DY4_FLAG_RDS) ? 1024 : 4096;
     if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
     p->pll_table = p->stereo && p->n_streams <= tab_max;
-    if (const char* e = std::getenv("DY4_PLL_SPEC")) p->pll_spec = atoi(e) != 0;
     const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 32 : 16) : 1);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
@@ -212,7 +210,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
             // padded: the serial loop copies whole chunks of 64 rows
-            if (p->pll_table) CU(cudaMalloc(&w.tab, (p->pll_spec ? 4 : 8) * bytes + 256 * sizeof(float4)));
+            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 512 * sizeof(float4)));
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
@@ -395,7 +393,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.spec = p->pll_spec ? 1 : 0; pa.tab_stride = (p->pll_spec ? 1 : 2) * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
     if (w.tab) {
         pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
         pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;
@@ -496,26 +494,31 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     // front(c+2), which is queued after back(c) (their last reader), and back(c) has waited for pll(c).
     CU(cudaEventRecord(p->ev_in, st));
     CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
+    const bool fresh_call = p->pll_fresh;              // no sample processed since create / reset: the streams start in this call
+    p->pll_fresh = false;
     SubChunk prev{};
     bool have_prev = false;
     int prev_b = 0, prev_i = 0;
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
         const int b = plan[i].first;
         SubChunk c = sub(b, plan[i].second, p->seq);
-        // Table-driven PLL (dy4_pll.cu).  Sub-chunk 0 starts from the exact carried state; at the start of a stream —
-        // and of every multi-sub-chunk call, where the signal may have jumped — its first samples go through the direct
-        // loop while the PLL (re)acquires lock.  Sub-chunk 1 is predicted from the exact state too (its prediction waits
-        // for the loop of sub-chunk 0, on the PLL stream); from sub-chunk 2 on the prediction carries its own state and
-        // runs with the FIR kernels on the main stream, beside the serial loop of the sub-chunk before.
-        c.pred_carry = i < 2 ? 0 : (i == 2 ? 1 : 2);
-        c.fresh = (i == 0 && (p->pll_fresh || plan.size() > 1)) ? 1536 : 0;       // DY4_TAB_EARLY (dy4_plltab.h)
-        p->pll_fresh = false;
-        const bool prep_on_pll = p->pll_table && i == 1;
+        // Table-driven PLL (dy4_pll.cu).  Sub-chunk 0 starts from the exact carried state; at the START of a stream its first
+        // samples go through the direct loop while the PLL acquires lock, and sub-chunk 1 is predicted from the exact state
+        // too (its prediction waits for the loop of sub-chunk 0, on the PLL stream); from sub-chunk 2 on the prediction
+        // carries its own state and runs with the FIR kernels on the main stream, beside the serial loop of the sub-chunk before.
+        // A CONTINUING stream (not the first call after create / reset) needs none of that: the loop of the previous call has
+        // finished, so sub-chunk 0 is predicted from the exact state on the main stream, sub-chunk 1 carries on from that
+        // prediction, and nothing but the serial loops is queued on the PLL stream.  Should the signal have jumped between two
+        // calls, the loop notices (its picks stop being certain) and finishes that launch with the direct loop's steps.
+        if (fresh_call) c.pred_carry = i < 2 ? 0 : (i == 2 ? 1 : 2);
+        else c.pred_carry = i == 0 ? 0 : (i == 1 ? 1 : 2);
+        c.fresh = (i == 0 && fresh_call) ? 1536 : 0;                              // DY4_TAB_EARLY (dy4_plltab.h)
+        const bool prep_on_pll = p->pll_table && i == 1 && fresh_call;
         if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
         // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
         if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
-        if (p->pll_table && i == 2) CU(cudaStreamWaitEvent(st, p->ev_prep1, 0));
+        if (p->pll_table && i == 2 && fresh_call) CU(cudaStreamWaitEvent(st, p->ev_prep1, 0));
         if (!prep_on_pll && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
@@ -633,11 +636,19 @@ extern "C" int dy4_pipeline_reset(dy4_pipeline_t* p)
     return init_state(p, nullptr);
 }
 
+extern "C" int dy4_debug_pll_stats(long long* out4);
+
 extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
 {
     if (!p) return DY4_OK;
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
+    if (p->pll_table && std::getenv("DY4_PLL_STATS")) {                       // development counters of the serial PLL loop
+        long long v[4];
+        if (dy4_debug_pll_stats(v) == 0 && v[1] > 0)
+            fprintf(stderr, "dy4 pll stats: rows %lld groups %lld (%.2f rows/group) direct steps %lld (%.3f%%) %lld\n", v[0], v[1], (double)v[0] / (double)v[1],
+                    v[2], 100.0 * (double)v[2] / (double)std::max(1LL, v[0]), v[3]);
+    }
     for (auto& r : p->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : p->pool) cudaEventDestroy(e);
     cudaFree(p->d_rf_taps); cudaFree(p->d_taps_poly);

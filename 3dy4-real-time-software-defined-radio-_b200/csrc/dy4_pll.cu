@@ -187,7 +187,7 @@ constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop f
 // so that prediction and table of sub-chunk c+1 do not wait for the serial loop of sub-chunk c (dy4_pipeline.cu).
 // The loop locks to the pilot modulo 2*pi, and after a loss of lock the predictor may settle a whole number of turns
 // away from the true phaseEst — a table built there never matches.  So every serial launch reports how many turns its
-// prediction was off (`need`, k_pll_tab), and with carry == 2 the launch two later shifts its start by that much.
+// prediction was off (`need`, k_pll_sel), and with carry == 2 the launch two later shifts its start by that much.
 __global__ void __launch_bounds__(128)
 k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __restrict__ state, const double* __restrict__ pred_in,
               double* __restrict__ pred_out, const double* __restrict__ need, int carry, double* __restrict__ th_hat, long long wide_stride,
@@ -232,38 +232,6 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
     }
 }
 
-// 2. one table row per sample: the exact errorD of the next step for the two float grid points the prediction lies between
-__global__ void __launch_bounds__(128)
-k_pll_table(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
-            const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
-{
-    const int s = blockIdx.x;
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double T0 = pred_out[8 * s + 3];                          // sample counter at the start of this launch (k_pll_predict)
-    const float* x = in + (long long)s * in_stride;
-    dy4_tabrow_t r;
-    dy4_tab_make_row(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
-                     k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, c.Kp, c.Ki, &r);
-    float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
-    o[0] = make_float4(r.t, r.hu, r.hm, 0.0f);
-    o[1] = make_float4(r.a_lo, r.a_hi, r.b_lo, r.b_hi);
-}
-
-// 3. the serial loop.  One lane per stream, `lanes` streams per warp (few: a direct evaluation stalls the whole warp).
-// Measured on a B200 (tools/ubench_pick.cu): a dependent FADD 4.9 cycles, FSETP -> FSEL 8.9 (both at half issue rate) —
-// and ~55 cycles for every BRANCH a lone warp executes.  So:
-//  * table rows arrive through a per-lane shared-memory ring, ONE bulk asynchronous copy (cp.async.bulk, completing on
-//    the lane's own mbarrier) per super-group of 64 samples, three super-groups ahead: no waiting on global memory and
-//    no issue slots spent on it;
-//  * a super-group is straight-line code: per sample two speculative loop-filter updates (float adds of the table's
-//    precomputed products), ONE compare of phaseEst with the row's threshold, two selects, and a three-instruction
-//    guard — with ONE branch per super-group on "every pick was certain"; if not, the super-group is redone step by
-//    step from its saved state (tab_redo, out of line).
-// Output: phaseEst after every sample (float); trigArg and the NCO follow from it elementwise in k_nco_phase.
-constexpr int TAB_LANES = 4;                       // most streams per warp
-constexpr int TAB_ROW_Q = 2;                       // 16-byte words per row
-// template parameters of k_pll_tab: TAB_SG samples per super-group (64; 32 / 128 through the A/B knob DY4_PLL_SG), TAB_SLOTS ring slots
 constexpr int TAB_EARLY = DY4_TAB_EARLY;
 
 __device__ __forceinline__ unsigned tab_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -284,45 +252,6 @@ __device__ __forceinline__ bool tab_mbar_try(unsigned long long* bar, unsigned p
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(tab_smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
-}
-
-// state_k -> state_{k+1} with no branch.  q0 = (t, u/2, hm, -), q1 = (a_lo, a_hi, b_lo, b_hi).
-// `ok` stays true while every pick was certain; if not, integ/phase are garbage and the caller redoes the super-group.
-// On the serial chain: one compare of phaseEst with the threshold and one select (8.9 cycles, tools/ubench_pick.cu);
-// the two speculative updates and the three-instruction guard run beside it.
-__device__ __forceinline__ void tab_step_spec(const float4 q0, const float4 q1, float& integ, float& phase, bool& ok)
-{
-    const float i_lo = __fadd_rn(integ, q1.x), i_hi = __fadd_rn(integ, q1.y);
-    const float p_lo = __fadd_rn(phase, __fadd_rn(q1.z, i_lo));
-    const float p_hi = __fadd_rn(phase, __fadd_rn(q1.w, i_hi));
-    const bool up = phase > q0.x;
-    const float v = __fadd_rn(fabsf(__fadd_rn(phase, -q0.x)), -q0.y);
-    ok = ok && (fabsf(v) < q0.z);
-    integ = up ? i_hi : i_lo;
-    phase = up ? p_hi : p_lo;
-}
-
-// A super-group again, carefully: a pick where it is certain, else that step directly (dy4_pllmath.h), as k_pll does.
-// Out of line and looping: it runs for a fraction of a percent of the super-groups once the loop is in lock.
-__device__ __noinline__ int tab_redo(const float4* src, const float* x_next, float* y, double T0, int k, int count, double w, float Kp, float Ki,
-                                     float* integ_io, float* phase_io)
-{
-    float integ = *integ_io, phase = *phase_io;
-    int n_direct = 0;
-#pragma unroll 1
-    for (int r = 0; r < count; r++) {
-        const float4 q0 = src[2 * r], q1 = src[2 * r + 1];
-        y[r] = phase;
-        int up;
-        if (dy4_tab_pick(phase, q0.x, q0.y, q0.z, &up))
-            dy4_pll_filter_ab(up ? q1.y : q1.x, up ? q1.w : q1.z, &integ, &phase);
-        else {
-            dy4_pll_filter(dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + r + 1), phase), x_next[r]), Kp, Ki, &integ, &phase);
-            n_direct++;
-        }
-    }
-    *integ_io = integ; *phase_io = phase;
-    return n_direct;                                          // steps that had to be evaluated directly
 }
 
 // Samples k0+1 .. k1 through the steps of the direct loop (pll_step_fast: straight-line groups of four whose independent
@@ -360,152 +289,22 @@ __device__ __noinline__ void tab_direct_span(const float* __restrict__ x, float*
     *rp = r; *op = o;
 }
 
-template <bool FENCE, int TAB_SG, int TAB_SLOTS>
-__global__ void __launch_bounds__(32)
-k_pll_tab(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
-          float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
-          const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int n, int n_streams, PllConst c, int lanes)
-{
-    constexpr int TAB_SG_BYTES = TAB_SG * TAB_ROW_Q * 16;
-    constexpr int TAB_LANE_Q = TAB_SG * TAB_ROW_Q + 1;   // lane stride in 16-byte words: +1 spreads the lanes over the banks
-    __shared__ __align__(16) float4 ring[TAB_SLOTS * TAB_LANES * TAB_LANE_Q];
-    __shared__ __align__(8) unsigned long long bars[TAB_SLOTS * TAB_LANES];
-    const int lane = threadIdx.x;
-    const int s = blockIdx.x * lanes + lane;
-    if (lane >= lanes || s >= n_streams || n <= 0) return;
-    float* st = state + (long long)s * 8;
-    float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
-    const double T0 = (double)st[4];
-    nco0[s] = st[5];                                 // nco_state opens this launch's NCO row (filter.cpp:184)
-    tstart[s] = st[4];                               // k_nco_phase needs the sample counter this launch started from
-    const float* x = in + (long long)s * in_stride;
-    const float4* rows = tab + (long long)s * tab_stride;
-    float* y = phase_out + (long long)s * phase_stride;
-    const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
-    // Start of a stream: while the loop acquires lock the detector crosses +-pi, where one ulp decides the sign of a
-    // 2*pi jump — nothing predicts that, so those samples are evaluated directly (as k_pll does) and the table starts
-    // after them.  k_pll_table leaves their rows empty.
-    int kd = 0;
-    if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
-    // A pick certifies "trigArg = RN_f(RN_d(w*T) + phaseEst) is this grid point" for the sample counter T the TABLE was
-    // built with: it must be this stream's own counter.  It always is when the launches are ordered as dy4_pipeline.cu
-    // orders them; if it ever is not, nothing of the table is used.
-    if (pred[8 * s + 3] != T0) kd = n_pick;
-    const int n_sg = (n_pick - kd) / TAB_SG;         // whole super-groups after the direct part
-#pragma unroll
-    for (int i = 0; i < TAB_SLOTS; i++) tab_mbar_init(&bars[i * TAB_LANES + lane]);   // each lane owns its barriers: no CTA-wide sync
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    auto issue = [&](int i) {                        // super-group i -> slot i % TAB_SLOTS
-        if (i < n_sg) {
-            const int slot = i % TAB_SLOTS;
-            tab_bulk_load<TAB_SG_BYTES>(ring + (slot * TAB_LANES + lane) * TAB_LANE_Q, rows + TAB_ROW_Q * ((long long)kd + (long long)i * TAB_SG), &bars[slot * TAB_LANES + lane]);
-        }
-    };
-    for (int i = 0; i < TAB_SLOTS - 1; i++) issue(i);
-    // first sample: the carried feedbackI/Q are whatever the caller holds, so the detector is libm's
-    if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
-    else {
-        // direct part (tab_direct_span), samples 0 .. kd; it ends holding state_kd
-        PllRegs r = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
-        dy4_nco_t o;
-        o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
-        pll_advance<1, false>(detector_libm(x[0], r.fbI, r.fbQ), r, c, o, n > 1 && x[1] < 0.0f);
-        tab_direct_span(x, y, n, 0, kd, &r, &o, c.w, c.Kp, c.Ki);
-        integ = r.integ; phase = r.phase;
-    }
-    int directs = 0, sg_done = n_sg;
-    bool bailed = false;
-#pragma unroll 1
-    for (int i = 0; i < n_sg; i++) {
-        const int slot = i % TAB_SLOTS;
-        // slot (i-1) % TAB_SLOTS was read in the previous trip: order those reads before the async write that refills it.
-        // (Every value read from it has been consumed by then — `ok` depends on all of them — so DY4_PLL_FENCE=0 drops
-        // the fence for an A/B measurement; the default keeps it.)
-        if (FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(i + TAB_SLOTS - 1);
-        unsigned long long* bar = &bars[slot * TAB_LANES + lane];
-        const unsigned parity = (unsigned)((i / TAB_SLOTS) & 1);
-        if (!tab_mbar_try(bar, parity)) { while (!tab_mbar_try(bar, parity)) { } }     // super-group i has landed (normally long ago)
-        const float4* src = ring + (slot * TAB_LANES + lane) * TAB_LANE_Q;
-        const int k = kd + i * TAB_SG;
-        float si = integ, sp = phase;
-        bool ok = true;
-#pragma unroll
-        for (int r = 0; r < TAB_SG; r += 4) {
-            float ph[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                ph[q] = sp;
-                tab_step_spec(src[2 * (r + q)], src[2 * (r + q) + 1], si, sp, ok);
-            }
-            *reinterpret_cast<float4*>(y + k + r) = make_float4(ph[0], ph[1], ph[2], ph[3]);   // (rewritten by tab_redo if a pick was not certain)
-        }
-        if (!ok) {
-            si = integ; sp = phase;
-            directs += tab_redo(src, x + k + 1, y + k, T0, k, TAB_SG, c.w, c.Kp, c.Ki, &si, &sp);
-            // A stream whose loop is not in lock (no pilot, noise) misses all the time, and a direct evaluation inside the
-            // redo costs four times a step of the direct loop: once more than a quarter of the samples so far had to be
-            // evaluated directly, the rest of this launch goes through the direct loop.
-            if (i >= 2 && 4 * directs > (i + 1) * TAB_SG) { integ = si; phase = sp; sg_done = i + 1; bailed = true; break; }
-        }
-        integ = si; phase = sp;
-    }
-    {
-        const int k = kd + sg_done * TAB_SG;
-        if (bailed && k < n_pick) {                              // the rest directly, from state_k
-            const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
-            dy4_nco_t o;
-            dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
-            PllRegs r = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
-            tab_direct_span(x, y, n, k, n_pick, &r, &o, c.w, c.Kp, c.Ki);
-            integ = r.integ; phase = r.phase;
-        } else if (k < n_pick) {
-            // tail (fewer than TAB_SG samples): its rows are first copied into ring slot 0 with all loads in flight at once —
-            // read one by one from global memory inside the step loop they would cost a DRAM latency per sample
-            float4* dst = ring + lane * TAB_LANE_Q;
-            const float4* src = rows + TAB_ROW_Q * (long long)k;
-            const int nq = TAB_ROW_Q * (n_pick - k);
-            for (int q = 0; q < nq; q += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = __ldg(src + min(q + j, nq - 1));
-#pragma unroll
-                for (int j = 0; j < 8; j++) if (q + j < nq) dst[q + j] = v[j];
-            }
-            tab_redo(dst, x + k + 1, y + k, T0, k, n_pick - k, c.w, c.Kp, c.Ki, &integ, &phase);
-        }
-    }
-    // last sample of the launch: trigArg and feedbackI/Q directly (they are carried to the next launch)
-    y[n - 1] = phase;
-    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
-    dy4_nco_t o;
-    dy4_sincos_nco_v((double)th, 0, &o, 0);
-    st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
-    st[4] = (float)dy4_pll_count(T0, n);
-    st[5] = nco_value(th, c.ncoScale, c.phaseAdjust);          // nco_state for the next launch (filter.cpp:218-219)
-    // how many whole turns the prediction of this launch ended away from the true phaseEst (see k_pll_predict)
-    need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
-}
-
 // ====================================================================================================================
-// Speculative serial loop (dy4_plltab.h §2b): 16-byte rows (predicted candidate, other candidate, double threshold).
-// One WARP per stream.  The dependent chain of a step is three float adds of the predicted candidate's products — no
-// compare, no select: the predictor names the right candidate ~96 % of the time.  All 32 lanes run the same chain;
-// G steps are straight-line code, every step parks (integ, phaseEst) in shared memory, and afterwards lane i certifies
-// step i (dy4_spec_check, in double, off the chain).  A ballot finds the first step that is not certainly the predicted
-// candidate: the loop resumes THERE, from the parked state, with that step forced to the other candidate (certified the
-// same way); if neither candidate is certain the step is evaluated directly (dy4_pllmath.h), so the result is the
-// reference's by construction, as in k_pll_tab.  Rows arrive by one bulk asynchronous copy per 64 samples into a ring
-// of 4 slots; the lanes turn each landed chunk into the chain's operands (Ki*e, Kp*e of both candidates) in one pass.
+// 16-byte rows (dy4_plltab.h 2b) and the serial loop on them, k_pll_sel.
 // ====================================================================================================================
 constexpr int SPEC_SG = 128;                         // rows per bulk copy
 constexpr int SPEC_SLOTS = 4;
 constexpr int SPEC_R = SPEC_SG * SPEC_SLOTS;         // ring size in rows
 
+// The table kernel for k_pll_sel: one CHAIN-READY 32-byte row per sample, so the serial warp spends nothing on preparing operands:
+//   (Ki e_lo, Ki e_hi, Kp e_lo, Kp e_hi)   the products of filter.cpp:207,210 for the lower / upper candidate of trigArg
+//   (t, tc_lo, tc_hi, hm)                  float threshold between the two in the phaseEst domain, centres of the two cells and the
+//                                          certified half-width of a cell (dy4_spec_fast_row)
+// (A 16-byte row (t, hm, e_lo, e_hi) with the four products formed inside the loop was measured too: the four extra FMUL per
+// step cost the lone warp 39.8 instead of 26.5 ns per sample — issue slots, not bytes, are what the serial loop is short of.)
 __global__ void __launch_bounds__(128)
-k_pll_table16(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
-              const double* __restrict__ th_hat, long long wide_stride, dy4_row16_t* __restrict__ tab, long long tab_stride, int n, PllConst c)
+k_pll_table_ops(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
+                const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
 {
     const int s = blockIdx.x;
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
@@ -515,84 +314,49 @@ k_pll_table16(const float* __restrict__ in, long long in_stride, const double* _
     dy4_row16_t r;
     dy4_tab_make_row16(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
                        k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r, nullptr, nullptr);
-    float4 v;
-    v.x = __int_as_float(__double2loint(r.t)); v.y = __int_as_float(__double2hiint(r.t)); v.z = r.e_p; v.w = r.e_o;
-    reinterpret_cast<float4*>(tab + (long long)s * tab_stride)[k] = v;
+    const bool ph = (dy4_d2u_bits(r.t) & 1ull) != 0;                // the predicted candidate is the upper one
+    const float e_lo = ph ? r.e_o : r.e_p, e_hi = ph ? r.e_p : r.e_o;
+    float tc_p, hm, tc_o;
+    dy4_spec_fast_row(r.t, &tc_p, &hm, &tc_o);
+    float4* o = tab + (long long)s * tab_stride + 2 * (long long)k;
+    o[0] = make_float4(__fmul_rn(c.Ki, e_lo), __fmul_rn(c.Ki, e_hi), __fmul_rn(c.Kp, e_lo), __fmul_rn(c.Kp, e_hi));
+    o[1] = make_float4(__double2float_rn(r.t), ph ? tc_o : tc_p, ph ? tc_p : tc_o, hm);
 }
 
-// One step at row k, carefully: dy4_spec_check (double) for the predicted, then the other candidate; if neither is
-// certain the step is evaluated directly (filter.cpp:192-214 through dy4_pllmath.h).  Returns (integ, phase); *direct = 1
-// if it came to that.  Out of line: it runs where the float certificate of the loop is too coarse (the first ~0.1 s of
-// a stream), at binade edges of trigArg, and where the loop is not in lock.
-__device__ __noinline__ float2 spec_slow_step(double t, float e_p, float e_o, const float* __restrict__ x, int n, int k, double T0, double w, float Kp, float Ki,
-                                              float integ, float phase, int* direct)
+__device__ int g_spec_stats[4];      // rows, groups, direct steps, - (development counters, DY4_PLL_STATS=1)
+
+__device__ __forceinline__ float4 spec_lds128(unsigned a) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+
+// one step evaluated directly from state (integ, phase) after sample k: filter.cpp:192-214 through dy4_pllmath.h
+__device__ __noinline__ float2 spec_direct_step(const float* __restrict__ x, int n, int k, double T0, double w, float Kp, float Ki, float integ, float phase)
 {
-    float eD;
-    *direct = 0;
-    if (dy4_spec_check(phase, t, 0)) eD = e_p;
-    else if (dy4_spec_check(phase, t, 1)) eD = e_o;
-    else {
-        eD = dy4_next_errorD((double)dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase), x[min(k + 1, n - 1)]);
-        *direct = 1;
-    }
-    dy4_pll_filter(eD, Kp, Ki, &integ, &phase);
+    const float th = dy4_pll_trigarg(w, dy4_pll_count(T0, k + 1), phase);
+    dy4_pll_filter(dy4_next_errorD((double)th, x[min(k + 1, n - 1)]), Kp, Ki, &integ, &phase);
     return make_float2(integ, phase);
 }
 
-__device__ int g_spec_stats[4];      // rows, groups run, flips, direct steps (development counters, DY4_PLL_STATS=1)
-
-// Per-warp state of the speculative loop.  `r`: first row not yet run (rows before it are run, the last group of them
-// possibly not yet certified); (integ, phase): state before row r.  The group [pr, pr + pn) is run but not certified.
-struct SpecLoop {
-    int r, forced;                   // forced: row r must take the OTHER candidate (it was certainly not the predicted one)
-    int pr, pn, pforced;             // pending group: first row, rows, whether its first step took the other candidate
-    float integ, phase;
-};
-
-// One trip: certify the pending group (its states are in cap_prev) while the chain of the next group runs from the
-// state the pending group ended in.  ab: the chain's operands (Ki e, Kp e) of rows r .. r+G-1, already in registers;
-// abn receives those of rows r+G .. r+2G-1 for the next trip.  Returns the number of certain steps of the pending group
-// (== L.pn: all of them; the caller then makes the new group the pending one).
-template <int G>
-__device__ __forceinline__ int spec_trip(const SpecLoop& L, const float4* __restrict__ conv, const float4* __restrict__ chk,
-                                         const float2* __restrict__ cap_prev, float2* __restrict__ cap_cur, const float2 (&ab)[G], float2 (&abn)[G],
-                                         float* __restrict__ y_prev, int lane, float& si, float& sp)
-{
-    // certificate of the pending group, lane i for step i (float form; dy4_spec_fast_row)
-    const float myph = cap_prev[min(lane, G)].y;
-    const float4 q = chk[(L.pr + lane) & (SPEC_R - 1)];
-    const float tc = (lane == 0 && L.pforced) ? q.z : q.x;
-    const bool good = (lane >= L.pn) | (dy4_spec_fast_check(myph, tc, q.y) != 0);
-    // operands of the group after this one (optimistic: this group will be found certain)
-    const float4* cvn = conv + ((L.r + G) & (SPEC_R - 1));
-#pragma unroll
-    for (int i = 0; i < G; i++) abn[i] = *reinterpret_cast<const float2*>(cvn + i);
-    // the chain: three dependent float adds per step (filter.cpp:207,210), state parked before every step
-    si = L.integ; sp = L.phase;
-#pragma unroll
-    for (int i = 0; i < G; i++) {
-        cap_cur[i] = make_float2(si, sp);
-        si = __fadd_rn(si, ab[i].x);
-        sp = __fadd_rn(sp, __fadd_rn(ab[i].y, si));
-    }
-    cap_cur[G] = make_float2(si, sp);
-    const unsigned bad = ~__ballot_sync(0xffffffffu, good);
-    const int j = bad ? __ffs(bad) - 1 : L.pn;
-    if (lane < j) y_prev[lane] = myph;                 // phaseEst after each certain sample (k_nco_phase turns it into the NCO row)
-    return j;
-}
-
-template <int G>
+// ====================================================================================================================
+// k_pll_sel: the serial loop.  Both candidates carried, the pick on the chain, its certificate OFF it.
+// One warp per stream, all lanes run the same chain.  Per step: both candidates' loop-filter updates (six float adds, the
+// table's products as operands), ONE compare of phaseEst with the row's float threshold and two selects — nothing else
+// sits between two steps.  Whether that pick was CERTAIN (phaseEst at least the rounding budget away from the threshold
+// and from the far ends of the two cells, dy4_spec_fast_check) is decided afterwards: lane i parks phaseEst of "before
+// step i" in a register on the way (one LOP3), and after B steps every lane takes the certificate of its own step at
+// once — one vote for the group.  An uncertain step (the first ~0.1 s of a stream, where the float threshold's half-ulp
+// is a visible fraction of the cell; binade edges; a loop out of lock) is evaluated directly (dy4_pllmath.h) and the loop
+// resumes behind it: the result is the reference's by construction.
+// Rows arrive chain-ready (k_pll_table_ops) by one bulk asynchronous copy per 128 samples straight into the ring the
+// chain reads: the warp neither waits on global memory nor spends issue slots on it.
+// ====================================================================================================================
+template <int B>
 __global__ void __launch_bounds__(32)
-k_pll_spec(const float* __restrict__ in, long long in_stride, const dy4_row16_t* __restrict__ tab, long long tab_stride,
-           float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
-           const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int* __restrict__ stats, int n, int n_streams, PllConst c)
+k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
+          float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
+          const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int* __restrict__ stats, int n, int n_streams, PllConst c)
 {
-    static_assert(G >= 4 && G <= 32 && 3 * G <= SPEC_SG, "one lane certifies one step; three groups must fit a chunk");
-    __shared__ __align__(16) dy4_row16_t raw[SPEC_R];
-    __shared__ __align__(16) float4 conv[SPEC_R + 32];            // (Ki e_p, Kp e_p, Ki e_o, Kp e_o); the last 32 mirror the first 32
-    __shared__ __align__(16) float4 chk[SPEC_R];                  // (tc_p, hm, tc_o, -), dy4_spec_fast_row
-    __shared__ __align__(8) float2 cap0[G + 1], cap1[G + 1];      // (integ, phaseEst) before every step of a group, double-buffered
+    static_assert(B <= 32 && 2 * B <= SPEC_SG, "lane i certifies step i of a group");
+    constexpr int RQ = 2;                                         // 16-byte words per row
+    __shared__ __align__(128) float4 ring[RQ * (SPEC_R + 32)];    // the last 32 rows mirror the first 32 (a group may straddle the end)
     __shared__ __align__(8) unsigned long long bars[SPEC_SLOTS];
     const int lane = threadIdx.x;
     const int s = blockIdx.x;
@@ -602,17 +366,25 @@ k_pll_spec(const float* __restrict__ in, long long in_stride, const dy4_row16_t*
     const double T0 = (double)st[4];
     const float nco_carry = st[5];
     const float* x = in + (long long)s * in_stride;
-    const dy4_row16_t* rows = tab + (long long)s * tab_stride;
+    const float4* rows = tab + (long long)s * tab_stride;
     float* y = phase_out + (long long)s * phase_stride;
     const int n_pick = n - 1;                        // steps k = 0 .. n-2 go through the table (row k, input x[k+1])
-    int kd = 0;                                      // leading samples evaluated directly (see k_pll_tab)
+    int kd = 0;                                      // leading samples evaluated directly (the direct loop's steps)
     if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
     if (pred[8 * s + 3] != T0) kd = n_pick;          // a table built for another sample counter: nothing of it is used
     const int n_rows = n_pick - kd;
     const int n_chunks = (n_rows + SPEC_SG - 1) / SPEC_SG;
-    auto issue = [&](int cc) {                       // chunk cc -> slot cc % SPEC_SLOTS (lane 0)
+    auto issue = [&](int cc) {                       // chunk cc -> slot cc % SPEC_SLOTS; slot 0 also refreshes the mirror (lane 0)
         const int slot = cc % SPEC_SLOTS;
-        tab_bulk_load<SPEC_SG * 16>(raw + slot * SPEC_SG, rows + (long long)kd + (long long)cc * SPEC_SG, &bars[slot]);
+        const float4* src = rows + RQ * ((long long)kd + (long long)cc * SPEC_SG);
+        constexpr int CB = SPEC_SG * 16 * RQ, MB = 32 * 16 * RQ;
+        if (slot == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tab_smem_u32(&bars[0])), "n"(CB + MB) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tab_smem_u32(ring)), "l"(src), "n"(CB), "r"(tab_smem_u32(&bars[0])) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tab_smem_u32(ring + RQ * SPEC_R)), "l"(src), "n"(MB), "r"(tab_smem_u32(&bars[0])) : "memory");
+        } else tab_bulk_load<CB>(ring + RQ * slot * SPEC_SG, src, &bars[slot]);
     };
     if (lane == 0) {
 #pragma unroll
@@ -632,115 +404,83 @@ k_pll_spec(const float* __restrict__ in, long long in_stride, const dy4_row16_t*
         tab_direct_span(x, y, n, 0, kd, &rg, &o, c.w, c.Kp, c.Ki);
         integ = rg.integ; phase = rg.phase;
     }
-    int conv_chunks = 0, directs = 0, trips = 0, flips = 0;
+    int ready = 0;                                    // chunks that have landed (and been waited for)
+    int directs = 0, groups = 0;
     bool bailed = false;
-    // rows up to `upto` (exclusive) must be in conv / chk: turn the chunks that have landed into the loop's operands
-    // and keep two more chunks in flight.  Chunk cc-2 is consumed by then: the oldest row the loop can come back to is
-    // the pending group's first, r - G, and conversion of chunk cc is asked for when r + 2G > cc*SG, i.e. r - G > (cc-1)*SG.
-    auto cover = [&](int upto) {
-        while (conv_chunks < n_chunks && conv_chunks * SPEC_SG < upto) {
-            const int cc = conv_chunks, slot = cc % SPEC_SLOTS;
+    unsigned sm_ring = tab_smem_u32(ring);
+    asm volatile("mov.b32 %0, %0;" : "+r"(sm_ring));  // opaque: keeps ptxas from re-deriving the shared window address in the loop
+    unsigned mask[B];                                 // lane i: all ones in mask[i]
+#pragma unroll
+    for (int i = 0; i < B; i++) { const unsigned m = lane == i ? 0xffffffffu : 0u; asm volatile("mov.b32 %0, %1;" : "=r"(mask[i]) : "r"(m)); }
+    int r = 0;
+    float gi = integ, gp = phase;
+    float* yp = y + kd + lane;                        // phaseEst row: lane i writes the sample of step i
+#pragma unroll 1
+    while (r < n_rows) {
+        // rows r .. r+B-1 must have landed.  The first time chunk cc is needed the loop is still inside chunk cc-1 (B < SG), so
+        // chunk cc-2 is done with: its slot takes chunk cc+2.
+        while (ready < n_chunks && ready * SPEC_SG < r + B) {
+            const int cc = ready, slot = cc % SPEC_SLOTS;
             const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
             while (!tab_mbar_try(&bars[slot], parity)) { }
-#pragma unroll
-            for (int p = 0; p < SPEC_SG / 32; p++) {
-                const int idx = slot * SPEC_SG + p * 32 + lane;
-                const dy4_row16_t row = raw[idx];
-                const float4 q = make_float4(__fmul_rn(c.Ki, row.e_p), __fmul_rn(c.Kp, row.e_p), __fmul_rn(c.Ki, row.e_o), __fmul_rn(c.Kp, row.e_o));
-                conv[idx] = q;
-                if (idx < 32) conv[SPEC_R + idx] = q;
-                float4 v;
-                dy4_spec_fast_row(row.t, &v.x, &v.y, &v.z);
-                v.w = 0.0f;
-                chk[idx] = v;
-            }
-            conv_chunks++;
-            __syncwarp();
+            ready++;
             if (cc >= 2 && cc + 2 < n_chunks && lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(cc + 2);
             }
         }
-    };
-    SpecLoop L;
-    L.r = 0; L.forced = 0; L.pr = 0; L.pn = 0; L.pforced = 0; L.integ = integ; L.phase = phase;
-    float2 ab0[G], ab1[G];
-    // (re)start at row L.r from (L.integ, L.phase): nothing pending, operands of rows r .. r+G-1 into ab0
-    auto restart = [&]() {
-        cover(L.r + 2 * G);
-        L.pn = 0; L.pr = L.r; L.pforced = 0;
-        const float4* cv = conv + (L.r & (SPEC_R - 1));
-        const float4 q0 = cv[0];
-        ab0[0] = L.forced ? make_float2(q0.z, q0.w) : make_float2(q0.x, q0.y);
+        const int nv = min(B, n_rows - r);
+        const unsigned base = sm_ring + 16u * RQ * (unsigned)(r & (SPEC_R - 1));
+        const float4 q = spec_lds128(base + 32u * (unsigned)lane + 16u);      // (t, tc_lo, tc_hi, hm) of this lane's step
+        unsigned cph = 0u, cig = 0u;
+        float i0 = gi, p0 = gp;
 #pragma unroll
-        for (int i = 1; i < G; i++) ab0[i] = *reinterpret_cast<const float2*>(cv + i);
-    };
-    // the pending group failed at its step j (< L.pn): resume there
-    auto recover = [&](int j, const float2* cap_prev) {
-        const int k = L.pr + j;                                  // row that is not certainly the predicted candidate
-        const float2 sj = cap_prev[j];
-        if (j == 0 && L.pforced) {                               // ... and not certainly the other one either (float certificate)
-            const dy4_row16_t row = raw[k & (SPEC_R - 1)];
-            int direct;
-            const float2 nx = spec_slow_step(row.t, row.e_p, row.e_o, x, n, kd + k, T0, c.w, c.Kp, c.Ki, sj.x, sj.y, &direct);
-            if (lane == 0) y[kd + k] = sj.y;
-            L.integ = nx.x; L.phase = nx.y; L.r = k + 1; L.forced = 0;
-            directs += direct;
-        } else {
-            // a row with no usable threshold (NaN) goes straight to the careful step
-            L.integ = sj.x; L.phase = sj.y; L.r = k; L.forced = 1;
-            flips++;
+        for (int i = 0; i < B; i++) {
+            const float4 A = spec_lds128(base + 32u * i);                                          // (a_lo, a_hi, b_lo, b_hi)
+            float T;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(T) : "r"(base + 32u * i + 16u));
+            cph |= __float_as_uint(p0) & mask[i];
+            cig |= __float_as_uint(i0) & mask[i];
+            const float i_lo = __fadd_rn(i0, A.x), i_hi = __fadd_rn(i0, A.y);                          // filter.cpp:207, both candidates
+            const float p_lo = __fadd_rn(p0, __fadd_rn(A.z, i_lo)), p_hi = __fadd_rn(p0, __fadd_rn(A.w, i_hi));     // :210
+            const bool up = p0 > T;                                                                    // trigArg rounds to the upper candidate
+            i0 = up ? i_hi : i_lo;
+            p0 = up ? p_hi : p_lo;
         }
-    };
-    restart();
-#pragma unroll 1
-    while (L.r < n_rows || L.pn > 0) {
-        float si, sp;
-        int j;
-        // ---- even trip: pending states in cap1, this group's into cap0, operands ab0 -> prefetch ab1
-        cover(L.r + 2 * G);
-        j = spec_trip<G>(L, conv, chk, cap1, cap0, ab0, ab1, y + kd + L.pr, lane, si, sp);
-        trips++;
-        if (j < L.pn) {
-            recover(j, cap1);
-            if (L.r >= 2 * SPEC_SG && 4 * directs > L.r) { bailed = true; L.pn = 0; break; }
-            restart();
+        const float myph = __uint_as_float(cph);
+        const float tc = myph > q.x ? q.z : q.y, hm = q.w;
+        const unsigned bad = ~__ballot_sync(0xffffffffu, (lane >= nv) | (dy4_spec_fast_check(myph, tc, hm) != 0));
+        groups++;
+        if (__builtin_expect(bad == 0u && nv == B, 1)) {                       // every pick certain: straight on
+            *yp = myph;
+            yp += B; r += B; gi = i0; gp = p0;
             continue;
         }
-        {
-            const int nv = max(0, min(G, n_rows - L.r));
-            L.pr = L.r; L.pn = nv; L.pforced = L.forced; L.forced = 0;
-            if (nv < G) { const float2 e = cap0[nv]; si = e.x; sp = e.y; }   // the launch's last rows: state after the last valid one
-            L.r += nv; L.integ = si; L.phase = sp;
-        }
-        // ---- odd trip: roles of the buffers swapped
-        cover(L.r + 2 * G);
-        j = spec_trip<G>(L, conv, chk, cap0, cap1, ab1, ab0, y + kd + L.pr, lane, si, sp);
-        trips++;
-        if (j < L.pn) {
-            recover(j, cap0);
-            if (L.r >= 2 * SPEC_SG && 4 * directs > L.r) { bailed = true; L.pn = 0; break; }
-            restart();
-            continue;
-        }
-        {
-            const int nv = max(0, min(G, n_rows - L.r));
-            L.pr = L.r; L.pn = nv; L.pforced = L.forced; L.forced = 0;
-            if (nv < G) { const float2 e = cap1[nv]; si = e.x; sp = e.y; }
-            L.r += nv; L.integ = si; L.phase = sp;
-        }
+        const int j = bad ? __ffs(bad) - 1 : nv;                               // steps 0 .. j-1 are certain
+        if (lane < j) *yp = myph;
+        const float pj = __uint_as_float(__shfl_sync(0xffffffffu, cph, j & 31)), ij = __uint_as_float(__shfl_sync(0xffffffffu, cig, j & 31));
+        if (j == nv) { yp += j; r += j; gi = (j == B) ? i0 : ij; gp = (j == B) ? p0 : pj; continue; }      // the launch's last rows (nv < B)
+        // step j directly, then on from behind it
+        const int k = r + j;
+        const float2 nx = spec_direct_step(x, n, kd + k, T0, c.w, c.Kp, c.Ki, ij, pj);
+        yp += j;
+        if (lane == 0) *yp = pj;
+        gi = nx.x; gp = nx.y; r = k + 1; yp += 1;
+        directs++;
+        // a stream whose loop is not in lock lands here all the time: hand the rest of the launch to the direct loop
+        if (r >= 2 * SPEC_SG && 4 * directs > r) { bailed = true; break; }
     }
-    integ = L.integ; phase = L.phase;
+    integ = gi; phase = gp;
     // no bulk copy may be in flight when the CTA retires: wait for every chunk that was issued and not consumed
     {
-        const int issued = min(n_chunks, max(SPEC_SLOTS, conv_chunks + 2));
-        for (int cc = conv_chunks; cc < issued; cc++) {
+        const int issued = min(n_chunks, max(SPEC_SLOTS, ready + 2));
+        for (int cc = ready; cc < issued; cc++) {
             const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
             while (!tab_mbar_try(&bars[cc % SPEC_SLOTS], parity)) { }
         }
     }
-    if (bailed && kd + L.r < n_pick) {                                        // the rest directly, from state_k
-        const int k = kd + L.r;
+    if (bailed && kd + r < n_pick) {                                          // the rest directly, from state_k
+        const int k = kd + r;
         const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
         dy4_nco_t o;
         dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
@@ -762,181 +502,11 @@ k_pll_spec(const float* __restrict__ in, long long in_stride, const dy4_row16_t*
         st[5] = nco_next;
         // how many whole turns the prediction of this launch ended away from the true phaseEst (see k_pll_predict)
         need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
-        if (stats) { atomicAdd(stats + 0, n_rows); atomicAdd(stats + 1, trips); atomicAdd(stats + 2, flips); atomicAdd(stats + 3, directs); }
+        if (stats) { atomicAdd(stats + 0, n_rows); atomicAdd(stats + 1, groups); atomicAdd(stats + 2, directs); atomicAdd(stats + 3, directs); }
     }
 }
 
-// Variant B of the speculative loop: the group is certified right after its own chain (nothing runs ahead on an
-// uncertified state, so a flip wastes only the steps behind it).  Lane i catches phaseEst before step i in a register
-// on the way (one LOP3 with a lane mask per step), so the certificate is one subtract, one compare and a vote after the
-// last step; (integ, phaseEst) of every step are also parked in shared memory for the resume.
-template <int G>
-__global__ void __launch_bounds__(32)
-k_pll_spec2(const float* __restrict__ in, long long in_stride, const dy4_row16_t* __restrict__ tab, long long tab_stride,
-            float* __restrict__ phase_out, long long phase_stride, float* __restrict__ nco0, float* __restrict__ tstart,
-            const double* __restrict__ pred, double* __restrict__ need, float* __restrict__ state, int* __restrict__ stats, int n, int n_streams, PllConst c)
-{
-    static_assert(G >= 4 && G <= 32 && 3 * G <= SPEC_SG, "one lane certifies one step");
-    __shared__ __align__(16) dy4_row16_t raw[SPEC_R];
-    __shared__ __align__(16) float4 conv[SPEC_R + 32];
-    __shared__ __align__(16) float4 chk[SPEC_R];
-    __shared__ __align__(16) float2 cap[G + 2];
-    __shared__ __align__(8) unsigned long long bars[SPEC_SLOTS];
-    const int lane = threadIdx.x;
-    const int s = blockIdx.x;
-    if (s >= n_streams || n <= 0) return;
-    float* st = state + (long long)s * 8;
-    float fbI = st[0], fbQ = st[1], integ = st[2], phase = st[3];
-    const double T0 = (double)st[4];
-    const float nco_carry = st[5];
-    const float* x = in + (long long)s * in_stride;
-    const dy4_row16_t* rows = tab + (long long)s * tab_stride;
-    float* y = phase_out + (long long)s * phase_stride;
-    const int n_pick = n - 1;
-    int kd = 0;
-    if (T0 < (double)TAB_EARLY) kd = min(n_pick, ((int)((double)TAB_EARLY - T0) + 3) & ~3);
-    if (pred[8 * s + 3] != T0) kd = n_pick;
-    const int n_rows = n_pick - kd;
-    const int n_chunks = (n_rows + SPEC_SG - 1) / SPEC_SG;
-    auto issue = [&](int cc) {
-        const int slot = cc % SPEC_SLOTS;
-        tab_bulk_load<SPEC_SG * 16>(raw + slot * SPEC_SG, rows + (long long)kd + (long long)cc * SPEC_SG, &bars[slot]);
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < SPEC_SLOTS; i++) tab_mbar_init(&bars[i]);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int i = 0; i < SPEC_SLOTS && i < n_chunks; i++) issue(i);
-    }
-    __syncwarp();
-    if (kd == 0) dy4_pll_filter(detector_libm(x[0], fbI, fbQ), c.Kp, c.Ki, &integ, &phase);
-    else {
-        PllRegs rg = {fbI, fbQ, integ, phase, T0, 0.0, 0.0, 0.0};
-        dy4_nco_t o;
-        o.c = 1.0; o.s = 0.0; o.base_hi = 0.0; o.base_lo = 0.0;
-        pll_advance<1, false>(detector_libm(x[0], rg.fbI, rg.fbQ), rg, c, o, n > 1 && x[1] < 0.0f);
-        tab_direct_span(x, y, n, 0, kd, &rg, &o, c.w, c.Kp, c.Ki);
-        integ = rg.integ; phase = rg.phase;
-    }
-    int conv_chunks = 0, directs = 0, trips = 0, flips = 0;
-    bool bailed = false;
-    auto cover = [&](int upto) {
-        while (conv_chunks < n_chunks && conv_chunks * SPEC_SG < upto) {
-            const int cc = conv_chunks, slot = cc % SPEC_SLOTS;
-            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
-            while (!tab_mbar_try(&bars[slot], parity)) { }
-#pragma unroll
-            for (int p = 0; p < SPEC_SG / 32; p++) {
-                const int idx = slot * SPEC_SG + p * 32 + lane;
-                const dy4_row16_t row = raw[idx];
-                const float4 q = make_float4(__fmul_rn(c.Ki, row.e_p), __fmul_rn(c.Kp, row.e_p), __fmul_rn(c.Ki, row.e_o), __fmul_rn(c.Kp, row.e_o));
-                conv[idx] = q;
-                if (idx < 32) conv[SPEC_R + idx] = q;
-                float4 v;
-                dy4_spec_fast_row(row.t, &v.x, &v.y, &v.z);
-                v.w = 0.0f;
-                chk[idx] = v;
-            }
-            conv_chunks++;
-            __syncwarp();
-            if (cc >= 2 && cc + 2 < n_chunks && lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(cc + 2);
-            }
-        }
-    };
-    unsigned mask[G];                                 // lane i: all ones in mask[i]
-#pragma unroll
-    for (int i = 0; i < G; i++) { const unsigned m = lane == i ? 0xffffffffu : 0u; asm volatile("mov.b32 %0, %1;" : "=r"(mask[i]) : "r"(m)); }
-    int r = 0, forced = 0;
-    float2 ab[G], abn[G];
-    auto load_ops = [&](float2 (&dst)[G], int row, int f) {
-        const float4* cv = conv + (row & (SPEC_R - 1));
-        const float4 q0 = cv[0];
-        dst[0] = f ? make_float2(q0.z, q0.w) : make_float2(q0.x, q0.y);
-#pragma unroll
-        for (int i = 1; i < G; i++) dst[i] = *reinterpret_cast<const float2*>(cv + i);
-    };
-    cover(2 * G);
-    load_ops(ab, 0, 0);
-#pragma unroll 1
-    while (r < n_rows) {
-        cover(r + 2 * G);
-        const int nv = min(G, n_rows - r);
-        const float4 q = chk[(r + lane) & (SPEC_R - 1)];
-        const float tc = (lane == 0 && forced) ? q.z : q.x;
-        load_ops(abn, r + G, 0);                      // operands of the next group, should this one hold
-        float si = integ, sp = phase;
-        unsigned mine = 0;
-#pragma unroll
-        for (int i = 0; i < G; i++) {
-            cap[i] = make_float2(si, sp);
-            mine |= __float_as_uint(sp) & mask[i];
-            si = __fadd_rn(si, ab[i].x);
-            sp = __fadd_rn(sp, __fadd_rn(ab[i].y, si));
-        }
-        cap[G] = make_float2(si, sp);
-        const float myph = __uint_as_float(mine);
-        const bool good = (lane >= nv) | (dy4_spec_fast_check(myph, tc, q.y) != 0);
-        const unsigned bad = ~__ballot_sync(0xffffffffu, good);
-        const int j = bad ? __ffs(bad) - 1 : nv;
-        if (lane < j) y[kd + r + lane] = myph;
-        trips++;
-        if (j == G) {                                 // the whole group is certain: straight on
-            r += G; integ = si; phase = sp; forced = 0;
-#pragma unroll
-            for (int i = 0; i < G; i++) ab[i] = abn[i];
-            continue;
-        }
-        const float2 sj = cap[j];
-        if (j == nv) { r += nv; integ = sj.x; phase = sj.y; break; }       // the launch's last rows
-        const int k = r + j;
-        if (j == 0 && forced) {
-            const dy4_row16_t row = raw[k & (SPEC_R - 1)];
-            int direct;
-            const float2 nx = spec_slow_step(row.t, row.e_p, row.e_o, x, n, kd + k, T0, c.w, c.Kp, c.Ki, sj.x, sj.y, &direct);
-            if (lane == 0) y[kd + k] = sj.y;
-            integ = nx.x; phase = nx.y; r = k + 1; forced = 0;
-            directs += direct;
-            if (r >= 2 * SPEC_SG && 4 * directs > r) { bailed = true; break; }
-        } else { integ = sj.x; phase = sj.y; r = k; forced = 1; flips++; }
-        cover(r + 2 * G);
-        load_ops(ab, r, forced);
-    }
-    {
-        const int issued = min(n_chunks, max(SPEC_SLOTS, conv_chunks + 2));
-        for (int cc = conv_chunks; cc < issued; cc++) {
-            const unsigned parity = (unsigned)((cc / SPEC_SLOTS) & 1);
-            while (!tab_mbar_try(&bars[cc % SPEC_SLOTS], parity)) { }
-        }
-    }
-    if (bailed && kd + r < n_pick) {
-        const int k = kd + r;
-        const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, k + 1), phase);
-        dy4_nco_t o;
-        dy4_sincos_nco_v((double)th, x[min(k + 1, n - 1)] < 0.0f, &o, 0);
-        PllRegs rg = {__double2float_rn(o.c), __double2float_rn(o.s), integ, phase, dy4_pll_count(T0, k + 1), 0.0, 0.0, 0.0};
-        tab_direct_span(x, y, n, k, n_pick, &rg, &o, c.w, c.Kp, c.Ki);
-        integ = rg.integ; phase = rg.phase;
-    }
-    const float th = dy4_pll_trigarg(c.w, dy4_pll_count(T0, n), phase);
-    dy4_nco_t o;
-    dy4_sincos_nco_v((double)th, 0, &o, 0);
-    const float nco_next = nco_value(th, c.ncoScale, c.phaseAdjust);
-    if (lane == 0) {
-        y[n - 1] = phase;
-        nco0[s] = nco_carry;
-        tstart[s] = (float)T0;
-        st[0] = __double2float_rn(o.c); st[1] = __double2float_rn(o.s); st[2] = integ; st[3] = phase;
-        st[4] = (float)dy4_pll_count(T0, n);
-        st[5] = nco_next;
-        need[s] = pred[8 * s + 4] + rint(((double)phase - pred[8 * s + 1]) * 0.15915494309189533577);
-        if (stats) { atomicAdd(stats + 0, n_rows); atomicAdd(stats + 1, trips); atomicAdd(stats + 2, flips); atomicAdd(stats + 3, directs); }
-    }
-}
-
-// NCO row from the phaseEst row of k_pll_tab: trigArg[k-1] = RN_f(RN_d(w*T) + phase[k-1]) (filter.cpp:214), then as k_nco
+// NCO row from the phaseEst row of k_pll_sel: trigArg[k-1] = RN_f(RN_d(w*T) + phase[k-1]) (filter.cpp:214), then as k_nco
 __global__ void __launch_bounds__(256)
 k_nco_phase(const float* __restrict__ phase, long long phase_stride, const float* __restrict__ nco0, const float* __restrict__ tstart,
             float* __restrict__ nco, long long nco_stride, int n, PllConst c)
@@ -1015,9 +585,7 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
     c.w = 2 * 3.14159265358979323846 * (double)ratio;           // (2*PI)*(freq/Fs), left to right in double
     c.ncoScale = a.ncoScale;
     c.phaseAdjust = a.phaseAdjust;
-    static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // tuning knob
     // Table-driven loop (dy4_plltab.h) when the caller provides the row buffer: predict -> table -> serial pick.
-    static const int tab_lanes_env = std::getenv("DY4_PLL_LANES") ? atoi(std::getenv("DY4_PLL_LANES")) : 0;
     if (a.tab && a.fresh > 0 && a.n > a.fresh + 64) {
         // First launch of a stream.  While the loop acquires lock the detector crosses +-pi, where one ulp decides the
         // sign of a 2*pi jump: the predictor cannot know on which turn phaseEst settles, and a table built around the
@@ -1045,53 +613,17 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
             k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.pred_in, a.pred_out, a.need, a.pred_carry,
                                                                                  a.theta, a.wide_stride, a.n, c);
-            // DY4_PLL_TABLE_SMEM (bytes of unused dynamic shared memory per CTA) caps the resident CTAs of the table kernel: fewer
-            // warps contending with the serial loops it runs beside (A/B knob)
-            static const int tab_smem = std::getenv("DY4_PLL_TABLE_SMEM") ? atoi(std::getenv("DY4_PLL_TABLE_SMEM")) : 0;
-            if (a.spec) k_pll_table16<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride,
-                                                                                              reinterpret_cast<dy4_row16_t*>(a.tab), a.tab_stride, a.n, c);
-            else k_pll_table<<<dim3(a.n_streams, (a.n + 127) / 128), 128, tab_smem, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            k_pll_table_ops<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
             g_dy4_launches += 2;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
-        if ((parts & DY4_PLL_LOOP) && a.spec) {
+        if (parts & DY4_PLL_LOOP) {
             float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
-            static const int g = std::getenv("DY4_PLL_G") ? atoi(std::getenv("DY4_PLL_G")) : 16;
             int* stats = nullptr;
             if (g_spec_stats_on) cudaGetSymbolAddress(reinterpret_cast<void**>(&stats), g_spec_stats);
-#define DY4_SPEC_ARGS a.in, a.in_stride, reinterpret_cast<const dy4_row16_t*>(a.tab), a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, stats, a.n, a.n_streams, c
-            static const int variant = std::getenv("DY4_PLL_VARIANT") ? atoi(std::getenv("DY4_PLL_VARIANT")) : 2;
-            if (variant == 1) {
-                if (g <= 8) k_pll_spec<8><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 12) k_pll_spec<12><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 16) k_pll_spec<16><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 24) k_pll_spec<24><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else k_pll_spec<32><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-            } else {
-                if (g <= 8) k_pll_spec2<8><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 12) k_pll_spec2<12><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 16) k_pll_spec2<16><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else if (g <= 24) k_pll_spec2<24><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-                else k_pll_spec2<32><<<a.n_streams, 32, 0, st>>>(DY4_SPEC_ARGS);
-            }
-#undef DY4_SPEC_ARGS
-            g_dy4_launches++;
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return e;
-        } else if (parts & DY4_PLL_LOOP) {
-            int lanes = tab_lanes_env > 0 ? tab_lanes_env : (a.n_streams + 591) / 592;       // one warp per SM sub-partition while they last
-            lanes = std::max(1, std::min(lanes, TAB_LANES));
-            static const bool fence = !(std::getenv("DY4_PLL_FENCE") && atoi(std::getenv("DY4_PLL_FENCE")) == 0);
-            const int grid = (a.n_streams + lanes - 1) / lanes;
-            float* ph = reinterpret_cast<float*>(a.inv);     // phaseEst row (the reciprocal row of the direct loop is free in this mode)
-            static const int sg = std::getenv("DY4_PLL_SG") ? atoi(std::getenv("DY4_PLL_SG")) : 64;
-#define DY4_TAB_ARGS a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state, a.n, a.n_streams, c, lanes
-            if (sg == 32) k_pll_tab<true, 32, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-            else if (sg == 128) k_pll_tab<true, 128, 2><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-            else if (fence) k_pll_tab<true, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-            else k_pll_tab<false, 64, 4><<<grid, 32, 0, st>>>(DY4_TAB_ARGS);
-#undef DY4_TAB_ARGS
+            k_pll_sel<32><<<a.n_streams, 32, 0, st>>>(a.in, a.in_stride, a.tab, a.tab_stride, ph, 2 * a.wide_stride, a.nco0, a.tstart, a.pred_out, a.need, a.state,
+                                                      stats, a.n, a.n_streams, c);
             g_dy4_launches++;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
@@ -1110,13 +642,8 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
         cudaError_t e0 = cudaGetLastError();
         if (e0 != cudaSuccess) return e0;
     }
-    // DY4_PLL_NARROW=f2f selects the plain double->float->double narrowing of trigArg instead of the
-    // magic-constant rounding inside a tracked binade (A/B knob; results are identical, see tests).
-    static const bool f2f = std::getenv("DY4_PLL_NARROW") && std::string(std::getenv("DY4_PLL_NARROW")) == "f2f";
     if (parts & DY4_PLL_LOOP) {
-        const dim3 g((a.n_streams + threads - 1) / threads);
-        if (f2f) k_pll<0, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
-        else k_pll<2, false><<<g, threads, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
+        k_pll<2, false><<<(a.n_streams + 31) / 32, 32, 0, st>>>(a.in, a.in_stride, a.inv, a.theta, a.wide_stride, a.nco0, a.state, a.n, a.n_streams, c);
         g_dy4_launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -9,15 +9,15 @@
 // only thing the predictor lacks is the float rounding of trigArg, |q| <= u/2, which the loop filter attenuates).
 //
 // So the work is split three ways (dy4_pll.cu):
-//   1. k_pll_predict   time-parallel (segments with a warm-up), serial only in cheap double adds: predicted trigArg
-//   2. k_pll_table     fully parallel: for every sample the EXACT errorD of the next step for the two neighbouring floats
-//                      the prediction lies between (the dy4_pllmath.h sincos + detector, unchanged arithmetic)
-//   3. k_pll_tab       the serial loop: per sample ONE float compare of phaseEst with a precomputed threshold picks the
-//                      grid point the true trigArg falls on, and two speculative loop-filter updates (float adds) are
-//                      selected from — tens of cycles instead of ~445.  Whenever the pick is not certain (outside the
-//                      two candidates, within a rounding-error guard band of the threshold, binade edges, start-up) the
-//                      thread evaluates that step directly with dy4_pllmath.h, so the result is the reference's bit for
-//                      bit by construction.
+//   1. k_pll_predict    time-parallel (segments with a warm-up), serial only in cheap double adds: predicted trigArg
+//   2. k_pll_table_ops  fully parallel: for every sample the EXACT errorD of the next step for the two neighbouring floats the
+//                       prediction lies between (the dy4_pllmath.h sincos + detector, unchanged arithmetic), as a chain-ready row
+//   3. k_pll_sel        the serial loop: per sample ONE float compare of phaseEst with a precomputed threshold picks the grid
+//                       point the true trigArg falls on, and two speculative loop-filter updates (float adds) are selected
+//                       from.  Whether each pick was CERTAIN under its rounding-error budget is decided after every 32 steps,
+//                       one lane per step; a step that is not (outside the two candidates, within the guard band of the
+//                       threshold, binade edges, start-up) is evaluated directly with dy4_pllmath.h, so the result is the
+//                       reference's bit for bit by construction.
 //
 // Everything here is a fixed sequence of IEEE operations compiled for host and device; tests/host/plltab_host.c runs the
 // three parts on the host against the reference recurrence with glibc (tests/test_host_logic.py).
@@ -37,18 +37,6 @@
 // Samples of a stream evaluated directly before the table takes over: while the loop acquires lock the detector
 // crosses +-pi, where one ulp decides the sign of a 2*pi jump, and nothing predicts that.
 #define DY4_TAB_EARLY 1536
-
-// One table row per sample k of a launch: what the serial loop needs to go from state_k to state_{k+1}.
-// 32 bytes (the first eight fields), read as two 16-byte words.  The prediction th_hat lies between two neighbouring floats
-// lo < hi = lo + u, and so — almost always — does the true trigArg.  With t = (lo - RN_d(w*T_k)) + u/2:
-// trigArg_k = RN_f(RN_d(w*T_k) + phase_k) is lo for phase_k in (t - u, t) and hi for phase_k in (t, t + u).
-typedef struct {
-    float t, hu;      // the threshold rounded to float (NaN: row not usable); u/2
-    float hm, pad;    // hm = u/2 - m, m the guard band (rounding-error budget of the pick): certain iff | |phase - t| - u/2 | < hm
-    float a_lo, a_hi; // Ki*errorD of step k+1 if trigArg_k = lo, hi   (filter.cpp:207's product)
-    float b_lo, b_hi; // Kp*errorD                                     (filter.cpp:210's product)
-    float lo, u;      // (not stored on the device) the lower candidate, grid spacing of its binade
-} dy4_tabrow_t;
 
 // float counter of filter.cpp:213 as a double: exact below 2^24, sticks there (16777217 rounds back to 16777216)
 DY4_HD double dy4_pll_count(double T0, int steps) { return fmin(T0 + (double)steps, 16777216.0); }
@@ -111,44 +99,17 @@ DY4_HD int dy4_f2i_bits(float v) { int b; memcpy(&b, &v, 4); return b; }
 DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 #endif
 
-// th_hat: predicted trigArg of this sample; wT = RN_d(w*T_k);
-// x_next: input of step k+1 (has_next == 0 for the last sample of a launch: products unused).
-// `force_invalid`: rows the serial loop must evaluate directly whatever the prediction says.
-DY4_HD void dy4_tab_make_row(double th_hat, double wT, float x_next, int has_next, int force_invalid, float Kp, float Ki, dy4_tabrow_t* r)
-{
-    const float c = DY4_D2F(th_hat);
-    const int bits = dy4_f2i_bits(c);
-    const int expo = (bits >> 23) & 0xff, mant = bits & 0x7fffff;
-    // usable: positive normal float with both neighbours in the same binade and u in a sane range (2^-40 .. 2^40)
-    const int ok = !force_invalid && bits > 0 && expo >= 110 && expo <= 190 && mant >= 2 && mant <= 0x7ffffd;
-    const float u = dy4_i2f_bits((ok ? expo - 23 : 127) << 23);
-    const float lo = (th_hat >= (double)c) ? c : DY4_FADDF(c, -u), hi = DY4_FADDF(lo, u);
-    const double hu = DY4_MUL(0.5, (double)u);
-    const float t = DY4_D2F(DY4_ADD(DY4_SUB((double)lo, wT), hu));
-    r->lo = lo; r->u = u; r->hu = DY4_D2F(hu); r->pad = 0.0f;
-    r->t = ok ? t : dy4_i2f_bits(0x7fc00000);
-    // t is within 2^-24|t| (half an ulp) of the exact threshold; the pick's two float subtractions add at most 2^-24 u, the
-    // reference's double add 2^-29 u: the guard band is two half-ulps of t plus 2^-23 u.
-    const float m = DY4_FADDF(DY4_FMULF(1.1920928955078125e-07f, fabsf(t)), DY4_FMULF(1.1920928955078125e-07f, u));
-    r->hm = DY4_FADDF(r->hu, -m);
-    r->a_lo = r->a_hi = r->b_lo = r->b_hi = 0.0f;
-    if (ok && has_next) {
-        const float e_lo = dy4_next_errorD((double)lo, x_next);
-        const float e_hi = dy4_next_errorD((double)hi, x_next);
-        r->a_lo = DY4_FMULF(Ki, e_lo); r->a_hi = DY4_FMULF(Ki, e_hi);
-        r->b_lo = DY4_FMULF(Kp, e_lo); r->b_hi = DY4_FMULF(Kp, e_hi);
-    }
-}
-
-// ---- 2b. the 16-byte row of the speculative loop (k_pll_spec) -------------------------------------------------------
-// The same two candidates, stored as (predicted, other) instead of (lo, hi): the serial loop ADDS the predicted
-// candidate's products unconditionally — its dependent chain is three float adds per sample, no compare, no select —
-// and certifies afterwards, off the chain, that phaseEst really was inside the predicted candidate's cell.
-//   t    double: threshold between lo and hi in the phaseEst domain, t = (lo - RN_d(w*T)) + u/2, with the low 9 mantissa
-//        bits replaced by  bit 0: the predicted candidate is hi;  bits 1..8: biased float exponent of u.  NaN: row unusable.
+// ---- 2b. the row: two candidates and the threshold between them ------------------------------------------------------
+// The prediction th_hat lies between two neighbouring floats lo < hi = lo + u, and so - almost always - does the true trigArg.
+//   t    double: threshold between lo and hi in the phaseEst domain, t = (lo - RN_d(w*T)) + u/2: trigArg = RN_f(RN_d(w*T) + phase)
+//        is lo for phase in (t - u, t) and hi for phase in (t, t + u).  The low 9 mantissa bits carry  bit 0: the candidate nearest
+//        to the prediction is hi;  bits 1..8: biased float exponent of u.  NaN: row unusable.
 //   e_p, e_o   errorD of the next step if trigArg is the predicted / the other candidate (filter.cpp:200)
-// A double threshold makes the certificate's error budget 2^-26 u + 2^-40 |t| (see dy4_spec_check): with a float
-// threshold (dy4_tabrow_t) the half-ulp of t alone is 0.6 % of u early in a stream.
+// k_pll_table_ops turns this into the 32-byte row the loop reads (products with Ki, Kp; float threshold; the cells' centres and
+// certified half-width, dy4_spec_fast_row).  dy4_spec_check is the certificate in double (budget 2^-26 u + 2^-40 |t|): the host
+// tests hold the loop's float certificate to it.
+// th_hat: predicted trigArg of this sample; wT = RN_d(w*T_k); x_next: input of step k+1 (has_next == 0 for the last sample of a
+// launch: errorD unused); force_invalid: rows the serial loop must evaluate directly whatever the prediction says.
 typedef struct { double t; float e_p, e_o; } dy4_row16_t;
 
 #if defined(__CUDA_ARCH__)
@@ -159,7 +120,7 @@ DY4_HD unsigned long long dy4_d2u_bits(double v) { unsigned long long b; memcpy(
 DY4_HD double dy4_u2d_bits(unsigned long long v) { double f; memcpy(&f, &v, 8); return f; }
 #endif
 
-// Arguments as dy4_tab_make_row.  *lo_out / *u_out (host checks only, may be NULL): the lower candidate and the grid spacing.
+// *lo_out / *u_out (host checks only, may be NULL): the lower candidate and the grid spacing.
 DY4_HD void dy4_tab_make_row16(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_row16_t* r, float* lo_out, float* u_out)
 {
     const float c = DY4_D2F(th_hat);
@@ -197,10 +158,10 @@ DY4_HD int dy4_spec_check(float phase, double t, int other)
     return dd > m && dd < DY4_SUB(u, m);
 }
 
-// The loop's fast certificate, in float, for whole groups at once: the cell's centre tc = t -+ u/2 rounded to float and
+// The loop's certificate, in float, one lane per step: the cell's centre tc = t -+ u/2 rounded to float and
 // a half-width hm = u/2 - m_f with m_f = 2^-22 (|t| + u), which covers the float rounding of t (2^-24 |t|), of tc
 // (2^-24 (|t| + u/2)) and of the loop's own subtraction (2^-24 u) on top of dy4_spec_check's budget, twice over.
-// |phase - tc| < hm  =>  dy4_spec_check holds.  Where it fails the loop falls back on dy4_spec_check itself.
+// |phase - tc| < hm  =>  dy4_spec_check holds.  Where it fails the loop evaluates the step directly.
 // q = (tc of the predicted candidate, hm, tc of the other candidate); a NaN row gives NaN everywhere (never certain).
 DY4_HD void dy4_spec_fast_row(double t, float* tc_p, float* hm, float* tc_o)
 {
@@ -213,15 +174,3 @@ DY4_HD void dy4_spec_fast_row(double t, float* tc_p, float* hm, float* tc_o)
     *hm = DY4_FADDF(hu, -DY4_FMULF(2.384185791015625e-07f, DY4_FADDF(fabsf(tf), u)));
 }
 DY4_HD int dy4_spec_fast_check(float phase, float tc, float hm) { return fabsf(DY4_FADDF(phase, -tc)) < hm; }
-
-// ---- 3. the pick ----------------------------------------------------------------------------------------------------
-// Which grid point is trigArg_k = RN_f(RN_d(w*T_k) + phase_k)?  Returns 1 and *up (0: lo, 1: hi) when that is certain:
-// phase is farther than m from the threshold t between the two and closer than u - m (their far ends), i.e.
-// | |phase - t| - u/2 | < u/2 - m.  0: the serial loop has to evaluate the step directly.  A NaN row fails the comparison.
-DY4_HD int dy4_tab_pick(float phase, float t, float hu, float hm, int* up)
-{
-    const float w = DY4_FADDF(phase, -t);
-    const float v = DY4_FADDF(fabsf(w), -hu);
-    *up = phase > t;
-    return fabsf(v) < hm;
-}

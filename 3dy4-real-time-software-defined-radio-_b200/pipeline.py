@@ -56,6 +56,7 @@ class Pipeline:
         assert iq.stride(1) == 1
         if n_blocks is None:
             n_blocks = iq.shape[1] // p.block_size
+        assert 0 <= n_blocks and iq.shape[1] >= n_blocks * p.block_size, "every row must hold n_blocks * block_size bytes"
         dev = iq.device
         self._last_blocks = int(n_blocks)
         out = dict(out or {})
@@ -85,6 +86,7 @@ class Pipeline:
         assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[0] == self.n_streams and a.strides[1] == 1
         if n_blocks is None:
             n_blocks = a.shape[1] // p.block_size
+        assert 0 <= n_blocks and a.shape[1] >= n_blocks * p.block_size, "every row must hold n_blocks * block_size bytes"
         self._last_blocks = int(n_blocks)
         na = n_blocks * p.audio_per_block * self.channels
         out = dict(out or {})

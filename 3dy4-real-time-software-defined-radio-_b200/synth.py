@@ -15,11 +15,18 @@ import numpy as np
 RF_FS = {0: 2.4e6, 1: 1.44e6, 2: 2.4e6, 3: 1.92e6}  # reference src/project.cpp:180,192,204,216
 
 
-def stream_params(seed):
+def stream_params(seed, period_s=None):
+    """period_s: make the stream periodic with that period (tone frequencies moved to the nearest multiple of 1/period_s; the
+    19 kHz pilot and its harmonics must be multiples already): replaying the buffer then IS a continuous signal."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    return dict(fL=rng.uniform(300, 5000), fR=rng.uniform(300, 5000),
-                aL=rng.uniform(0.2, 0.5), aR=rng.uniform(0.2, 0.5),
-                phi=rng.uniform(0, 2 * np.pi), noise_seed=int(rng.integers(0, 2**31)))
+    p = dict(fL=rng.uniform(300, 5000), fR=rng.uniform(300, 5000),
+             aL=rng.uniform(0.2, 0.5), aR=rng.uniform(0.2, 0.5),
+             phi=rng.uniform(0, 2 * np.pi), noise_seed=int(rng.integers(0, 2**31)))
+    if period_s:
+        assert abs(19e3 * period_s - round(19e3 * period_s)) < 1e-9, "the pilot must complete whole cycles in one period"
+        p["fL"] = round(p["fL"] * period_s) / period_s
+        p["fR"] = round(p["fR"] * period_s) / period_s
+    return p
 
 
 RDS_OFFSET_WORDS = {"A": 0x0FC, "B": 0x198, "C": 0x168, "Cp": 0x350, "D": 0x1B4}   # IEC 62106 annex A
@@ -54,6 +61,11 @@ def rds_bitstream(n_bits, seed):
     return np.cumsum(rds_group_bits(n_bits, seed)) % 2
 
 
+def whole_cycles(mode, n_pairs):
+    """True if the 19 kHz pilot completes whole cycles in n_pairs samples (then periodic=True streams of that length exist)."""
+    return (n_pairs * 19000) % int(RF_FS[mode]) == 0
+
+
 def make_stream(mode, n_pairs, seed, rds=False):
     """One stream: uint8[2*n_pairs], interleaved I0 Q0 I1 Q1 ..."""
     fs = RF_FS[mode]
@@ -83,9 +95,10 @@ def make_batch(mode, n_streams, n_pairs, base_seed=65, rds=False):
     return np.stack([make_stream(mode, n_pairs, base_seed + s, rds) for s in range(n_streams)])
 
 
-def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chunk_streams=16, rds=False):
+def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chunk_streams=16, rds=False, periodic=False):
     """Same signal model generated on the GPU with torch (benchmark input only:
-    the random draws differ from make_batch, the statistics do not)."""
+    the random draws differ from make_batch, the statistics do not).  periodic: every component completes whole cycles
+    in the buffer (tones, pilot, FM phase), so feeding the buffer again continues the signal without a jump."""
     import torch
     fs = RF_FS[mode]
     out = torch.empty((n_streams, 2 * n_pairs), dtype=torch.uint8, device=device)
@@ -93,7 +106,7 @@ def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chun
     t = torch.arange(n_pairs, dtype=torch.float64, device=device) / fs
     for s0 in range(0, n_streams, chunk_streams):
         s1 = min(n_streams, s0 + chunk_streams)
-        ps = [stream_params(base_seed + s) for s in range(s0, s1)]
+        ps = [stream_params(base_seed + s, n_pairs / fs if periodic else None) for s in range(s0, s1)]
         col = lambda k: torch.tensor([p[k] for p in ps], dtype=torch.float64, device=device)[:, None]
         L = col("aL") * torch.sin(2 * np.pi * col("fL") * t)
         R = col("aR") * torch.sin(2 * np.pi * col("fR") * t)
@@ -108,6 +121,8 @@ def make_batch_torch(mode, n_streams, n_pairs, base_seed=65, device="cuda", chun
             m = m + 0.05 * d * torch.cos(3 * wp)
             del bits, sym, d
         del L, R, wp
+        if periodic:
+            m = m - m.mean(dim=1, keepdim=True)         # the FM phase must return to its start (rounding leaves ~1e-17 per sample)
         phase = (2 * np.pi * 75e3 / fs) * torch.cumsum(m, dim=1)
         del m
         g.manual_seed(base_seed * 1000003 + s0)

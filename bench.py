@@ -7,7 +7,9 @@
 Workload = BASELINE.json configs[1]: mode 0 stereo FM (pilot BPF + PLL + 38 kHz mix), a batch of 256
 independent synthetic 8-bit IQ streams per GPU (weak scaling: N GPUs carry N x 256 streams, partitioned by
 stream index, no data-path collective).  One "step" = one pass of the whole receiver over the batch:
-256 streams x 47 blocks (1.003 s of signal each, 1.23 GB of input per GPU — larger than the 126 MB L2).
+256 streams x 48 blocks (1.024 s of signal each, 1.26 GB of input per GPU — larger than the 126 MB L2).  The synthetic
+streams are periodic over that length (tones, pilot and FM phase complete whole cycles), so feeding the buffer again at every
+step continues every stream without a jump: the receivers carry their state from step to step as they would on live input.
 
 One JSON line on stdout (rank 0):
   value     device-resident throughput: inputs already in HBM, CUDA events on the launch stream, max over ranks
@@ -31,7 +33,7 @@ sys.path.insert(0, ROOT)
 MODE, STEREO = 0, 1
 RDS = False                      # --rds: BASELINE configs[3], the stereo receiver plus the RDS path
 STREAMS_PER_GPU = 256
-BLOCKS_PER_STREAM = 47           # 47 x 21.33 ms = 1.003 s per stream
+BLOCKS_PER_STREAM = 48           # 48 x 21.33 ms = 1.024 s per stream: every component of the synthetic signal completes whole cycles in it
 METRIC = "aggregate_iq_msamples_per_s_stereo_fm"
 UNIT = "Msamples/s"
 FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45: SMs x lanes x 2 flop x max SM clock
@@ -188,7 +190,8 @@ def run_gpu_arm(args):
     n_if, n_audio = nb * m.if_per_block, nb * m.audio_per_block
 
     # synthetic input, generated on the GPU; stream s of the whole job uses seed 65+s
-    d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev, rds=RDS)
+    periodic = dy4_b200.synth.whole_cycles(MODE, nb * m.block_size // 2)       # 48 blocks in mode 0: yes
+    d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev, rds=RDS, periodic=periodic)
     if S > 512:                                      # very large batches: tile 512 distinct streams (generation time, not a kernel matter)
         d_iq = d_iq.repeat((S + 511) // 512, 1)[:S].contiguous()
     pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, rds=RDS)
@@ -236,22 +239,40 @@ def run_gpu_arm(args):
     h_iq = torch.empty((S, nb * m.block_size), dtype=torch.uint8).pin_memory()
     h_iq.copy_(d_iq)
     h_pcm = torch.empty((S, n_audio * nch), dtype=torch.int16).pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     pipe.reset()
     pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)   # warm-up (allocates staging)
     torch.cuda.synchronize(dev)
     shard.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        pipe.reset()
+    for i in range(e2e_steps):                       # the streams continue from step to step, as in the device-resident leg
         pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)
     torch.cuda.synchronize(dev)
     e2e_ms = shard.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
     e2e_value = world * pairs_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
-    pipe.reset()                                     # same starting state as the e2e pass, then compare the two paths
+    # the two paths from the same starting state: identical PCM?
+    pipe.reset()
+    pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)
+    pipe.reset()
     pipe.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
     torch.cuda.synchronize(dev)
     pcm_matches = bool(torch.equal(h_pcm.to(dev), out["pcm"]))
+
+    # ---- the timed path against the oracle (rank 0, two streams x 4 blocks from a fresh start): same bytes in, PCM out -----
+    oracle_check = None
+    if rank == 0 and not args.no_cpu and not RDS:
+        import oracle
+        chk = oracle.load("ref") if oracle.have_ref() else oracle.load("oracle")
+        nbc = min(4, nb)
+        small = d_iq[:2, :nbc * m.block_size].contiguous()
+        pc = dy4_b200.Pipeline(MODE, STEREO, 2, device=local_rank)
+        got = pc.process(small, n_blocks=nbc, want=("pcm",))["pcm"].cpu().numpy()
+        pc.close()
+        worst = 0
+        for s_ in range(2):
+            ref = chk.pipeline(MODE, STEREO, small[s_].cpu().numpy(), want=("pcm",))["pcm"]
+            worst = max(worst, int(np.abs(got[s_].astype(np.int64) - ref.astype(np.int64)).max()))
+        oracle_check = {"checker": chk.kind, "streams": 2, "blocks": nbc, "pcm_max_abs_diff_lsb": worst, "ok": worst <= 1}
 
     # ---- the same kernels in whole-job launches, not overlapped with the PLL (one sub-chunk per step) ------------
     # In the timed region above the job is cut into sub-chunks of 1, 2, 4, ... blocks whose FIR kernels run beside the
@@ -370,6 +391,8 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": S * n_audio * nch * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
                 "timing": "host clock around the synchronous process_host() calls, max over ranks",
                 "pcm_equals_device_path": pcm_matches},
+        "oracle_check": oracle_check,
+        "signal": "periodic over one step: the streams continue from step to step without a jump" if periodic else "the same buffer again every step: a phase jump per step",
         "gpu_launches": total_launches,
         "roofline": roofline, "kernels": kernels, "pll": pll_info, "cpu_baseline": cpu,
         "clocks": sampler.result(),
