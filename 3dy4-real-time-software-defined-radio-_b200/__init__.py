@@ -22,6 +22,7 @@ from .pipeline import Pipeline, launch_count  # noqa: F401
 from . import filterh  # noqa: F401
 from . import fourierh  # noqa: F401
 from . import rds_app  # noqa: F401
+from . import rate_change  # noqa: F401
 from . import synth  # noqa: F401
 from . import shard  # noqa: F401
 

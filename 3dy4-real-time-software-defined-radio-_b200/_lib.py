@@ -72,6 +72,10 @@ def _load():
         "dy4_pipeline_rds_bounds": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         "dy4_pipeline_rds_drain": (i, [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp]),
         "dy4_pipeline_debug_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), psz, C.POINTER(i)]),
+        "dy4_compute_twiddles": (i, [sz, i, vp]),
+        "dy4_fft": (i, [vp, sz, i, vp, sz, vp]),
+        "dy4_fft_batch": (i, [vp, sz, i, sz, i, vp, sz, vp, sz, vp]),
+        "dy4_pipeline_pll_risk": (i, [vp, vp, i]),
         "dy4_pipeline_profile": (i, [vp, i]),
         "dy4_pipeline_profile_get": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]),
         "dy4_pipeline_state_size": (sz, [vp]),

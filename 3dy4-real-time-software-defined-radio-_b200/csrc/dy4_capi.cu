@@ -12,13 +12,17 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return dy4_cuda_fail(e_, #x); } while (0)
 
 namespace {
 
-// per-thread scratch arena on the current device (filter.h functions may be called from any host thread)
+// Scratch arena on the current device (device buffer + stream).  filter.h functions may be called from any host thread — the
+// reference's main() spawns two short-lived threads per block (project.cpp:299-305) — so a thread LEASES an arena from a
+// process-wide pool on its first call and hands it back when it exits: a live stream cycles through two arenas for ever
+// instead of leaking a buffer and a stream per thread.
 struct Arena {
     char* base = nullptr; size_t cap = 0, used = 0; cudaStream_t st = nullptr;
     int reserve(size_t bytes)
@@ -35,7 +39,30 @@ struct Arena {
     }
     template <typename T> T* take(size_t n) { used = (used + 255) & ~(size_t)255; T* p = (T*)(base + used); used += n * sizeof(T); return p; }
 };
-thread_local Arena t_arena;
+struct ArenaPool { std::mutex mu; std::vector<Arena*> free_list; };
+ArenaPool& arena_pool() { static ArenaPool* p = new ArenaPool(); return *p; }      // never destroyed: threads may outlive static destructors
+struct ArenaLease {
+    Arena* a = nullptr;
+    Arena& get()
+    {
+        if (!a) {
+            ArenaPool& p = arena_pool();
+            std::lock_guard<std::mutex> lk(p.mu);
+            if (!p.free_list.empty()) { a = p.free_list.back(); p.free_list.pop_back(); }
+            else a = new Arena();
+        }
+        return *a;
+    }
+    ~ArenaLease()
+    {
+        if (!a) return;
+        ArenaPool& p = arena_pool();                  // every entry point synchronises its stream before returning: nothing is in flight
+        std::lock_guard<std::mutex> lk(p.mu);
+        p.free_list.push_back(a);
+    }
+};
+thread_local ArenaLease t_lease;
+#define t_arena (t_lease.get())
 
 inline size_t al(size_t bytes) { return (bytes + 255 + 256) & ~(size_t)255; }
 

@@ -2,7 +2,12 @@
 //   DFT          fourier.cpp:14-23    naive O(n^2) DFT of a real vector
 //   IDFT         fourier.cpp:98-107   naive inverse DFT of a complex vector
 //   estimatePSD  fourier.cpp:37-94    Hann window, DFT per segment, 10 log10 of the scaled power, segment average
-// and a batched PSD over [stream][time] rows for the receiver's IF / audio buffers.
+// and a batched PSD over [stream][time] rows for the receiver's IF / audio buffers; and its three radix-2 FFTs
+//   compute_twiddles  fourier.cpp:125-130   exp(i * float(-2 PI float(k) / NFFT))
+//   FFT_recursive     fourier.cpp:132-160   decimation in time, twiddles exp(i * float(-2 PI float(k) / size)) per level
+//   FFT_improved      fourier.cpp:162-187   the same recursion on a precomputed twiddle table, stride 2^(level-1)
+//   FFT_optimized     fourier.cpp:189-211   the same butterflies iteratively after a bit-reversal permutation
+// (one kernel: the three are the same butterfly graph and differ only in where a butterfly's twiddle VALUE comes from).
 //
 // Parity means the REFERENCE'S numbers, and its DFT is not an accurate one: every twiddle is exp(i a) with the angle
 // a = -2 PI k m / n narrowed to float before cosf/sinf — k m reaches n^2, so late twiddles are off by 1e-4 rad — and the
@@ -16,6 +21,7 @@
 #include "dy4_common.cuh"
 #include "dy4_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <map>
@@ -169,6 +175,116 @@ extern "C" int dy4_psd_batch(const float* d_samples, size_t row_stride, int n_st
     g_dy4_launches++;
     CU(cudaGetLastError());
     return DY4_OK;
+}
+
+// ---- FFTs --------------------------------------------------------------------------------------------------------
+// One CTA per row.  Stage l (sub-transform size 2^(l+1)) combines Xf[k] and Xf[k + 2^l] exactly as the reference's three
+// variants do (fourier.cpp:154-155, :181-182, :203-205): t = twiddle * odd as the four products and two sums of a complex<float>
+// multiplication, then even +- t — float, unfused.  tw holds the stage's twiddles consecutively: stage l at offset 2^l - 1.
+__device__ __forceinline__ float2 cmul_ref(float2 a, float2 b)
+{
+    return make_float2(__fadd_rn(__fmul_rn(a.x, b.x), -__fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__global__ void __launch_bounds__(1024)
+k_fft(const float2* __restrict__ x, long long x_stride, int n, int levels, const float2* __restrict__ tw, float2* __restrict__ X, long long X_stride)
+{
+    extern __shared__ float2 s_v[];
+    const float2* xr = x + (long long)blockIdx.x * x_stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_v[i] = xr[__brev((unsigned)i) >> (32 - levels)];     // fourier.cpp:115-123, :194-196
+    if (levels == 0 && threadIdx.x == 0) s_v[0] = xr[0];
+    __syncthreads();
+    for (int l = 0; l < levels; l++) {
+        const int half = 1 << l;
+        for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {
+            const int j = b & (half - 1), k = ((b >> l) << (l + 1)) + j;
+            const float2 t = cmul_ref(tw[half - 1 + j], s_v[k + half]);
+            const float2 e = s_v[k];
+            s_v[k] = make_float2(__fadd_rn(e.x, t.x), __fadd_rn(e.y, t.y));
+            s_v[k + half] = make_float2(__fadd_rn(e.x, -t.x), __fadd_rn(e.y, -t.y));
+        }
+        __syncthreads();
+    }
+    float2* Xr = X + (long long)blockIdx.x * X_stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) Xr[i] = s_v[i];
+}
+
+// per-stage twiddle values of the chosen variant, stage l at offset 2^l - 1 (n - 1 values in all)
+static int fft_stage_twiddles(size_t n, int levels, int variant, const float* twiddles, size_t n_tw, std::vector<float2>* out)
+{
+    out->assign(n > 1 ? n - 1 : 1, make_float2(1.0f, 0.0f));
+    for (int l = 0; l < levels; l++) {
+        const size_t half = (size_t)1 << l, size = half * 2, stride = n / size;
+        for (size_t j = 0; j < half; j++) {
+            float2 w;
+            if (variant == DY4_FFT_RECURSIVE) {
+                const std::complex<float> expval(0.0, -2 * kPi * float(j) / size);                 // fourier.cpp:152
+                const std::complex<float> t = std::exp(expval);
+                w = make_float2(t.real(), t.imag());
+            } else {                                                                                // :181 / :203: twiddles[j * (n / size)]
+                const size_t idx = j * stride;
+                if (!twiddles || idx >= n_tw) { dy4_set_error("dy4_fft: twiddle table too short for this length (needs n/2 entries for NFFT = n)"); return DY4_ERR_ARG; }
+                w = make_float2(twiddles[2 * idx], twiddles[2 * idx + 1]);
+            }
+            (*out)[half - 1 + j] = w;
+        }
+    }
+    return DY4_OK;
+}
+
+extern "C" int dy4_compute_twiddles(size_t n_twiddles, int nfft, float* twiddles)
+{
+    if (!twiddles || nfft < 1) { dy4_set_error("dy4_compute_twiddles: bad arguments"); return DY4_ERR_ARG; }
+    for (size_t k = 0; k < n_twiddles; k++) {
+        const std::complex<float> expval(0.0, -2 * kPi * float(k) / nfft);                          // fourier.cpp:127
+        const std::complex<float> t = std::exp(expval);
+        twiddles[2 * k] = t.real(); twiddles[2 * k + 1] = t.imag();
+    }
+    return DY4_OK;
+}
+
+extern "C" int dy4_fft_batch(const float* d_x, size_t x_stride, int n_rows, size_t n, int variant, const float* twiddles, size_t n_twiddles,
+                             float* d_X, size_t X_stride, void* stream)
+{
+    if (!d_x || !d_X || n_rows < 0 || variant < DY4_FFT_RECURSIVE || variant > DY4_FFT_OPTIMIZED) { dy4_set_error("dy4_fft_batch: bad arguments"); return DY4_ERR_ARG; }
+    int rc = check_n(n, "dy4_fft_batch");
+    if (rc) return rc;
+    if (n & (n - 1)) { dy4_set_error("dy4_fft_batch: the reference's FFTs are radix-2: length must be a power of two"); return DY4_ERR_ARG; }
+    if (n_rows == 0) return DY4_OK;
+    int levels = 0;
+    while (((size_t)1 << levels) < n) levels++;
+    std::vector<float2> tw;
+    if ((rc = fft_stage_twiddles(n, levels, variant, twiddles, n_twiddles, &tw))) return rc;
+    float2* d_tw = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMalloc(&d_tw, tw.size() * sizeof(float2)));
+    cudaError_t e = cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, n / 2));
+        k_fft<<<n_rows, threads, n * sizeof(float2), st>>>(reinterpret_cast<const float2*>(d_x), (long long)x_stride, (int)n, levels, d_tw,
+                                                           reinterpret_cast<float2*>(d_X), (long long)X_stride);
+        g_dy4_launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // tw (host) and d_tw are released here
+    cudaFree(d_tw);
+    if (e != cudaSuccess) return dy4_cuda_fail(e, "dy4_fft_batch");
+    return DY4_OK;
+}
+
+extern "C" int dy4_fft(const float* x, size_t n, int variant, const float* twiddles, size_t n_twiddles, float* Xf)
+{
+    if (!x || !Xf) { dy4_set_error("dy4_fft: null pointer"); return DY4_ERR_ARG; }
+    int rc = check_n(n, "dy4_fft");
+    if (rc) return rc;
+    float *d_x = nullptr, *d_X = nullptr;
+    CU(cudaMalloc(&d_x, n * sizeof(float2)));
+    CU(cudaMalloc(&d_X, n * sizeof(float2)));
+    cudaError_t e = cudaMemcpy(d_x, x, n * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) rc = dy4_fft_batch(d_x, n, 1, n, variant, twiddles, n_twiddles, d_X, n, nullptr);
+    if (e == cudaSuccess && rc == DY4_OK) e = cudaMemcpy(Xf, d_X, n * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaFree(d_x); cudaFree(d_X);
+    if (e != cudaSuccess) return dy4_cuda_fail(e, "dy4_fft");
+    return rc;
 }
 
 // ---- compatibility tier: host pointers, one vector per call (include/fourier.h:20, :31, :38) -------------------------

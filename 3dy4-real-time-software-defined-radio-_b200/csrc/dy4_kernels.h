@@ -34,6 +34,7 @@ struct Dy4PllArgs {
     const double* pred_in = nullptr; double* pred_out = nullptr; int pred_carry = 0;   // table-driven loop: the predictor's own state [n_streams][8] before / after this launch
     double* need = nullptr;                             // [n_streams]: whole turns between prediction and true phaseEst (written by the loop of this set, read two launches later)
     int fresh = 0; float* nco0b = nullptr;              // table-driven loop, first launch of a stream: samples left to the direct loop; second NCO carry row
+    int* risk = nullptr;                                // optional [n_streams]: census of near-tie narrowings in the table's evaluations (dy4_near_float_tie)
     float4* tab = nullptr; long long tab_stride = 0;    // optional [n_streams][tab_stride] 16-byte words, 2 per sample: selects the table-driven loop (dy4_plltab.h)
     float* nco0;                                // scratch [n_streams]: NCO value that opens this launch's row
     float* nco; long long nco_stride;

@@ -54,6 +54,7 @@ struct dy4_pipeline {
     struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
     WorkSet ws[2];
     float* ws_nco0 = nullptr;
+    int* pll_risk = nullptr;                         // [n_streams]: near-tie narrowings seen by the PLL table kernel (dy4_pipeline_pll_risk)
     double* pred_state = nullptr;                    // table-driven PLL: the predictor's own state, [2][n_streams][8], then [2][n_streams] turns
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
     // RDS filtering front end (DY4_FLAG_RDS): its own stream beside the stereo PLL
@@ -185,7 +186,6 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     blocks = std::min(blocks, std::max(n_blocks, 1));
     const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
     int nsub = 3;                                      // largest sub-chunk = a third of the job (see plan_subchunks)
-    if (const char* e = std::getenv("DY4_SUBCHUNKS")) nsub = std::max(1, atoi(e));
     if (p->stereo && !whole && n_blocks >= 8) blocks = std::min(blocks, (n_blocks + nsub - 1) / nsub);
     if (const char* e = std::getenv("DY4_SUBCHUNK_BLOCKS")) blocks = std::max(1, atoi(e));
     if (whole) blocks = std::max(blocks, n_blocks);
@@ -214,6 +214,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         }
     }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
+    if (p->pll_table && !p->pll_risk) { CU(cudaMalloc(&p->pll_risk, (size_t)p->n_streams * sizeof(int))); CU(cudaMemset(p->pll_risk, 0, (size_t)p->n_streams * sizeof(int))); }
     if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, 2 * (size_t)p->n_streams * 9 * sizeof(double)));   // [2][S][8] predictor state + [2][S] turns
     if (p->stereo && !p->s_pll) {
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
@@ -289,8 +290,7 @@ int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_o
         ba.pilot = w.pilot; ba.sband = w.sband; ba.out_stride = (long long)p->ws_stride;
         ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.variant = 0; ba.neg_zero2 = kNegZero2;
         // the stereo band only has to be bit-exact when the audio is asked to be (DY4_FLAG_EXACT_AUDIO)
-        static const bool mixed_ok = !(std::getenv("DY4_BPF") && std::string(std::getenv("DY4_BPF")) == "pair");
-        const bool mixed = mixed_ok && !(p->flags & DY4_FLAG_EXACT_AUDIO);
+        const bool mixed = !(p->flags & DY4_FLAG_EXACT_AUDIO);
         { Timer t(p, DY4_K_BPF, st); CU(mixed ? dy4_launch_bpf_mixed(ba, st) : dy4_launch_bpf(ba, st)); }
     }
     return DY4_OK;
@@ -393,7 +393,7 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.risk = p->pll_risk; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
     if (w.tab) {
         pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
         pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;
@@ -551,15 +551,6 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
     }
     if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
-    if (p->pred_state && std::getenv("DY4_DEBUG_PRED")) {          // development aid: predictor state vs PLL state of stream 0
-        CU(cudaDeviceSynchronize());
-        double h[8]; float f[8];
-        CU(cudaMemcpy(h, p->pred_state, 4 * sizeof(double), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(h + 4, p->pred_state + (size_t)p->n_streams * 8, 4 * sizeof(double), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(f, p->pll_state, 8 * sizeof(float), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "pred[0] %g %.9g %g %g | pred[1] %g %.9g %g %g | pll integ %g phase %.9g T %g | seq %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7],
-                f[2], f[3], f[4], (long long)p->seq);
-    }
     return DY4_OK;
 }
 
@@ -658,7 +649,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
-    cudaFree(p->ws_nco0); cudaFree(p->pred_state);
+    cudaFree(p->ws_nco0); cudaFree(p->pred_state); cudaFree(p->pll_risk);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); }
@@ -842,6 +833,18 @@ extern "C" int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size
     }
     CU(cudaMemset(p->rds_counts, 0, S * 4 * sizeof(int)));
     p->rds_blocks_since_drain = 0;
+    return DY4_OK;
+}
+
+extern "C" int dy4_pipeline_pll_risk(dy4_pipeline_t* p, int32_t* h_counts, int reset)
+{
+    if (!p || !h_counts) { dy4_set_error("dy4_pipeline_pll_risk: bad arguments"); return DY4_ERR_ARG; }
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    const size_t S = (size_t)p->n_streams;
+    if (!p->pll_risk) { std::memset(h_counts, 0, S * sizeof(int32_t)); return DY4_OK; }     // mono, or the direct loop: nothing counted
+    CU(cudaMemcpy(h_counts, p->pll_risk, S * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(p->pll_risk, 0, S * sizeof(int32_t)));
     return DY4_OK;
 }
 

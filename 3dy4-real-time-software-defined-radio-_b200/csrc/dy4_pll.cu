@@ -304,7 +304,7 @@ constexpr int SPEC_R = SPEC_SG * SPEC_SLOTS;         // ring size in rows
 // step cost the lone warp 39.8 instead of 26.5 ns per sample — issue slots, not bytes, are what the serial loop is short of.)
 __global__ void __launch_bounds__(128)
 k_pll_table_ops(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
-                const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int n, PllConst c)
+                const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int* __restrict__ risk, int n, PllConst c)
 {
     const int s = blockIdx.x;
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
@@ -312,8 +312,10 @@ k_pll_table_ops(const float* __restrict__ in, long long in_stride, const double*
     const double T0 = pred_out[8 * s + 3];                          // sample counter at the start of this launch (k_pll_predict)
     const float* x = in + (long long)s * in_stride;
     dy4_row16_t r;
-    dy4_tab_make_row16(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
-                       k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r, nullptr, nullptr);
+    int rk = 0;                                                     // evaluations of this row that narrow a near-tie (dy4_near_float_tie)
+    dy4_tab_make_row16_r(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
+                       k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r, nullptr, nullptr, &rk);
+    if (rk && risk) atomicAdd(risk + s, rk);                        // ~1e-8 per evaluation
     const bool ph = (dy4_d2u_bits(r.t) & 1ull) != 0;                // the predicted candidate is the upper one
     const float e_lo = ph ? r.e_o : r.e_p, e_hi = ph ? r.e_p : r.e_o;
     float tc_p, hm, tc_o;
@@ -613,7 +615,7 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
             const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
             k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.pred_in, a.pred_out, a.need, a.pred_carry,
                                                                                  a.theta, a.wide_stride, a.n, c);
-            k_pll_table_ops<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.n, c);
+            k_pll_table_ops<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.risk, a.n, c);
             g_dy4_launches += 2;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;

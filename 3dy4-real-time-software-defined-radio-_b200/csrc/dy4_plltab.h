@@ -73,23 +73,45 @@ DY4_HD double dy4_pred_step(float x, double th_prev, double wT, double Kp, doubl
     return wT + *phase;
 }
 
+#if defined(__CUDA_ARCH__)
+DY4_HD unsigned long long dy4_d2u_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+DY4_HD double dy4_u2d_bits(unsigned long long v) { return __longlong_as_double((long long)v); }
+#else
+DY4_HD unsigned long long dy4_d2u_bits(double v) { unsigned long long b; memcpy(&b, &v, 8); return b; }
+DY4_HD double dy4_u2d_bits(unsigned long long v) { double f; memcpy(&f, &v, 8); return f; }
+#endif
+
+// A double that is about to be narrowed to float lies within 2 double-ulps of a float rounding boundary (a tie of round-to-
+// nearest: the 29 bits that are dropped read 1000...0).  dy4_pllmath.h is not glibc: its results may differ from glibc's in
+// the last double ulp, and only at such a value can that change the float — so this is the census of evaluations on which
+// bit-identity with the reference rests on more than the arithmetic contract (dy4_pipeline_pll_risk).
+DY4_HD int dy4_near_float_tie(double v)
+{
+    const int d = (int)(unsigned)(dy4_d2u_bits(v) & 0x1fffffffull) - 0x10000000;
+    return d >= -2 && d <= 2;
+}
+
 // ---- 2. table row --------------------------------------------------------------------------------------------------
 // errorD of the step that follows trigArg = th (a float value) when its input sample is x: the arithmetic of
 // pll_step_fast / detector_libm in dy4_pll.cu, i.e. of filter.cpp:192-200,216-217.
-DY4_HD float dy4_next_errorD(double th, float x)
+DY4_HD float dy4_next_errorD_r(double th, float x, int* risk)
 {
     dy4_nco_t o;
     dy4_sincos_nco_v(th, x < 0.0f, &o, 0);
     const float fbI = DY4_D2F(o.c), fbQ = DY4_D2F(o.s);                                   // :216-217
+    if (risk) *risk += dy4_near_float_tie(o.c) + dy4_near_float_tie(o.s);
     if (dy4_fast_ok(x)) {
         const float eI = DY4_FMULF(x, fbI);                                               // :192 (x != 0)
         const float eQ = DY4_FMULF(x, -fbQ);                                              // :193
-        return DY4_D2F(dy4_detector_atan2((double)eQ, (double)eI, &o, dy4_recip(x)));     // :200
+        const double a = dy4_detector_atan2((double)eQ, (double)eI, &o, dy4_recip(x));
+        if (risk) *risk += dy4_near_float_tie(a);
+        return DY4_D2F(a);                                                                // :200
     }
     const float eI = DY4_FMULF((x == 0.0f ? 1.0f : x), fbI);
     const float eQ = DY4_FMULF(x, -fbQ);
     return DY4_D2F(atan2((double)eQ, (double)eI));
 }
+DY4_HD float dy4_next_errorD(double th, float x) { return dy4_next_errorD_r(th, x, (int*)0); }
 
 #if defined(__CUDA_ARCH__)
 DY4_HD int dy4_f2i_bits(float v) { return __float_as_int(v); }
@@ -112,16 +134,9 @@ DY4_HD float dy4_i2f_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 // launch: errorD unused); force_invalid: rows the serial loop must evaluate directly whatever the prediction says.
 typedef struct { double t; float e_p, e_o; } dy4_row16_t;
 
-#if defined(__CUDA_ARCH__)
-DY4_HD unsigned long long dy4_d2u_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
-DY4_HD double dy4_u2d_bits(unsigned long long v) { return __longlong_as_double((long long)v); }
-#else
-DY4_HD unsigned long long dy4_d2u_bits(double v) { unsigned long long b; memcpy(&b, &v, 8); return b; }
-DY4_HD double dy4_u2d_bits(unsigned long long v) { double f; memcpy(&f, &v, 8); return f; }
-#endif
 
 // *lo_out / *u_out (host checks only, may be NULL): the lower candidate and the grid spacing.
-DY4_HD void dy4_tab_make_row16(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_row16_t* r, float* lo_out, float* u_out)
+DY4_HD void dy4_tab_make_row16_r(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_row16_t* r, float* lo_out, float* u_out, int* risk)
 {
     const float c = DY4_D2F(th_hat);
     const int bits = dy4_f2i_bits(c);
@@ -137,9 +152,13 @@ DY4_HD void dy4_tab_make_row16(double th_hat, double wT, float x_next, int has_n
     if (lo_out) *lo_out = lo;
     if (u_out) *u_out = u;
     if (ok && has_next) {
-        r->e_p = dy4_next_errorD((double)(pred_hi ? hi : lo), x_next);
-        r->e_o = dy4_next_errorD((double)(pred_hi ? lo : hi), x_next);
+        r->e_p = dy4_next_errorD_r((double)(pred_hi ? hi : lo), x_next, risk);
+        r->e_o = dy4_next_errorD_r((double)(pred_hi ? lo : hi), x_next, risk);
     }
+}
+DY4_HD void dy4_tab_make_row16(double th_hat, double wT, float x_next, int has_next, int force_invalid, dy4_row16_t* r, float* lo_out, float* u_out)
+{
+    dy4_tab_make_row16_r(th_hat, wT, x_next, has_next, force_invalid, r, lo_out, u_out, (int*)0);
 }
 
 // Is trigArg = RN_f(RN_d(w*T) + phase) CERTAINLY the predicted candidate of this row (other == 0) / the other one (other == 1)?

@@ -414,7 +414,7 @@ cudaError_t dy4_upload_taps_rrc(const float* rrc)
 cudaError_t dy4_launch_rds_pll(const Dy4RdsArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
-    static const int threads = std::getenv("DY4_PLL_THREADS") ? atoi(std::getenv("DY4_PLL_THREADS")) : 32;   // same knob as the stereo PLL
+    const int threads = 32;                            // one warp per 32 streams: the loop is bound by its dependent chain, not by throughput
     k_rds_pll<<<(a.n_streams + threads - 1) / threads, threads, 0, st>>>(a.carrier, a.stride, a.theta, a.wide_stride, a.pll_state, a.n_if, a.n_streams, a.w, a.Kp, a.Ki);
     g_dy4_launches++;
     cudaError_t e = cudaGetLastError();

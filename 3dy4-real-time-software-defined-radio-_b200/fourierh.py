@@ -40,6 +40,40 @@ def estimatePSD(samples, nFFT, Fs):
     return freq, psd
 
 
+NFFT = 512      # include/dy4.h:18
+
+
+def compute_twiddles(n_twiddles=NFFT // 2, nfft=NFFT):
+    """fourier.h:35 / fourier.cpp:125 — twiddles[k] = exp(i * float(-2 PI float(k) / NFFT)), complex64[n_twiddles]."""
+    out = np.empty(n_twiddles, np.complex64)
+    check(lib.dy4_compute_twiddles(n_twiddles, int(nfft), _p(out)), "compute_twiddles")
+    return out
+
+
+def _fft(x, variant, twiddles):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty(x.size, np.complex64)
+    tw = None if twiddles is None else np.ascontiguousarray(twiddles, np.complex64)
+    check(lib.dy4_fft(_p(x), x.size, variant, None if tw is None else _p(tw), 0 if tw is None else tw.size, _p(out)), "FFT")
+    return out
+
+
+def FFT_recursive(x):
+    """fourier.h:37 — radix-2 decimation in time, twiddles computed at every level."""
+    return _fft(x, 0, None)
+
+
+def FFT_improved(x, twiddles, recursion_level=1):
+    """fourier.h:39 — the same on a precomputed table (len(x) == NFFT of the table; the reference is called with level 1)."""
+    assert recursion_level == 1, "the reference's entry call; deeper levels are its own recursion"
+    return _fft(x, 1, twiddles)
+
+
+def FFT_optimized(x, twiddles):
+    """fourier.h:41 — bit reversal, then the butterflies level by level."""
+    return _fft(x, 2, twiddles)
+
+
 def psd_batch(rows, nFFT, Fs, stream=None):
     """estimatePSD of every row of a CUDA float32 tensor [n_streams, n]: returns a CUDA tensor [n_streams, nFFT/2]."""
     import torch

@@ -151,6 +151,12 @@ class Pipeline:
             res.append(t)
         return res
 
+    def pll_risk(self, reset=True):
+        """int32[n_streams]: PLL evaluations narrowed to float within 2 double-ulps of a rounding boundary (dy4_pipeline_pll_risk)."""
+        out = np.zeros(self.n_streams, np.int32)
+        check(lib.dy4_pipeline_pll_risk(self._h, C.c_void_p(out.ctypes.data), int(reset)), "dy4_pipeline_pll_risk")
+        return out
+
     def profile(self, enable=True):
         check(lib.dy4_pipeline_profile(self._h, int(enable)), "dy4_pipeline_profile")
 

@@ -117,6 +117,20 @@ int dy4_estimate_psd(const float* samples, size_t n, int nfft, int Fs, float* fr
  * `stream` (a cudaStream_t). */
 int dy4_psd_batch(const float* d_samples, size_t row_stride, int n_streams, size_t n, int nfft, int Fs,
                   float* d_psd, size_t psd_stride, void* stream);
+/* fourier.h:35-41 — the reference's three radix-2 FFTs and its twiddle table (src/fourier.cpp:125-211).  complex64 vectors as
+ * interleaved (re, im) floats, n a power of two <= 2048.  All three run the same butterflies; they differ in where a butterfly's
+ * twiddle comes from: DY4_FFT_RECURSIVE computes exp(i * float(-2 PI float(k) / size)) at every level (:152); DY4_FFT_IMPROVED
+ * (:181) and DY4_FFT_OPTIMIZED (:203) read twiddles[k * n/size] from the caller's table, which must hold NFFT/2 entries with
+ * NFFT == n (compute_twiddles, :125).  Results are bit-identical to the reference's.
+ * dy4_compute_twiddles: twiddles[k] = exp(i * float(-2 PI float(k) / nfft)), k < n_twiddles (the reference fixes nfft = NFFT = 512).
+ * dy4_fft: host pointers, one vector.  dy4_fft_batch: n_rows complex rows on the DEVICE (strides in complex elements). */
+#define DY4_FFT_RECURSIVE 0
+#define DY4_FFT_IMPROVED 1
+#define DY4_FFT_OPTIMIZED 2
+int dy4_compute_twiddles(size_t n_twiddles, int nfft, float* twiddles);
+int dy4_fft(const float* x, size_t n, int variant, const float* twiddles, size_t n_twiddles, float* Xf);
+int dy4_fft_batch(const float* d_x, size_t x_stride, int n_rows, size_t n, int variant, const float* twiddles, size_t n_twiddles,
+                  float* d_X, size_t X_stride, void* stream);
 
 /* ---- throughput tier: batched receiver ----------------------------------- */
 typedef struct dy4_pipeline dy4_pipeline_t;
@@ -213,6 +227,11 @@ int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pilot, const f
 #define DY4_K_PLL_AUX 8       /* the PLL's data-parallel passes (reciprocals before, NCO row after), on the main stream */
 int dy4_pipeline_profile(dy4_pipeline_t* p, int enable);
 int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long* launches, int reset);
+/* Census of the PLL's transcendental evaluations whose double result lay within 2 double-ulps of a float rounding boundary when
+ * it was narrowed to float (filter.cpp:200,216-217 narrow atan2 / cos / sin to float): the only evaluations on which a libm other
+ * than the reference's glibc could produce a different float.  One count per stream (table-driven PLL loop; streams on the direct
+ * loop and mono receivers report 0), accumulated since create / the last call with reset != 0.  h_counts: int32[n_streams]. */
+int dy4_pipeline_pll_risk(dy4_pipeline_t* p, int32_t* h_counts, int reset);
 /* total kernels launched by this library in this process */
 long long dy4_launch_count(void);
 

@@ -152,6 +152,17 @@ class CpuReceiver:
         self._f("idft")(C.c_void_p(Xf.ctypes.data), C.c_int(Xf.size), C.c_void_p(out.ctypes.data))
         return out
 
+    def fft(self, x, variant):
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.empty(x.size, np.complex64)
+        self._f("fft")(C.c_void_p(x.ctypes.data), C.c_int(x.size), C.c_int(variant), C.c_void_p(out.ctypes.data))
+        return out
+
+    def compute_twiddles(self, n_tw=256):
+        out = np.empty(n_tw, np.complex64)
+        self._f("compute_twiddles")(C.c_int(n_tw), C.c_void_p(out.ctypes.data))
+        return out
+
     def estimate_psd(self, samples, nfft, Fs):
         s = np.ascontiguousarray(samples, np.float32)
         freq, psd = np.empty(nfft // 2, np.float32), np.empty(nfft // 2, np.float32)

@@ -337,6 +337,47 @@ void DY4_FN(idft)(const float* Xf, int n, float* x)
     }
 }
 
+/* compute_twiddles, fourier.cpp:125-130 (NFFT = 512, include/dy4.h:18): the angle is a double expression of float(k), narrowed by
+ * the complex<float> constructor */
+void DY4_FN(compute_twiddles)(int n_tw, float* out)
+{
+    for (int k = 0; k < n_tw; k++) {
+        const float a = (float)(-2 * DY4_PI * (float)k / 512);
+        out[2 * k] = cosf(a); out[2 * k + 1] = sinf(a);
+    }
+}
+
+/* FFT_recursive :132-160 (variant 0), FFT_improved :162-187 (1), FFT_optimized :189-211 (2) — one restatement: the three run
+ * the same radix-2 decimation-in-time butterflies (even/odd recursion == bit-reversal + levels) and differ only in the value
+ * of a butterfly's twiddle: exp(i float(-2 PI float(k) / size)) computed per level (:152), or twiddles[k * 512/size] (:181, :203). */
+void DY4_FN(fft)(const float* x, int n, int variant, float* Xf)
+{
+    int levels = 0;
+    while ((1 << levels) < n) levels++;
+    for (int i = 0; i < n; i++) {                                   /* :194-196 / the recursion's even-odd splits */
+        int r = 0;
+        for (int b = 0; b < levels; b++) if (i & (1 << b)) r |= 1 << (levels - 1 - b);
+        Xf[2 * i] = x[2 * r]; Xf[2 * i + 1] = x[2 * r + 1];
+    }
+    for (int l = 0; l < levels; l++) {
+        const int half = 1 << l, size = 2 * half;
+        for (int p = 0; p < n; p += size)
+            for (int j = 0; j < half; j++) {
+                float a;
+                if (variant == 0) a = (float)(-2 * DY4_PI * (float)j / (size_t)size);               /* :152 */
+                else a = (float)(-2 * DY4_PI * (float)(j * (n / size)) / 512);                      /* :127 at index j * 2^(level-1) */
+                const float wr = cosf(a), wi = sinf(a);
+                const int k = p + j;
+                const float orr = Xf[2 * (k + half)], oi = Xf[2 * (k + half) + 1];
+                const float ac = wr * orr, bd = wi * oi, ad = wr * oi, bc = wi * orr;              /* __mulsc3 */
+                const float tr = ac - bd, ti = ad + bc;
+                const float er = Xf[2 * k], ei = Xf[2 * k + 1];
+                Xf[2 * k] = er + tr; Xf[2 * k + 1] = ei + ti;                                        /* :154 */
+                Xf[2 * (k + half)] = er - tr; Xf[2 * (k + half) + 1] = ei - ti;                      /* :155 */
+            }
+    }
+}
+
 void DY4_FN(estimate_psd)(const float* samples, long n, int nfft, int Fs, float* freq, float* psd)
 {
     const float df = (float)Fs / (float)nfft;                      /* :40 */

@@ -88,6 +88,10 @@ long DY4_FN(pipeline)(int mode, int stereo, const uint8_t* iq, long nbytes,
 void DY4_FN(dft)(const float* x, int n, float* Xf);
 void DY4_FN(idft)(const float* Xf, int n, float* x);
 void DY4_FN(estimate_psd)(const float* samples, long n, int nfft, int Fs, float* freq, float* psd);
+/* fourier.cpp:125-211: compute_twiddles (NFFT = 512) and the three radix-2 FFTs (variant 0 recursive, 1 improved, 2 optimized);
+ * complex vectors as interleaved (re, im) floats, n a power of two (n == 512 for variants 1 and 2) */
+void DY4_FN(compute_twiddles)(int n_tw, float* out);
+void DY4_FN(fft)(const float* x, int n, int variant, float* Xf);
 
 #ifdef __cplusplus
 }

@@ -230,4 +230,22 @@ void dy4r_estimate_psd(const float* samples, long n, int nfft, int Fs, float* fr
     std::memcpy(psd, p.data(), sizeof(float) * p.size());
 }
 
+/* variant 0: FFT_recursive, 1: FFT_improved (level 1), 2: FFT_optimized; twiddles from the reference's compute_twiddles (NFFT/2) */
+void dy4r_fft(const float* x, int n, int variant, float* Xf)
+{
+    std::vector<std::complex<float>> xv(n), X(n), tw(NFFT / 2);
+    for (int i = 0; i < n; i++) xv[i] = std::complex<float>(x[2 * i], x[2 * i + 1]);
+    compute_twiddles(tw);
+    if (variant == 0) FFT_recursive(xv, X);
+    else if (variant == 1) FFT_improved(xv, X, tw, 1);
+    else FFT_optimized(xv, X, tw);
+    for (int i = 0; i < n; i++) { Xf[2 * i] = X[i].real(); Xf[2 * i + 1] = X[i].imag(); }
+}
+void dy4r_compute_twiddles(int n_tw, float* out)
+{
+    std::vector<std::complex<float>> tw(n_tw);
+    compute_twiddles(tw);
+    for (int i = 0; i < n_tw; i++) { out[2 * i] = tw[i].real(); out[2 * i + 1] = tw[i].imag(); }
+}
+
 } /* extern "C" */

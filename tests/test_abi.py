@@ -127,3 +127,18 @@ def test_streaming_command_line_has_no_cpu_fallback(dy4):
     exe = os.path.join(dy4.PACKAGE_DIR, "dy4_project")
     p = subprocess.run([exe, "0", "stereo"], input=b"\x80" * 4096, capture_output=True, timeout=120)
     assert p.returncode == 2 and p.stdout == b"" and b"dy4_project:" in p.stderr     # refuses to run: no CUDA device
+
+
+def test_cmake_file_builds_the_same_library_for_sm_100a():
+    """north_star: 'CMakeLists builds for sm_100a with no Triton, no multi-backend dispatch and no CPU fallback'.  The file names
+    exactly the sources csrc/Makefile compiles and one architecture."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "CMakeLists.txt")).read()
+    assert "CMAKE_CUDA_ARCHITECTURES 100a" in txt and len(re.findall(r"CUDA_ARCHITECTURES", txt)) == 1
+    mk = open(os.path.join(root, "3dy4-real-time-software-defined-radio-_b200", "csrc", "Makefile")).read()
+    cu = re.search(r"^CU := (.*)$", mk, re.M).group(1).split()
+    for name in cu:
+        assert "/%s.cu" % name in txt, name
+    for name in ("dy4_taps.cpp", "filter_shim.cpp", "dy4_project.cpp"):
+        assert name in txt

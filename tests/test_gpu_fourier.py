@@ -64,3 +64,30 @@ def test_fourier_argument_checks(dy4):
         dy4.fourierh.DFT(np.zeros(4096, np.float32))                        # above the table limit
     with pytest.raises(Exception):
         dy4.fourierh.estimatePSD(np.zeros(100, np.float32), 512, 48000)     # fewer samples than one segment
+
+
+def test_fft_variants_golden_and_checker(dy4, checker):
+    """The reference's three FFTs (fourier.cpp:132-211) and its twiddle table (:125): bit-identical to the fixture minted from the
+    reference's own code and to the checker at other lengths; magnitudes equal to the DFT's as test/fft_unittest.cpp:53-91 asks;
+    the twiddle table is required where the reference requires it."""
+    g = golden("fourier.npz")
+    F = dy4.fourierh
+    tw = F.compute_twiddles()
+    assert np.array_equal(tw.view(np.uint32), g["twiddles"].view(np.uint32))
+    c512 = g["x512"].astype(np.complex64)
+    got = {"recursive": F.FFT_recursive(c512), "improved": F.FFT_improved(c512, tw, 1), "optimized": F.FFT_optimized(c512, tw)}
+    for name, X in got.items():
+        assert np.array_equal(X.view(np.uint32), g["F512_" + name].view(np.uint32)), name
+        assert np.abs(np.abs(X) - np.abs(F.DFT(g["x512"]))).max() < 2e-2
+    assert np.array_equal(F.FFT_recursive(g["x64"].astype(np.complex64)).view(np.uint32), g["F64_recursive"].view(np.uint32))
+    rng = np.random.Generator(np.random.PCG64(77))
+    for n in (1, 2, 8, 128, 1024, 2048):
+        x = (rng.uniform(-10, 10, n) + 1j * rng.uniform(-10, 10, n)).astype(np.complex64)
+        assert np.array_equal(F.FFT_recursive(x).view(np.uint32), checker.fft(x, 0).view(np.uint32)), n
+    x = (rng.uniform(-10, 10, 512) + 1j * rng.uniform(-10, 10, 512)).astype(np.complex64)
+    assert np.array_equal(F.FFT_improved(x, tw).view(np.uint32), checker.fft(x, 1).view(np.uint32))
+    assert np.array_equal(F.FFT_optimized(x, tw).view(np.uint32), checker.fft(x, 2).view(np.uint32))
+    with pytest.raises(Exception):
+        F.FFT_recursive(np.zeros(100, np.complex64))                  # radix 2 only
+    with pytest.raises(Exception):
+        F.FFT_optimized(np.zeros(1024, np.complex64), tw)             # table built for NFFT = 512

@@ -177,3 +177,31 @@ def test_spec_pll_certificates_randomised():
         probes, fc, dc, wrong, fc_not_dc = list(out)
         assert probes > 2_000_000 and wrong == 0 and fc_not_dc == 0, list(out)
         assert dc > fc > 0.1 * probes, list(out)
+
+
+def test_rate_change_matches_the_model(dy4, tmp_path):
+    """model/fmRateChange.py:43-66 re-rates fixture files with scipy.signal.resample_poly; dy4_b200.rate_change restates that
+    algorithm in numpy: same samples (1e-12) and the same output bytes, for every rate pair the reference's table offers from
+    2.4 MS/s, and through the command line."""
+    from scipy import signal
+    rc = dy4.rate_change
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 256, 2 * 6000, dtype=np.uint8)
+    iq = (raw - 128.0) / 128.0
+    for out_id in range(1, 7):
+        fs_in, fs_out = 2400 * 1000, rc.SAMPLE_RATE_TABLE[out_id] * 1000
+        g = np.gcd(fs_in, fs_out)
+        up, down = fs_out // g, fs_in // g
+        want_i = signal.resample_poly(iq[0::2], up, down)
+        got_i = rc.resample_poly(iq[0::2], up, down)
+        assert got_i.shape == want_i.shape and np.abs(got_i - want_i).max() < 1e-12, out_id
+        want = np.empty(2 * want_i.size, np.uint8)
+        want_q = signal.resample_poly(iq[1::2], up, down)
+        for k in range(want_i.size):                                  # the model's own loop, fmRateChange.py:57-59
+            want[2 * k] = np.uint8((128 + int(want_i[k] * 127)) & 0xff)
+            want[2 * k + 1] = np.uint8((128 + int(want_q[k] * 127)) & 0xff)
+        assert np.array_equal(rc.rate_change(raw, out_id, 0), want), out_id
+    f = tmp_path / "cap.raw"
+    raw.tofile(f)
+    assert rc.main(["rate_change", str(f), "4"]) == 0
+    assert np.array_equal(np.fromfile(tmp_path / "cap_1440.raw", dtype=np.uint8), rc.rate_change(raw, 4, 0))

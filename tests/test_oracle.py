@@ -279,3 +279,26 @@ def test_fourier_properties(orc):
     back = orc.idft(X)
     assert np.abs(back.real - x).max() < 1e-3 and np.abs(back.imag).max() < 1e-3
     assert rel_l2(np.stack([X.real, X.imag]), np.stack([np.fft.fft(x).real, np.fft.fft(x).imag])) < 1e-4
+
+
+def test_fft_oracle_matches_golden_and_reference(orc):
+    """fourier.cpp:125-211: the restatement of compute_twiddles and of the three radix-2 FFTs reproduces the fixture minted from the
+    reference's own code, bit for bit; as test/fft_unittest.cpp:53-91 checks, their magnitudes agree with the DFT's; and — where
+    oracle/_ref is built — the restatement equals the reference live at other lengths."""
+    import oracle
+    g = golden("fourier.npz")
+    c512 = g["x512"].astype(np.complex64)
+    assert np.array_equal(orc.compute_twiddles(256).view(np.uint32), g["twiddles"].view(np.uint32))
+    for v, name in enumerate(("recursive", "improved", "optimized")):
+        assert np.array_equal(orc.fft(c512, v).view(np.uint32), g["F512_" + name].view(np.uint32)), name
+        assert np.abs(np.abs(g["F512_" + name]) - np.abs(g["X512"])).max() < 2e-2          # |FFT| vs |DFT|: the unit test's comparison
+    assert np.array_equal(orc.fft(g["x64"].astype(np.complex64), 0).view(np.uint32), g["F64_recursive"].view(np.uint32))
+    if oracle.have_ref():
+        ref = oracle.load("ref")
+        rng = np.random.Generator(np.random.PCG64(9))
+        for n in (1, 2, 8, 128, 512, 2048):
+            x = (rng.uniform(-10, 10, n) + 1j * rng.uniform(-10, 10, n)).astype(np.complex64)
+            assert np.array_equal(orc.fft(x, 0).view(np.uint32), ref.fft(x, 0).view(np.uint32)), n
+        x = (rng.uniform(-10, 10, 512) + 1j * rng.uniform(-10, 10, 512)).astype(np.complex64)
+        for v in (1, 2):
+            assert np.array_equal(orc.fft(x, v).view(np.uint32), ref.fft(x, v).view(np.uint32)), v
