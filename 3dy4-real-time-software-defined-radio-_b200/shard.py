@@ -88,9 +88,58 @@ def sum_over_ranks(value, device="cpu"):
     return float(t.item())
 
 
+class SharedRows:
+    """The host-side gather of the path (the reference's sink is fwrite at src/project.cpp:317): ONE array
+    [n_streams, row_len] in POSIX shared memory, mapped by every rank and registered with CUDA as pinned memory, so each rank's
+    device->host copies land directly in its slice and rank 0 holds the whole batch's output after a barrier — no pickling, no
+    second copy, no collective.  `mine` is this rank's slice (rows lo..hi of the job), `all` the whole array."""
+
+    def __init__(self, name, n_streams, row_len, dtype, rank, world, pin=True):
+        import numpy as np
+        self.path = "/dev/shm/" + name
+        self.rank, self.world = rank, world
+        nbytes = int(n_streams) * int(row_len) * np.dtype(dtype).itemsize
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(max(nbytes, 1))
+        barrier()
+        self.all = np.memmap(self.path, dtype=dtype, mode="r+", shape=(int(n_streams), int(row_len)))
+        lo, hi = stream_range(n_streams, world, rank)
+        self.mine = self.all[lo:hi]
+        self._registered = False
+        if pin:
+            try:
+                import torch
+                if torch.cuda.is_available() and nbytes:
+                    rc = torch.cuda.cudart().cudaHostRegister(self.all.ctypes.data, nbytes, 0)
+                    self._registered = int(rc) == 0
+            except Exception:
+                self._registered = False
+        barrier()
+
+    @property
+    def pinned(self):
+        return self._registered
+
+    def close(self):
+        barrier()
+        if self._registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.all.ctypes.data)
+            self._registered = False
+        del self.mine
+        del self.all
+        barrier()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def gather_rows_to_rank0(rows, n_streams):
-    """Host-side gather of per-rank output rows (CPU tensor [n_local, L]) into [n_streams, L] on rank 0.
-    Not on the timed path; returns None on other ranks."""
+    """Host-side gather of per-rank output rows (CPU tensor [n_local, L]) into [n_streams, L] on rank 0 through
+    torch.distributed (pickled objects): a convenience for small results.  The timed path uses SharedRows."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):

@@ -238,7 +238,10 @@ def run_gpu_arm(args):
     # ---- end to end through the public host API: pinned host input, H2D + kernels + D2H PCM every step -----
     h_iq = torch.empty((S, nb * m.block_size), dtype=torch.uint8).pin_memory()
     h_iq.copy_(d_iq)
-    h_pcm = torch.empty((S, n_audio * nch), dtype=torch.int16).pin_memory()
+    # Output: ONE int16 array [all streams of the job][samples] in shared pinned host memory; each rank's device->host copies land
+    # in its slice, so after the barrier rank 0 holds the whole batch's PCM: that IS the path's host-side gather.
+    shared = shard.SharedRows("dy4_bench_pcm_%s" % os.environ.get("MASTER_PORT", str(os.getpid())), S * world, n_audio * nch, np.int16, rank, world)
+    h_pcm = torch.from_numpy(shared.mine)
     e2e_steps = max(1, min(args.steps, 5))
     pipe.reset()
     pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)   # warm-up (allocates staging)
@@ -248,7 +251,9 @@ def run_gpu_arm(args):
     for i in range(e2e_steps):                       # the streams continue from step to step, as in the device-resident leg
         pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)
     torch.cuda.synchronize(dev)
+    shard.barrier()                                  # every rank's slice has landed: rank 0 now holds the gathered PCM
     e2e_ms = shard.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+    gathered_ok = bool(rank != 0 or all(np.any(shared.all[r * S]) for r in range(world)))      # a row of every rank is there
     e2e_value = world * pairs_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
     # the two paths from the same starting state: identical PCM?
     pipe.reset()
@@ -257,6 +262,9 @@ def run_gpu_arm(args):
     pipe.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
     torch.cuda.synchronize(dev)
     pcm_matches = bool(torch.equal(h_pcm.to(dev), out["pcm"]))
+    gather_info = {"kind": "shared pinned host array (/dev/shm, cudaHostRegister): each rank's D2H copies land in its slice of rank 0's buffer",
+                   "pinned": shared.pinned, "bytes_total": int(S * world * n_audio * nch * 2), "inside_e2e_timing": True, "all_slices_present": gathered_ok}
+    shared.close()
 
     # ---- the timed path against the oracle (rank 0, two streams x 4 blocks from a fresh start): same bytes in, PCM out -----
     oracle_check = None
@@ -389,8 +397,8 @@ def run_gpu_arm(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": S * nb * m.block_size,
                 "d2h_bytes_per_step": S * n_audio * nch * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-                "timing": "host clock around the synchronous process_host() calls, max over ranks",
-                "pcm_equals_device_path": pcm_matches},
+                "timing": "host clock around the synchronous process_host() calls and the closing barrier, max over ranks",
+                "pcm_equals_device_path": pcm_matches, "gather": gather_info},
         "oracle_check": oracle_check,
         "signal": "periodic over one step: the streams continue from step to step without a jump" if periodic else "the same buffer again every step: a phase jump per step",
         "gpu_launches": total_launches,

@@ -58,13 +58,21 @@ dy4_b200.shard.barrier()
 t = dy4_b200.shard.max_over_ranks(10.0 + rank)
 tot = dy4_b200.shard.sum_over_ranks(hi - lo)
 full = dy4_b200.shard.gather_rows_to_rank0(rows, S)
+# the timed gather: every rank writes its slice of ONE shared array (on a GPU box: the target of its device->host copies)
+sh = dy4_b200.shard.SharedRows("dy4_test_gather_%%d" %% os.getppid(), S, rows.shape[1], np.int16, rank, world)
+sh.mine[:] = rows.numpy()
+dy4_b200.shard.barrier()
 if rank == 0:
     want = np.stack([o.pipeline(mode, 1, iq[s])["pcm"] for s in range(S)])
     assert t == 10.0 + world - 1 and tot == S, (t, tot)
     assert np.array_equal(full.numpy(), want)
+    assert np.array_equal(np.asarray(sh.all), want)
     print("OK")
 else:
     assert full is None
+path = sh.path
+sh.close()
+assert not os.path.exists(path)
 dist.destroy_process_group()
 '''
 
