@@ -436,6 +436,8 @@ struct Hooks { std::function<int(int, int, int)> before_front, after_back; };   
 // so that (a) only one block's FIR work and, on the host path, one block's upload precede the first PLL launch, and
 // every later upload (PCIe moves a block ~2x faster than the PLL consumes it) lands before it is needed, while
 // (b) most of the job runs in large launches (front-end wave balance, few PLL launches).  Mono: uniform sub-chunks.
+// (Ending the job on small sub-chunks as well — so that little follows the last serial loop — was measured: the two extra
+// launches cost more than the shorter tail saves, 7.34 against 7.20 ms per step.)
 std::vector<std::pair<int, int>> plan_subchunks(int n_blocks, int sb, bool geometric)
 {
     std::vector<std::pair<int, int>> v;

@@ -176,7 +176,7 @@ k_pll(const float* __restrict__ in, long long in_stride, const double* __restric
 // Table-driven PLL (dy4_plltab.h): predict -> table -> serial pick.  Bit-identical to k_pll by construction (every step
 // is either a pick among exactly evaluated candidates, certain under its error budget, or a direct evaluation).
 // ====================================================================================================================
-constexpr int PRED_SEG = 256;      // samples per predictor thread
+constexpr int PRED_SEG = 512;      // samples per predictor thread: 256 -> 7.20, 512 -> 6.91, 1024 -> 7.67 ms per step (latency of the thread's own chain vs redundant warm-up work)
 constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop forgets its state as 0.98657^k (1e-6 after 1024)
 
 // 1. predicted trigArg of every sample (double) -> theta row.  One thread per (stream, segment); the first WARM samples
@@ -337,6 +337,23 @@ __device__ __noinline__ float2 spec_direct_step(const float* __restrict__ x, int
     return make_float2(integ, phase);
 }
 
+// integ before step j of the group whose rows start at shared address `base`, from the state (gi, gp) before its step 0: the
+// chain's own arithmetic, step by step (runs only when a step of the group was not certain)
+__device__ __noinline__ float spec_replay_integ(unsigned base, int j, float gi, float gp)
+{
+    for (int i = 0; i < j; i++) {
+        const float4 A = spec_lds128(base + 32u * i);
+        float T;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(T) : "r"(base + 32u * i + 16u));
+        const float i_lo = __fadd_rn(gi, A.x), i_hi = __fadd_rn(gi, A.y);
+        const float p_lo = __fadd_rn(gp, __fadd_rn(A.z, i_lo)), p_hi = __fadd_rn(gp, __fadd_rn(A.w, i_hi));
+        const bool up = gp > T;
+        gi = up ? i_hi : i_lo;
+        gp = up ? p_hi : p_lo;
+    }
+    return gi;
+}
+
 // ====================================================================================================================
 // k_pll_sel: the serial loop.  Both candidates carried, the pick on the chain, its certificate OFF it.
 // One warp per stream, all lanes run the same chain.  Per step: both candidates' loop-filter updates (six float adds, the
@@ -434,7 +451,7 @@ k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __res
         const int nv = min(B, n_rows - r);
         const unsigned base = sm_ring + 16u * RQ * (unsigned)(r & (SPEC_R - 1));
         const float4 q = spec_lds128(base + 32u * (unsigned)lane + 16u);      // (t, tc_lo, tc_hi, hm) of this lane's step
-        unsigned cph = 0u, cig = 0u;
+        unsigned cph = 0u;
         float i0 = gi, p0 = gp;
 #pragma unroll
         for (int i = 0; i < B; i++) {
@@ -442,7 +459,6 @@ k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __res
             float T;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(T) : "r"(base + 32u * i + 16u));
             cph |= __float_as_uint(p0) & mask[i];
-            cig |= __float_as_uint(i0) & mask[i];
             const float i_lo = __fadd_rn(i0, A.x), i_hi = __fadd_rn(i0, A.y);                          // filter.cpp:207, both candidates
             const float p_lo = __fadd_rn(p0, __fadd_rn(A.z, i_lo)), p_hi = __fadd_rn(p0, __fadd_rn(A.w, i_hi));     // :210
             const bool up = p0 > T;                                                                    // trigArg rounds to the upper candidate
@@ -460,7 +476,9 @@ k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __res
         }
         const int j = bad ? __ffs(bad) - 1 : nv;                               // steps 0 .. j-1 are certain
         if (lane < j) *yp = myph;
-        const float pj = __uint_as_float(__shfl_sync(0xffffffffu, cph, j & 31)), ij = __uint_as_float(__shfl_sync(0xffffffffu, cig, j & 31));
+        // (integ, phaseEst) before step j: phaseEst is parked in lane j; integ is replayed from the group's start (rare path)
+        const float pj = __uint_as_float(__shfl_sync(0xffffffffu, cph, j & 31));
+        const float ij = spec_replay_integ(base, j, gi, gp);
         if (j == nv) { yp += j; r += j; gi = (j == B) ? i0 : ij; gp = (j == B) ? p0 : pj; continue; }      // the launch's last rows (nv < B)
         // step j directly, then on from behind it
         const int k = r + j;

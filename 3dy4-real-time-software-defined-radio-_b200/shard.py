@@ -135,6 +135,7 @@ class SharedRows:
                 os.unlink(self.path)
             except OSError:
                 pass
+        barrier()
 
 
 def gather_rows_to_rank0(rows, n_streams):

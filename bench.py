@@ -206,7 +206,7 @@ def run_gpu_arm(args):
         if RDS:
             pipe.rds_drain(raw=True)                 # symbols / bits / frame-sync events of this step, to the host
 
-    for i in range(args.warmup):
+    for i in range(args.warmup):                     # the streams start here (step 0 resets) ...
         step(i)
     torch.cuda.synchronize(dev)
 
@@ -220,8 +220,8 @@ def run_gpu_arm(args):
     shard.barrier()
     torch.cuda.synchronize(dev)
     e0.record()
-    for i in range(args.steps):
-        step(i)
+    for i in range(args.steps):                      # ... and simply continue through the timed region
+        step(args.warmup + i)
     e1.record()
     torch.cuda.synchronize(dev)
     shard.barrier()

@@ -8,7 +8,7 @@
 #include <string.h>
 #include "../../3dy4-real-time-software-defined-radio-_b200/csrc/dy4_plltab.h"
 
-#define SEG 256
+#define SEG 512
 #define WARM 1024
 
 /* the reference recurrence (filter.cpp:174-228) with glibc, same outputs */
