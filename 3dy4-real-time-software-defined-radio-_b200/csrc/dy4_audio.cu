@@ -267,6 +267,101 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
     }   // tile loop
 }
 
+// ---- U > 1, tap-stationary (the default) -------------------------------------------------------------------------
+// The kernel above reads TWO things from shared memory per multiply-add pair — a sample pair and a tap — and is bound by those
+// wavefronts.  But an output's phase, (m D) mod U, repeats every U outputs: a thread that only ever computes outputs m, m + S,
+// m + 2S, ... (S a multiple of U) needs ONE set of 101 taps, and keeps it in registers for the lifetime of a persistent CTA.
+// Shared memory then serves nothing but samples: one 8-byte (delayed IF, mixed) read per tap for both filters of an output.
+// Tile = P groups of S consecutive outputs of one stream; thread <-> slot in [0, S), visited P times; the span of input the tile
+// needs (S P D/U + 100 samples) is staged once.  Slots are dealt to lanes with the same K-interleave as above (lane l of a
+// warp takes every K-th output, K D/U within 0.05 of an odd integer), so the 8-byte reads of a half-warp fall on distinct bank
+// pairs; slots beyond 32 K G sit in one extra, partly filled warp.
+template <int NTMAX, bool EXACT, bool STEREO>
+__global__ void __launch_bounds__(NTMAX, 1)
+k_audio_poly_ts(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+                const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
+                const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
+                int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
+                const float* __restrict__ taps_poly, int up_pad, int K, int KG, int S, int P, int tiles_per_stream, int n_tiles)
+{
+    const int NT = blockDim.x;
+    extern __shared__ __align__(16) float sm_f[];
+    constexpr int DELAY = DY4_NTAPS / 2;
+    float2* s_x = reinterpret_cast<float2*>(sm_f);                          // (delayed IF, mixed) over the tile's span
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = warp < KG ? 32 * K * (warp / K) + lane * K + (warp % K) : 32 * KG + (tid - 32 * KG);
+    const bool live = slot < S;
+    // this thread's phase and taps: (slot D) mod U, h[phase + j U] (taps_poly is the transposed table [tap j][phase])
+    float h[DY4_NTAPS];
+    {
+        const int phase = live ? (int)(((long long)slot * down) % up) : 0;
+#pragma unroll
+        for (int j = 0; j < DY4_NTAPS; j++) h[j] = live ? __ldg(taps_poly + (long long)j * up_pad + phase) : 0.0f;
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s = tile / tiles_per_stream;
+        const int m0 = (tile - s * tiles_per_stream) * S * P;
+        __syncthreads();                                                    // the previous tile's span is no longer read
+        const float* row = if_in + (long long)s * if_stride;
+        const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+        const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
+        const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
+        const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
+        const int m_last = min(m0 + S * P, n_audio) - 1;
+        const int i_lo = ((int)(((long long)m0 * down) / up) - (DY4_NTAPS - 1)) & ~3;   // aligned down: 16-byte loads below
+        const int i_hi = (int)(((long long)m_last * down) / up);
+        const int span = i_hi - i_lo + 1;
+        for (int p = 4 * tid; p < span; p += 4 * NT) {
+            const int i = i_lo + p;
+            float x0, x1, x2, x3, y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+            if (i - DELAY >= 0 && i + 3 < n_if) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(row + i - DELAY));
+                const float2 b = __ldg(reinterpret_cast<const float2*>(row + i - DELAY + 2));
+                x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
+                if (STEREO) {
+                    const float4 nv = __ldg(reinterpret_cast<const float4*>(nrow + i));
+                    const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + i));
+                    y0 = __fmul_rn(__fmul_rn(nv.x, sv.x), 2.0f); y1 = __fmul_rn(__fmul_rn(nv.y, sv.y), 2.0f);     // filter.cpp:264
+                    y2 = __fmul_rn(__fmul_rn(nv.z, sv.z), 2.0f); y3 = __fmul_rn(__fmul_rn(nv.w, sv.w), 2.0f);
+                }
+            } else {
+                x0 = if_at(row, itail, n_if, i - DELAY); x1 = if_at(row, itail, n_if, i + 1 - DELAY);
+                x2 = if_at(row, itail, n_if, i + 2 - DELAY); x3 = if_at(row, itail, n_if, i + 3 - DELAY);
+                if (STEREO) {
+                    y0 = mix_at(nrow, srow, mtail, n_if, i); y1 = mix_at(nrow, srow, mtail, n_if, i + 1);
+                    y2 = mix_at(nrow, srow, mtail, n_if, i + 2); y3 = mix_at(nrow, srow, mtail, n_if, i + 3);
+                }
+            }
+            float4* d = reinterpret_cast<float4*>(s_x + p);
+            d[0] = make_float4(x0, y0, x1, y1);
+            d[1] = make_float4(x2, y2, x3, y3);
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int q = 0; q < P; q++) {
+            const int m = m0 + q * S + slot;
+            if (m >= n_audio) break;
+            const int base = (int)(((long long)m * down) / up) - i_lo;      // position of x[floor(m D/U)] in the span
+            const float2* xs = s_x + base;
+            float mono = 0.0f, diff = 0.0f;
+#pragma unroll
+            for (int j = 0; j < DY4_NTAPS; j++) {                           // ascending taps, as filter.cpp:159-165
+                const float2 v = xs[-j];
+                if (EXACT) { mono = __fadd_rn(mono, __fmul_rn(h[j], v.x)); if (STEREO) diff = __fadd_rn(diff, __fmul_rn(h[j], v.y)); }
+                else { mono = fmaf(h[j], v.x, mono); if (STEREO) diff = fmaf(h[j], v.y, diff); }
+            }
+            if (STEREO) {
+                const float l = __fadd_rn(mono, diff), r = __fsub_rn(mono, diff);
+                if (audio) *reinterpret_cast<float2*>(audio + (long long)s * audio_stride + 2LL * m) = make_float2(l, r);
+                if (pcm) *reinterpret_cast<uint32_t*>(pcm + (long long)s * pcm_stride + 2LL * m) = (uint16_t)pcm16(l) | ((uint32_t)(uint16_t)pcm16(r) << 16);
+            } else {
+                if (audio) audio[(long long)s * audio_stride + m] = mono;
+                if (pcm) pcm[(long long)s * pcm_stride + m] = pcm16(mono);
+            }
+        }
+    }
+}
+
 template <int D, int R, int NT, bool EXACT, bool STEREO>
 cudaError_t launch_u1(const Dy4AudioArgs& a, cudaStream_t st)
 {
@@ -319,6 +414,46 @@ cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
         k_up = a.up; k_down = a.down;
     }
     const int K = k_best;
+    // measured (1 024 streams x 12 blocks, whole-job launch): 147/800 1.07 ms against 1.15 ms for the table-in-shared-memory kernel;
+    // 147/1280 1.52 against 1.33 ms (its tile holds one group only: staging is not overlapped with anything) — so each ratio takes its best
+    const bool prefer_ts = a.poly_variant == 0 ? (long long)a.down * 100 < (long long)a.up * 700 : a.poly_variant == 2;
+    if (a.n_if % a.down == 0 && (a.n_audio % a.up) == 0 && prefer_ts) {
+        // tap-stationary kernel: whole periods per chunk (every chunk of whole blocks is: a block is 10 periods in both modes)
+        constexpr int NTS = 512;
+        int best_L = 0, best_G = 0, best_extra = 0, best_nt = 1 << 30;
+        for (int L = 1; L <= 4; L++) {
+            const int Sx = a.up * L;
+            const int G = Sx / (32 * K), rest = Sx - 32 * K * G;
+            const int extra = rest > 0 ? (rest <= 32 ? 1 : -1) : 0;
+            const int nt = extra < 0 ? 32 * K * (G + 1) : 32 * (K * G + extra);
+            const int g_eff = extra < 0 ? G + 1 : G;
+            if (nt > NTS) continue;
+            // waste = idle threads per output slot
+            if (best_L == 0 || (long long)(nt - Sx) * (a.up * best_L) < (long long)(best_nt - a.up * best_L) * Sx) { best_L = L; best_G = g_eff; best_extra = extra > 0; best_nt = nt; }
+        }
+        if (best_L) {
+            const int S = a.up * best_L, KG = K * best_G, NT = best_nt;
+            int P = std::max(1, (int)(6400LL * a.up / ((long long)S * a.down)));          // ~6 400 staged samples per tile (51 KB)
+            const int span_max = ((int)(((long long)(S * P) * a.down) / a.up) + DY4_NTAPS + 3 + 4 + 7) & ~3;
+            const size_t smem = sizeof(float2) * (size_t)span_max;
+            auto kern = k_audio_poly_ts<NTS, EXACT, STEREO>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            static int sms = 0;
+            if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+            int per_sm = 1;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+            if (e != cudaSuccess) return e;
+            const int tiles_per_stream = (a.n_audio + S * P - 1) / (S * P);
+            const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
+            if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+            const int grid = (int)std::min<long long>(n_tiles, (long long)sms * std::max(per_sm, 1));
+            kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride, a.pcm, a.pcm_stride,
+                                         a.n_if, a.n_audio, a.up, a.down, a.taps_poly, a.up_pad, K, KG, S, P, tiles_per_stream, (int)n_tiles);
+            g_dy4_launches++;
+            return cudaGetLastError();
+        }
+    }
     const int NT = 32 * K * 2;                         // one 59 KB tap table per CTA, amortised over 64*K outputs
     const int span_max = ((int)(((long long)(NT - 1) * a.down) / a.up) + DY4_NTAPS + 3 + 4 + 7) & ~3;
     const size_t smem = sizeof(float) * ((size_t)DY4_NTAPS * a.up_pad + 2 * (size_t)span_max);

@@ -53,6 +53,7 @@ struct Dy4AudioArgs {
     int mode;                                                   // U==1: selects the (h,h) audio low-pass table
     const float* taps_poly;                                     // U>1: device [101][up_pad] polyphase taps, taps_poly[j*up_pad+phase] = h[phase + j*up]
     int up_pad;
+    int poly_variant = 0;                                       // U>1: 0 the better of the two per ratio, 1 the table-in-shared-memory kernel, 2 the tap-stationary kernel
     unsigned long long neg_zero2;
 };
 
