@@ -46,16 +46,17 @@ struct dy4_pipeline {
     float* d_rf_taps = nullptr;
     float* d_taps_poly = nullptr;
     int up_pad = 0;
-    // carried state.  if_tail is a ring of three slots: sub-chunk c reads slot c%3 and leaves slot (c+1)%3 for its
-    // successor, so the front end of c+1 / c+2 can run (under the PLL of c) before the audio kernel of c has read its slot.
+    // carried state.  if_tail is a ring of NSETS + 1 slots: sub-chunk c reads slot c % (NSETS+1) and leaves the next one for its
+    // successor, so the front ends of the sub-chunks ahead can run (under the PLL of c) before the audio kernel of c has read its slot.
     uint8_t* iq_tail = nullptr; float* if_tail = nullptr; float* mix_tail = nullptr; float* pll_state = nullptr;
     long long seq = 0;                               // sub-chunks processed so far: selects the if_tail slot
-    // workspace: two sets, sub-chunk c uses set c&1
+    // workspace: NSETS sets, sub-chunk c uses set c % NSETS
     struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
-    WorkSet ws[2];
+    static constexpr int NSETS = 3;                  // front(c+2) may run before back(c): the main stream works two sub-chunks ahead of the serial loop
+    WorkSet ws[NSETS];
     float* ws_nco0 = nullptr;
     int* pll_risk = nullptr;                         // [n_streams]: near-tie narrowings seen by the PLL table kernel (dy4_pipeline_pll_risk)
-    double* pred_state = nullptr;                    // table-driven PLL: the predictor's own state, [2][n_streams][8], then [2][n_streams] turns
+    double* pred_state = nullptr;                    // table-driven PLL: the predictor's own state, [NSETS][n_streams][8], then [NSETS][n_streams] turns
     size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
     // RDS filtering front end (DY4_FLAG_RDS): its own stream beside the stereo PLL
     float *rds_f = nullptr, *rds_carrier = nullptr, *rds_nco_i = nullptr, *rds_nco_q = nullptr, *rds_lp = nullptr, *rds_out = nullptr;
@@ -68,11 +69,12 @@ struct dy4_pipeline {
     int8_t *rds_sym = nullptr, *rds_bits = nullptr;
     size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0, rds_grp_cap = 0;
     long long rds_blocks_since_drain = 0;
-    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[2] = {nullptr, nullptr};
+    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[NSETS] = {};
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
-    cudaEvent_t ev_bpf[2] = {nullptr, nullptr}, ev_pll[2] = {nullptr, nullptr}, ev_in = nullptr, ev_prep1 = nullptr;
+    cudaStream_t s_aux = nullptr;                    // the PLL's time-parallel FP64 kernels (prediction, table) run here, beside the FP32-bound FIR kernels
+    cudaEvent_t ev_bpf[NSETS] = {}, ev_pll[NSETS] = {}, ev_prep[NSETS] = {}, ev_in = nullptr, ev_prep1 = nullptr;
     // host-facing staging
     uint8_t* d_stage = nullptr; int16_t* d_pcm_stage = nullptr; float* d_audio_stage = nullptr;
     int stage_blocks = 0; bool stage_audio = false;
@@ -135,7 +137,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
 {
     const size_t S = (size_t)p->n_streams;
     CU(cudaMemsetAsync(p->iq_tail, 128, S * DY4_IQ_TAIL, st));            // byte 128 = 0.0f: zero RF history (project.cpp:242-243)
-    CU(cudaMemsetAsync(p->if_tail, 0, 3 * S * DY4_IF_TAIL * sizeof(float), st));
+    CU(cudaMemsetAsync(p->if_tail, 0, (dy4_pipeline::NSETS + 1) * S * DY4_IF_TAIL * sizeof(float), st));
     p->seq = 0;
     p->pll_fresh = true;
     CU(cudaMemsetAsync(p->mix_tail, 0, S * DY4_MIX_TAIL * sizeof(float), st));
@@ -200,7 +202,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     }
     p->ws_stride = (size_t)blocks * p->mp.if_per_block;
     const size_t bytes = (size_t)p->n_streams * p->ws_stride * sizeof(float);
-    for (int i = 0; i < (p->stereo ? 2 : 1); i++) {
+    for (int i = 0; i < (p->stereo ? dy4_pipeline::NSETS : 1); i++) {
         auto& w = p->ws[i];
         CU(cudaMalloc(&w.w_if, bytes));
         if (p->stereo) {
@@ -213,13 +215,15 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 512 * sizeof(float4)));
         }
     }
-    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 6 * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
+    if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 3 * dy4_pipeline::NSETS * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
     if (p->pll_table && !p->pll_risk) { CU(cudaMalloc(&p->pll_risk, (size_t)p->n_streams * sizeof(int))); CU(cudaMemset(p->pll_risk, 0, (size_t)p->n_streams * sizeof(int))); }
-    if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, 2 * (size_t)p->n_streams * 9 * sizeof(double)));   // [2][S][8] predictor state + [2][S] turns
+    if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));   // [NSETS][S][8] predictor state + [NSETS][S] turns
     if (p->stereo && !p->s_pll) {
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        CU(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
+        for (int i = 0; i < dy4_pipeline::NSETS; i++) {
             CU(cudaEventCreateWithFlags(&p->ev_bpf[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_prep[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_pll[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
@@ -236,8 +240,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&p->ev_rds_set[0], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&p->ev_rds_set[1], cudaEventDisableTiming));
+            for (int i = 0; i < dy4_pipeline::NSETS; i++) CU(cudaEventCreateWithFlags(&p->ev_rds_set[i], cudaEventDisableTiming));
         }
     }
     p->ws_blocks = blocks;
@@ -264,7 +267,7 @@ struct SubChunk {                        // one sub-chunk of the job: where its 
     int pred_carry = 0;                  // table-driven PLL: the prediction continues from the previous sub-chunk's (not the first of a call)
 };
 
-float* if_tail_slot(dy4_pipeline* p, long long seq) { return p->if_tail + (size_t)(seq % 3) * p->n_streams * DY4_IF_TAIL; }
+float* if_tail_slot(dy4_pipeline* p, long long seq) { return p->if_tail + (size_t)(seq % (dy4_pipeline::NSETS + 1)) * p->n_streams * DY4_IF_TAIL; }
 
 // front half on the main stream: uint8 IQ -> IF -> (pilot, stereo band); leaves the IQ and IF history for the successor
 int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_out_stride, cudaStream_t st)
@@ -393,11 +396,11 @@ int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
     pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
-    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.risk = p->pll_risk; pa.tstart = p->ws_nco0 + (size_t)(2 + c.set) * p->n_streams;
+    pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.risk = p->pll_risk; pa.tstart = p->ws_nco0 + (size_t)(dy4_pipeline::NSETS + c.set) * p->n_streams;
     if (w.tab) {
-        pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)(c.set ^ 1) * p->n_streams * 8;
-        pa.need = p->pred_state + (size_t)(16 + c.set) * p->n_streams;
-        pa.pred_carry = c.pred_carry; pa.fresh = c.fresh; pa.nco0b = p->ws_nco0 + (size_t)(4 + c.set) * p->n_streams;
+        pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)((c.set + dy4_pipeline::NSETS - 1) % dy4_pipeline::NSETS) * p->n_streams * 8;
+        pa.need = p->pred_state + (size_t)(8 * dy4_pipeline::NSETS + c.set) * p->n_streams;      // written by the loop NSETS launches back, complete by now
+        pa.pred_carry = c.pred_carry; pa.fresh = c.fresh; pa.nco0b = p->ws_nco0 + (size_t)(2 * dy4_pipeline::NSETS + c.set) * p->n_streams;
     }
     pa.freq = 19e3f; pa.Fs = m.if_Fs; pa.ncoScale = 2.0f; pa.phaseAdjust = 0.0f; pa.normBandwidth = 0.01f;   // project.cpp:99-102
     { Timer t(p, (parts & DY4_PLL_LOOP) ? DY4_K_PLL : DY4_K_PLL_AUX, st); CU(dy4_launch_pll_parts(pa, st, parts)); }
@@ -474,7 +477,7 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         c.pcm = d_pcm ? d_pcm + (size_t)b * m.audio_per_block * ch : nullptr;
         c.audio = d_audio ? d_audio + (size_t)b * m.audio_per_block * ch : nullptr;
         c.d_if = d_if ? d_if + (size_t)b * m.if_per_block : nullptr;
-        c.set = p->stereo ? (int)(seq & 1) : 0;
+        c.set = p->stereo ? (int)(seq % dy4_pipeline::NSETS) : 0;
         c.if_tail_in = if_tail_slot(p, seq);
         c.if_tail_out = if_tail_slot(p, seq + 1);
         return c;
@@ -490,17 +493,30 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         }
         return DY4_OK;
     }
-    // stereo: software pipeline.  main stream:  front(0) | front(1) back(0) | front(2) back(1) | ... | back(last)
-    //                             PLL stream:            pll(0)         | pll(1)          | ...
-    // front(c+1) is queued before back(c), so it runs while pll(c) does; buffers of set c&1 are next written by
-    // front(c+2), which is queued after back(c) (their last reader), and back(c) has waited for pll(c).
+    // stereo: software pipeline over three streams and NSETS = 3 workspace sets.
+    //   main stream:  front(0) front(1) front(2) back(0) front(3) back(1) ...  back(last)      FIR kernels; NCO row + audio
+    //   aux stream:          prep(0)  prep(1)  prep(2) ...                                      prediction + table (FP64)
+    //   PLL stream:                  loop(0)   loop(1)   loop(2) ...                            the serial loops, back to back
+    // front(c) -> prep(c) -> loop(c) -> back(c) by events; the main stream runs up to two sub-chunks ahead of the loop, so the
+    // geometric growth of the sub-chunks (front + prep of c+1 is twice the work of c's) does not leave the PLL stream waiting.
+    // The buffers of set c % 3 are next written by front(c+3), queued after back(c), their last reader.
     CU(cudaEventRecord(p->ev_in, st));
     CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
     const bool fresh_call = p->pll_fresh;              // no sample processed since create / reset: the streams start in this call
     p->pll_fresh = false;
-    SubChunk prev{};
-    bool have_prev = false;
-    int prev_b = 0, prev_i = 0;
+    // back halves still to be queued (at most NSETS - 1 of them): back(c) follows front(c + NSETS - 1) on the main stream
+    struct Pending { SubChunk c; int b, i; };
+    std::vector<Pending> pend;
+    auto flush_back = [&]() -> int {
+        const Pending q = pend.front();
+        pend.erase(pend.begin());
+        CU(cudaStreamWaitEvent(st, p->ev_pll[q.c.set], 0));
+        int r2;
+        if ((r2 = run_pll(p, q.c, st, DY4_PLL_NCO))) return r2;
+        if ((r2 = run_back(p, q.c, pcm_stride, audio_stride, st))) return r2;
+        if (hooks && (r2 = hooks->after_back(q.i, q.b, q.c.nb))) return r2;
+        return DY4_OK;
+    };
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
         const int b = plan[i].first;
         SubChunk c = sub(b, plan[i].second, p->seq);
@@ -518,10 +534,9 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         const bool prep_on_pll = p->pll_table && i == 1 && fresh_call;
         if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
         // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
-        if ((p->flags & DY4_FLAG_RDS) && i >= 2) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
+        if ((p->flags & DY4_FLAG_RDS) && i >= (size_t)dy4_pipeline::NSETS) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
         if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
-        if (p->pll_table && i == 2 && fresh_call) CU(cudaStreamWaitEvent(st, p->ev_prep1, 0));
-        if (!prep_on_pll && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;
+        if (!p->pll_table && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;   // direct loop: its reciprocal pre-pass rides with the FIR kernels
         CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
             CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
@@ -529,7 +544,16 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
             CU(cudaEventRecord(p->ev_rds_set[c.set], p->s_rds));
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
-        CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
+        if (p->pll_table && !prep_on_pll) {
+            // prediction + table on the AUX stream: FP64-bound, they run beside the FP32-bound FIR kernels of the next sub-chunk
+            // (which the main stream goes on to queue) instead of in line with them.  Ordering: they read the pilot row front(c)
+            // just wrote; the previous prediction (same stream) and, two launches back, the loop's turn report are complete.
+            CU(cudaStreamWaitEvent(p->s_aux, p->ev_bpf[c.set], 0));
+            if (i == 2 && fresh_call) CU(cudaStreamWaitEvent(p->s_aux, p->ev_prep1, 0));
+            if ((rc = run_pll(p, c, p->s_aux, DY4_PLL_PREP))) return rc;
+            CU(cudaEventRecord(p->ev_prep[c.set], p->s_aux));
+            CU(cudaStreamWaitEvent(p->s_pll, p->ev_prep[c.set], 0));
+        } else CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
         if (prep_on_pll) {
             // prediction + table of sub-chunk 1 from the exact state loop(0) leaves; the prediction of sub-chunk 2 (main
             // stream) continues from this one's state, so it waits for it
@@ -538,20 +562,10 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         }
         if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_LOOP))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
-        if (have_prev) {
-            CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
-            if ((rc = run_pll(p, prev, st, DY4_PLL_NCO))) return rc;
-            if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
-            if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
-        }
-        prev = c; have_prev = true; prev_b = b; prev_i = (int)i;
+        pend.push_back({c, b, (int)i});
+        if ((int)pend.size() >= dy4_pipeline::NSETS && (rc = flush_back())) return rc;
     }
-    if (have_prev) {
-        CU(cudaStreamWaitEvent(st, p->ev_pll[prev.set], 0));
-        if ((rc = run_pll(p, prev, st, DY4_PLL_NCO))) return rc;
-        if ((rc = run_back(p, prev, pcm_stride, audio_stride, st))) return rc;
-        if (hooks && (rc = hooks->after_back(prev_i, prev_b, prev.nb))) return rc;
-    }
+    while (!pend.empty()) if ((rc = flush_back())) return rc;
     if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
     return DY4_OK;
 }
@@ -612,7 +626,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
         CU(cudaMalloc(&p->rds_counts, S * 4 * sizeof(int)));
     }
     CU(cudaMalloc(&p->iq_tail, S * DY4_IQ_TAIL));
-    CU(cudaMalloc(&p->if_tail, 3 * S * DY4_IF_TAIL * sizeof(float)));
+    CU(cudaMalloc(&p->if_tail, (dy4_pipeline::NSETS + 1) * S * DY4_IF_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->mix_tail, S * DY4_MIX_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->pll_state, S * 8 * sizeof(float)));
     int rc = init_state(p, nullptr);
@@ -648,13 +662,14 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
     cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
     cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_groups); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
-    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); cudaEventDestroy(p->ev_rds_set[0]); cudaEventDestroy(p->ev_rds_set[1]); }
+    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); for (int i = 0; i < dy4_pipeline::NSETS; i++) cudaEventDestroy(p->ev_rds_set[i]); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
     cudaFree(p->ws_nco0); cudaFree(p->pred_state); cudaFree(p->pll_risk);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
-        for (int i = 0; i < 2; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); }
+        if (p->s_aux) cudaStreamDestroy(p->s_aux);
+        for (int i = 0; i < dy4_pipeline::NSETS; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); if (p->ev_prep[i]) cudaEventDestroy(p->ev_prep[i]); }
         if (p->ev_prep1) cudaEventDestroy(p->ev_prep1);
         cudaEventDestroy(p->ev_in);
     }

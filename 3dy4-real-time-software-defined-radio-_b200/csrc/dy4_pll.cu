@@ -179,7 +179,8 @@ k_pll(const float* __restrict__ in, long long in_stride, const double* __restric
 constexpr int PRED_SEG = 512;      // samples per predictor thread: 256 -> 7.20, 512 -> 6.91, 1024 -> 7.67 ms per step (latency of the thread's own chain vs redundant warm-up work)
 constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop forgets its state as 0.98657^k (1e-6 after 1024)
 
-// 1. predicted trigArg of every sample (double) -> theta row.  One thread per (stream, segment); the first WARM samples
+// 1. predicted phaseEst of every sample (a float: |phaseEst| is a few radians, so its 2^-24 relative precision is far below the
+// float grid of trigArg = w*T + phaseEst it is used to locate) -> the theta row.  One thread per (stream, segment); the first WARM samples
 // of a launch start from the exact carried state, later segments from that state as a guess plus the warm-up.
 // `pred_in` / `pred_out`: [n_streams][8] doubles (integ, phase, sample counter after / before the launch, turns) — the
 // predictor's own state at the start / end of the launch.  carry == 0: the launch starts from the exact carried PLL
@@ -190,7 +191,7 @@ constexpr int PRED_WARM = 1024;    // warm-up steps before a segment: the loop f
 // prediction was off (`need`, k_pll_sel), and with carry == 2 the launch two later shifts its start by that much.
 __global__ void __launch_bounds__(128)
 k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __restrict__ state, const double* __restrict__ pred_in,
-              double* __restrict__ pred_out, const double* __restrict__ need, int carry, double* __restrict__ th_hat, long long wide_stride,
+              double* __restrict__ pred_out, const double* __restrict__ need, int carry, float* __restrict__ ph_hat, long long ph_stride,
               int n, PllConst c)
 {
     const int s = blockIdx.x;
@@ -198,7 +199,7 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
     if (s0 >= n) return;
     const float* st = state + (long long)s * 8;
     const float* x = in + (long long)s * in_stride;
-    double* y = th_hat + (long long)s * wide_stride;
+    float* y = ph_hat + (long long)s * ph_stride;          // predicted phaseEst, as a float: the table kernel adds RN_d(w*T) back
     const double Kp = (double)c.Kp, Ki = (double)c.Ki;
     double integ, phase, T0, turns = 0.0;
     if (carry) {
@@ -213,18 +214,15 @@ k_pll_predict(const float* __restrict__ in, long long in_stride, const float* __
     int k = kw;
     for (; k + 4 <= k1; k += 4) {                                   // kw, s0 are multiples of 4; rows are 16-byte aligned
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + k));
-        const double t0 = th_prev = dy4_pred_step(v.x, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase);
-        const double t1 = th_prev = dy4_pred_step(v.y, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 2)), Kp, Ki, &integ, &phase);
-        const double t2 = th_prev = dy4_pred_step(v.z, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 3)), Kp, Ki, &integ, &phase);
-        const double t3 = th_prev = dy4_pred_step(v.w, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 4)), Kp, Ki, &integ, &phase);
-        if (k >= s0) {
-            *reinterpret_cast<double2*>(y + k) = make_double2(t0, t1);
-            *reinterpret_cast<double2*>(y + k + 2) = make_double2(t2, t3);
-        }
+        th_prev = dy4_pred_step(v.x, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase); const float p0 = (float)phase;
+        th_prev = dy4_pred_step(v.y, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 2)), Kp, Ki, &integ, &phase); const float p1 = (float)phase;
+        th_prev = dy4_pred_step(v.z, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 3)), Kp, Ki, &integ, &phase); const float p2 = (float)phase;
+        th_prev = dy4_pred_step(v.w, th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 4)), Kp, Ki, &integ, &phase); const float p3 = (float)phase;
+        if (k >= s0) *reinterpret_cast<float4*>(y + k) = make_float4(p0, p1, p2, p3);
     }
     for (; k < k1; k++) {
         th_prev = dy4_pred_step(__ldg(x + k), th_prev, __dmul_rn(c.w, dy4_pll_count(T0, k + 1)), Kp, Ki, &integ, &phase);
-        if (k >= s0) y[k] = th_prev;
+        if (k >= s0) y[k] = (float)phase;
     }
     if (k1 == n) {                                                  // the thread of the last segment: state for the next launch
         pred_out[8 * s] = integ; pred_out[8 * s + 1] = phase; pred_out[8 * s + 2] = dy4_pll_count(T0, n); pred_out[8 * s + 3] = T0;
@@ -304,7 +302,7 @@ constexpr int SPEC_R = SPEC_SG * SPEC_SLOTS;         // ring size in rows
 // step cost the lone warp 39.8 instead of 26.5 ns per sample — issue slots, not bytes, are what the serial loop is short of.)
 __global__ void __launch_bounds__(128)
 k_pll_table_ops(const float* __restrict__ in, long long in_stride, const double* __restrict__ pred_out,
-                const double* __restrict__ th_hat, long long wide_stride, float4* __restrict__ tab, long long tab_stride, int* __restrict__ risk, int n, PllConst c)
+                const float* __restrict__ ph_hat, long long ph_stride, float4* __restrict__ tab, long long tab_stride, int* __restrict__ risk, int n, PllConst c)
 {
     const int s = blockIdx.x;
     const int k = blockIdx.y * blockDim.x + threadIdx.x;
@@ -313,7 +311,8 @@ k_pll_table_ops(const float* __restrict__ in, long long in_stride, const double*
     const float* x = in + (long long)s * in_stride;
     dy4_row16_t r;
     int rk = 0;                                                     // evaluations of this row that narrow a near-tie (dy4_near_float_tie)
-    dy4_tab_make_row16_r(__ldg(th_hat + (long long)s * wide_stride + k), __dmul_rn(c.w, dy4_pll_count(T0, k + 1)),
+    const double wT = __dmul_rn(c.w, dy4_pll_count(T0, k + 1));
+    dy4_tab_make_row16_r(wT + (double)__ldg(ph_hat + (long long)s * ph_stride + k), wT,
                        k + 1 < n ? __ldg(x + k + 1) : 0.0f, k + 1 < n, T0 + (double)k < (double)DY4_TAB_EARLY, &r, nullptr, nullptr, &rk);
     if (rk && risk) atomicAdd(risk + s, rk);                        // ~1e-8 per evaluation
     const bool ph = (dy4_d2u_bits(r.t) & 1ull) != 0;                // the predicted candidate is the upper one
@@ -632,8 +631,8 @@ cudaError_t dy4_launch_pll_parts(const Dy4PllArgs& a, cudaStream_t st, int parts
         if (parts & DY4_PLL_PREP) {                          // time-parallel: may run beside the serial loop of the previous launch
             const int nseg = (a.n + PRED_SEG - 1) / PRED_SEG;
             k_pll_predict<<<dim3(a.n_streams, (nseg + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.state, a.pred_in, a.pred_out, a.need, a.pred_carry,
-                                                                                 a.theta, a.wide_stride, a.n, c);
-            k_pll_table_ops<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, a.theta, a.wide_stride, a.tab, a.tab_stride, a.risk, a.n, c);
+                                                                                 reinterpret_cast<float*>(a.theta), 2 * a.wide_stride, a.n, c);
+            k_pll_table_ops<<<dim3(a.n_streams, (a.n + 127) / 128), 128, 0, st>>>(a.in, a.in_stride, a.pred_out, reinterpret_cast<const float*>(a.theta), 2 * a.wide_stride, a.tab, a.tab_stride, a.risk, a.n, c);
             g_dy4_launches += 2;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;

@@ -57,7 +57,7 @@ void pllspec_launch_carry(const float* x, int n, float* state, double w, float K
         double th_prev = w * dy4_pll_count(T0, kw) + phase;
         for (int k = kw; k < s0 + SEG && k < n; k++) {
             th_prev = dy4_pred_step(x[k], th_prev, DY4_MUL(w, dy4_pll_count(T0, k + 1)), (double)Kp, (double)Ki, &integ, &phase);
-            if (k >= s0) th_hat[k] = th_prev;
+            if (k >= s0) th_hat[k] = DY4_MUL(w, dy4_pll_count(T0, k + 1)) + (double)(float)phase;      /* k_pll_predict stores phaseEst as a float; k_pll_table_ops adds RN_d(w*T) back */
         }
         if (s0 + SEG >= n) { pred[0] = integ; pred[1] = phase; pred[2] = dy4_pll_count(T0, n); pred[3] = T0; }
     }
