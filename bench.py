@@ -40,9 +40,11 @@ FP32_PEAK_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45: SMs x la
 # Measured ceiling of the BIT-EXACT multiply-add (FFMA2(x,h,-0) then FADD2: two packed instructions on the fmaheavy pipe per
 # pair of MACs), tools/ubench.cu "exact2" on this pool's B200 (profiles/ubench_r1b.txt): 36.3 TFLOP/s = 0.49 of the FMA peak.
 EXACT_MAC_CEILING_TFLOPS = 36.3
-# DRAM traffic of k_frontend_stream from the `ncu --set full` capture summarised in profiles/r1_ncu_frontend_stream.md:
-# (1297.74 + 248.79) MB for 256 streams x 47 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4)
-NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (1297.743e6 + 248.788736e6) / (256 * 47 * 51200)
+# DRAM traffic of k_frontend_stream from the round-2 `ncu --set full` capture of the whole-job launch, profiles/r2_ncu_k_frontend_stream.md:
+# (1323.959 + 257.409) MB for 256 streams x 48 blocks x 51200 pairs  ->  bytes per IQ pair (algorithmic: 2.4).  DRAM counters cannot
+# be read without a profiler attached, so this figure is carried from that capture and scaled to the launch; per-kernel traffic of a
+# whole step is in profiles/r2_step_traffic.md.
+NCU_FRONTEND_DRAM_BYTES_PER_PAIR = (1323.959e6 + 257.408512e6) / (256 * 48 * 51200)
 
 
 def measured_peaks():
@@ -112,7 +114,9 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(),
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "note": "each worker runs the reference's frontend() then backend() per block on ONE thread (oracle/ref_replay.cpp), not main()'s two "
+                                 "short-lived threads per block: that favours the reference slightly (no thread spawn/join per 21 ms block)"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -322,8 +326,8 @@ def run_gpu_arm(args):
         "pll": {"bytes": (36 if PLL_TABLE else 20) / rd, "mac": 0.0},
         "audio": {"bytes": (12 if STEREO else 4) / rd + 4 / ad, "mac": (2 if STEREO else 1) * 101 / ad},
         "tails": {"bytes": 0.0, "mac": 0.0},
-        # direct: reciprocals (4 in, 8 out) and NCO row (8 in, 4 out); table-driven: prediction (4 in, 8 out), table (12 in, 32 out), NCO (4 in, 4 out)
-        "pll_aux": {"bytes": (64 if PLL_TABLE else 24) / rd, "mac": 0.0},
+        # direct: reciprocals (4 in, 8 out) and NCO row (8 in, 4 out); table-driven: prediction (4 in, 4 out), table (8 in, 32 out), NCO (4 in, 4 out)
+        "pll_aux": {"bytes": (56 if PLL_TABLE else 24) / rd, "mac": 0.0},
         # RDS path: two 101-tap band-pass filters; PLL rows; 19/120 resampler + RRC on I and Q
         "rds_bpf": {"bytes": 16 / rd, "mac": 2 * 101 / rd},
         "rds_pll": {"bytes": 28 / rd, "mac": 0.0},
@@ -365,7 +369,7 @@ def run_gpu_arm(args):
         "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"],
         "algorithmic_bytes": int(alg["frontend"]["bytes"] * pairs_per_step),
         "traffic": int(NCU_FRONTEND_DRAM_BYTES_PER_PAIR * pairs_per_step),
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r1_ncu_frontend_stream.md, scaled to this launch",
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r2_ncu_k_frontend_stream.md (ncu --set full, whole-job launch), scaled to this launch",
         "whole_job_launches": isolated,
         "whole_job_note": "same kernels, one launch per step over the whole batch, not overlapped with the PLL (second, untimed-for-value pass)",
     }
@@ -376,10 +380,10 @@ def run_gpu_arm(args):
         pll_info = {"share_of_step": pll["share"], "avg_launch_ms": pll["avg_ms"], "ms_per_step": round(pll_ms_per_step, 3),
                     "ns_per_sample_per_stream": round(pll_ms_per_step * 1e6 / n_if, 2),
                     "stream_samples_per_s": round(S * n_if / (pll_ms_per_step * 1e-3), 0),
-                    "loop": "table-driven (predict -> exact two-candidate table -> serial picks; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
-                    "note": ("serial recurrence per stream, one thread per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
-                             "pll_aux), the serial loop is float adds, compares and selects - bound by the latency of that dependent chain and by branch "
-                             "cost of a lone warp, not by FLOPs or bytes") if PLL_TABLE else
+                    "loop": "table-driven (k_pll_predict -> k_pll_table_ops: exact two-candidate rows -> k_pll_sel: serial picks, certified per lane; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
+                    "note": ("serial recurrence per stream, one warp per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
+                             "pll_aux), the serial loop is float adds, one compare and selects - bound by the issue rate of a lone warp on that dependent "
+                             "chain (14.9 ns per sample alone, ~25 beside the FIR kernels it shares SM sub-partitions with), not by FLOPs or bytes") if PLL_TABLE else
                             "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
 
     # ---- CPU baseline: the reference's own code on the host cores, bounded sample (N=1 only) ----------------
