@@ -46,7 +46,7 @@ __device__ __forceinline__ float mix_at(const float* nco, const float* sband, co
 
 template <int D, int R, int NT, bool EXACT, bool STEREO>
 __global__ void __launch_bounds__(NT)
-k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail, long long tail_stride,
            const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
            const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
            int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio,
@@ -61,7 +61,7 @@ k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __
     const int m0 = blockIdx.y * T;
     const int s = blockIdx.x;                       // streams on grid.x (no 65535 limit), tiles on grid.y
     const float* row = if_in + (long long)s * if_stride;
-    const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+    const float* itail = if_tail + (long long)s * tail_stride;
     const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
     const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
     const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
@@ -183,7 +183,7 @@ k_audio_u1(const float* __restrict__ if_in, long long if_stride, const float* __
 // and both the sample reads and the tap reads (phase stride K*D mod U = -3, -7) are bank-conflict free.
 template <int NTMAX, bool EXACT, bool STEREO>
 __global__ void __launch_bounds__(NTMAX)
-k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail, long long tail_stride,
              const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
              const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
              int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
@@ -204,7 +204,7 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
     const int m0 = (tile - s * tiles_per_stream) * NT;
     __syncthreads();                                                        // table visible; the previous tile's span no longer read
     const float* row = if_in + (long long)s * if_stride;
-    const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+    const float* itail = if_tail + (long long)s * tail_stride;
     const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
     const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
     const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
@@ -278,7 +278,7 @@ k_audio_poly(const float* __restrict__ if_in, long long if_stride, const float* 
 // pairs; slots beyond 32 K G sit in one extra, partly filled warp.
 template <int NTMAX, bool EXACT, bool STEREO>
 __global__ void __launch_bounds__(NTMAX, 1)
-k_audio_poly_ts(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+k_audio_poly_ts(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail, long long tail_stride,
                 const float* __restrict__ nco, const float* __restrict__ sband, long long bb_stride,
                 const float* __restrict__ mix_tail, float* __restrict__ audio, long long audio_stride,
                 int16_t* __restrict__ pcm, long long pcm_stride, int n_if, int n_audio, int up, int down,
@@ -303,7 +303,7 @@ k_audio_poly_ts(const float* __restrict__ if_in, long long if_stride, const floa
         const int m0 = (tile - s * tiles_per_stream) * S * P;
         __syncthreads();                                                    // the previous tile's span is no longer read
         const float* row = if_in + (long long)s * if_stride;
-        const float* itail = if_tail + (long long)s * DY4_IF_TAIL;
+        const float* itail = if_tail + (long long)s * tail_stride;
         const float* nrow = STEREO ? nco + (long long)s * bb_stride : nullptr;
         const float* srow = STEREO ? sband + (long long)s * bb_stride : nullptr;
         const float* mtail = STEREO ? mix_tail + (long long)s * DY4_MIX_TAIL : nullptr;
@@ -371,7 +371,7 @@ cudaError_t launch_u1(const Dy4AudioArgs& a, cudaStream_t st)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(a.n_streams, (a.n_audio + T - 1) / T);
-    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride,
+    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.if_tail_stride ? a.if_tail_stride : (long long)DY4_IF_TAIL, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride,
                                  a.pcm, a.pcm_stride, a.n_if, a.n_audio, a.neg_zero2, a.mode);
     g_dy4_launches++;
     return cudaGetLastError();
@@ -448,7 +448,7 @@ cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
             const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
             if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
             const int grid = (int)std::min<long long>(n_tiles, (long long)sms * std::max(per_sm, 1));
-            kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride, a.pcm, a.pcm_stride,
+            kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.if_tail_stride ? a.if_tail_stride : (long long)DY4_IF_TAIL, a.nco, a.sband, a.bb_stride, a.mix_tail, a.audio, a.audio_stride, a.pcm, a.pcm_stride,
                                          a.n_if, a.n_audio, a.up, a.down, a.taps_poly, a.up_pad, K, KG, S, P, tiles_per_stream, (int)n_tiles);
             g_dy4_launches++;
             return cudaGetLastError();
@@ -469,7 +469,7 @@ cudaError_t launch_poly(const Dy4AudioArgs& a, cudaStream_t st)
     const long long n_tiles = (long long)tiles_per_stream * a.n_streams;
     if (n_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int grid = (int)std::min<long long>(n_tiles, (long long)sms * std::max(per_sm, 1));
-    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.nco, a.sband, a.bb_stride, a.mix_tail,
+    kern<<<grid, NT, smem, st>>>(a.if_in, a.if_stride, a.if_tail, a.if_tail_stride ? a.if_tail_stride : (long long)DY4_IF_TAIL, a.nco, a.sband, a.bb_stride, a.mix_tail,
                                  a.audio, a.audio_stride, a.pcm, a.pcm_stride, a.n_if, a.n_audio,
                                  a.up, a.down, a.taps_poly, a.up_pad, span_max, a.neg_zero2, K, tiles_per_stream, (int)n_tiles);
     g_dy4_launches++;

@@ -22,7 +22,7 @@ __constant__ TapPairs c_bpf2[6];   // (pilot[k], stereo-band[k]) pairs per mode;
 // both outputs go to `pilot` rows, `sband` is unused.
 template <int R, int NT, bool EXACT, bool SQUARE, bool TWOSTREAMS>
 __global__ void __launch_bounds__(NT)
-k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail, long long tail_stride,
            float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if,
            u64 nz, int mode, int n_streams)
 {
@@ -35,9 +35,9 @@ k_twin_bpf(const float* __restrict__ if_in, long long if_stride, const float* __
     const int sa = TWOSTREAMS ? 2 * blockIdx.x : blockIdx.x;
     const int sb = TWOSTREAMS ? min(sa + 1, n_streams - 1) : sa;            // odd stream count: the last CTA filters its stream twice
     const float* row = if_in + (long long)sa * if_stride;
-    const float* tail = if_tail + (long long)sa * DY4_IF_TAIL;
+    const float* tail = if_tail + (long long)sa * tail_stride;
     const float* row_b = if_in + (long long)sb * if_stride;
-    const float* tail_b = if_tail + (long long)sb * DY4_IF_TAIL;
+    const float* tail_b = if_tail + (long long)sb * tail_stride;
 
     // stage 4 samples per step as 4 duplicated pairs; logical pair p <-> sample n0 - HALO + p
     for (int u = tid; u < NP / 4; u += NT) {
@@ -105,14 +105,14 @@ __constant__ float c_pilot[4][DY4_NTAPS + 3], c_stereo[4][DY4_NTAPS + 3];
 
 template <int MODE, int R, int NT>
 __global__ void __launch_bounds__(NT)
-k_bpf_mixed(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail,
+k_bpf_mixed(const float* __restrict__ if_in, long long if_stride, const float* __restrict__ if_tail, long long tail_stride,
             float* __restrict__ pilot, float* __restrict__ sband, long long out_stride, int n_if)
 {
     constexpr int T = NT * R, HALO = 128, NP = T + HALO;
     __shared__ float sm[NP + NP / R + 8];                        // one pad float per R: stride R+1 between threads' windows
     const int tid = threadIdx.x, n0 = blockIdx.y * T;
     const float* row = if_in + (long long)blockIdx.x * if_stride;
-    const float* tail = if_tail + (long long)blockIdx.x * DY4_IF_TAIL;
+    const float* tail = if_tail + (long long)blockIdx.x * tail_stride;
     for (int u = tid; u < NP / 4; u += NT) {
         const int i = n0 - HALO + 4 * u;                          // multiple of 4, never straddles 0
         float4 v;
@@ -161,12 +161,13 @@ cudaError_t dy4_launch_bpf_mixed(const Dy4BpfArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     constexpr int R = 8, NT = 128;
+    const long long ts = a.if_tail_stride ? a.if_tail_stride : DY4_IF_TAIL;
     dim3 grid(a.n_streams, (a.n_if + NT * R - 1) / (NT * R));
     switch (a.mode) {
-    case 0: k_bpf_mixed<0, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
-    case 1: k_bpf_mixed<1, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
-    case 2: k_bpf_mixed<2, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
-    case 3: k_bpf_mixed<3, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 0: k_bpf_mixed<0, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 1: k_bpf_mixed<1, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 2: k_bpf_mixed<2, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, a.sband, a.out_stride, a.n_if); break;
+    case 3: k_bpf_mixed<3, R, NT><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, a.sband, a.out_stride, a.n_if); break;
     default: return cudaErrorInvalidValue;
     }
     g_dy4_launches++;
@@ -177,10 +178,11 @@ cudaError_t dy4_launch_bpf(const Dy4BpfArgs& a, cudaStream_t st)
 {
     if (a.n_if <= 0 || a.n_streams <= 0) return cudaSuccess;
     constexpr int R = 8, NT = 128;
+    const long long ts = a.if_tail_stride ? a.if_tail_stride : DY4_IF_TAIL;
     dim3 grid(a.variant == 0 ? a.n_streams : (a.n_streams + 1) / 2, (a.n_if + NT * R - 1) / (NT * R));
-    if (a.variant == 0) k_twin_bpf<R, NT, true, false, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
-    else if (a.variant == 1) k_twin_bpf<R, NT, false, false, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
-    else k_twin_bpf<R, NT, false, true, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
+    if (a.variant == 0) k_twin_bpf<R, NT, true, false, false><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, a.sband, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
+    else if (a.variant == 1) k_twin_bpf<R, NT, false, false, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
+    else k_twin_bpf<R, NT, false, true, true><<<grid, NT, 0, st>>>(a.if_in, a.if_stride, a.if_tail, ts, a.pilot, nullptr, a.out_stride, a.n_if, a.neg_zero2, a.mode, a.n_streams);
     g_dy4_launches++;
     return cudaGetLastError();
 }

@@ -19,7 +19,9 @@ struct Dy4FrontendArgs {
 
 struct Dy4BpfArgs {
     const float* if_in; long long if_stride;    // IF samples of this chunk
-    const float* if_tail;                       // [n_streams][DY4_IF_TAIL] IF samples preceding the chunk
+    const float* if_tail;                       // [n_streams][DY4_IF_TAIL] IF samples preceding the chunk ...
+    long long if_tail_stride = 0;               // ... rows if_tail_stride floats apart (0: DY4_IF_TAIL).  With if_tail = if_in - DY4_IF_TAIL and the stride of if_in the
+                                                // history is simply the samples that precede the chunk in the same (call-wide) rows.
     float* pilot; float* sband; long long out_stride;
     int n_if, n_streams, mode;                  // mode 0..3: (pilot, stereo) table; 4, 5: RDS band-pass / carrier tables
     int variant;                                // 0: exact (pilot, stereo) pair of one stream; 1: ONE fused (h,h) filter over two streams per CTA -> pilot rows;
@@ -45,6 +47,7 @@ struct Dy4PllArgs {
 
 struct Dy4AudioArgs {
     const float* if_in; long long if_stride; const float* if_tail;
+    long long if_tail_stride = 0;                               // as in Dy4BpfArgs
     const float* nco; const float* sband; long long bb_stride;  // stereo only (else NULL)
     const float* mix_tail;                                      // [n_streams][DY4_MIX_TAIL] of nco*sband*2 before the chunk
     float* audio; long long audio_stride;                       // may be NULL; mono: [n] ; stereo: interleaved L,R [2n]
