@@ -46,18 +46,21 @@ struct dy4_pipeline {
     float* d_rf_taps = nullptr;
     float* d_taps_poly = nullptr;
     int up_pad = 0;
-    // carried state.  if_tail is a ring of NSETS + 1 slots: sub-chunk c reads slot c % (NSETS+1) and leaves the next one for its
-    // successor, so the front ends of the sub-chunks ahead can run (under the PLL of c) before the audio kernel of c has read its slot.
+    // carried state (input history)
     uint8_t* iq_tail = nullptr; float* if_tail = nullptr; float* mix_tail = nullptr; float* pll_state = nullptr;
-    long long seq = 0;                               // sub-chunks processed so far: selects the if_tail slot
-    // workspace: NSETS sets, sub-chunk c uses set c % NSETS
-    struct WorkSet { float *w_if = nullptr, *pilot = nullptr, *sband = nullptr, *nco = nullptr; double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
-    static constexpr int NSETS = 3;                  // front(c+2) may run before back(c): the main stream works two sub-chunks ahead of the serial loop
+    long long seq = 0;                               // sub-chunks processed so far: selects the workspace set
+    // call rows: IF, pilot, stereo band and NCO of the WHOLE call, [n_streams][c_stride].  The FIR kernels fill them in full-wave
+    // launches ahead of the PLL's sub-chunks; a sub-chunk's history is simply what precedes it in the same rows.
+    float *c_if = nullptr, *c_pilot = nullptr, *c_sband = nullptr, *c_nco = nullptr;
+    size_t c_stride = 0; int c_blocks = 0;
+    // per sub-chunk PLL workspace: NSETS sets, sub-chunk c uses set c % NSETS
+    static constexpr int NSETS = 3;                  // prediction + table may run two sub-chunks ahead of the serial loop
+    struct WorkSet { double *theta = nullptr, *inv = nullptr; float4* tab = nullptr; };
     WorkSet ws[NSETS];
     float* ws_nco0 = nullptr;
     int* pll_risk = nullptr;                         // [n_streams]: near-tie narrowings seen by the PLL table kernel (dy4_pipeline_pll_risk)
     double* pred_state = nullptr;                    // table-driven PLL: the predictor's own state, [NSETS][n_streams][8], then [NSETS][n_streams] turns
-    size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; int last_set = 0;
+    size_t ws_stride = 0; int ws_blocks = 0; int last_n_if = 0; size_t last_off = 0;
     // RDS filtering front end (DY4_FLAG_RDS): its own stream beside the stereo PLL
     float *rds_f = nullptr, *rds_carrier = nullptr, *rds_nco_i = nullptr, *rds_nco_q = nullptr, *rds_lp = nullptr, *rds_out = nullptr;
     double *rds_theta = nullptr, *rds_pll_state = nullptr;
@@ -69,12 +72,13 @@ struct dy4_pipeline {
     int8_t *rds_sym = nullptr, *rds_bits = nullptr;
     size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0, rds_grp_cap = 0;
     long long rds_blocks_since_drain = 0;
-    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr, ev_rds_set[NSETS] = {};
+    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr;
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaStream_t s_aux = nullptr;                    // the PLL's time-parallel FP64 kernels (prediction, table) run here, beside the FP32-bound FIR kernels
-    cudaEvent_t ev_bpf[NSETS] = {}, ev_pll[NSETS] = {}, ev_prep[NSETS] = {}, ev_in = nullptr, ev_prep1 = nullptr;
+    cudaEvent_t ev_back[NSETS] = {}, ev_pll[NSETS] = {}, ev_prep[NSETS] = {}, ev_in = nullptr, ev_prep1 = nullptr;
+    std::vector<cudaEvent_t> ev_fir;                 // one per FIR piece of a call
     // host-facing staging
     uint8_t* d_stage = nullptr; int16_t* d_pcm_stage = nullptr; float* d_audio_stage = nullptr;
     int stage_blocks = 0; bool stage_audio = false;
@@ -137,7 +141,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
 {
     const size_t S = (size_t)p->n_streams;
     CU(cudaMemsetAsync(p->iq_tail, 128, S * DY4_IQ_TAIL, st));            // byte 128 = 0.0f: zero RF history (project.cpp:242-243)
-    CU(cudaMemsetAsync(p->if_tail, 0, (dy4_pipeline::NSETS + 1) * S * DY4_IF_TAIL * sizeof(float), st));
+    CU(cudaMemsetAsync(p->if_tail, 0, S * DY4_IF_TAIL * sizeof(float), st));
     p->seq = 0;
     p->pll_fresh = true;
     CU(cudaMemsetAsync(p->mix_tail, 0, S * DY4_MIX_TAIL * sizeof(float), st));
@@ -166,10 +170,10 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     return DY4_OK;
 }
 
-// IF / pilot / stereo-band / NCO rows (and the PLL's double rows) for one sub-chunk, two sets.  A stereo job is cut
-// into sub-chunks (plan_subchunks) so that the FIR kernels of sub-chunk c+1 run beside the serial PLL of sub-chunk c;
-// the whole thing is capped by a byte budget (DY4_WS_BYTES, default 8 GiB).  DY4_FLAG_DEBUG_ROWS keeps the job in one
-// sub-chunk so that dy4_pipeline_debug_buffers() sees whole rows.
+// The PLL's per-sub-chunk rows (predicted phase, phaseEst / reciprocal row, table), NSETS sets.  A stereo job is cut
+// into sub-chunks (plan_subchunks) so that the data-parallel kernels of the sub-chunks ahead run beside the serial PLL of
+// sub-chunk c; the whole thing is capped by a byte budget (DY4_WS_BYTES, default 8 GiB).  DY4_FLAG_DEBUG_ROWS keeps the job in
+// one sub-chunk.
 int ensure_workspace(dy4_pipeline* p, int n_blocks)
 {
     size_t budget = 8ull << 30;
@@ -177,44 +181,34 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     // Table-driven PLL (dy4_plltab.h, 32 bytes of table per IF sample) while the stream count leaves the serial loop
     // latency-bound; with many streams the direct loop's FP64 work is already throughput-bound and the table's 3x
     // evaluations would only add to it.  DY4_PLL_TABLE_MAX=0 selects the direct loop always.
-    // Measured: 4 096 streams 99.5 -> 127 G samples/s with the table, 8 192 streams 160 -> 124 without / with.
+    // Measured: 4 096 streams 113 -> 131 G samples/s with the table, 8 192 streams 160 -> 135 without / with.
     // With the RDS branch beside it (its own FP64 carrier PLL and FIRs on another stream) the table's extra FP64 work
     // costs more than it saves at 4 096 streams (69.9 -> 63.8), so the switch-over is lower there.
     int tab_max = (p->flags & DY4_FLAG_RDS) ? 1024 : 4096;
     if (const char* e = std::getenv("DY4_PLL_TABLE_MAX")) tab_max = atoi(e);
     p->pll_table = p->stereo && p->n_streams <= tab_max;
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * sizeof(float) * (p->stereo ? (p->pll_table ? 32 : 16) : 1);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * (p->stereo ? (p->pll_table ? 48 : 16) * dy4_pipeline::NSETS : 4);
     int blocks = (int)std::max<size_t>(1, budget / per_block);
     blocks = std::min(blocks, std::max(n_blocks, 1));
     const bool whole = (p->flags & DY4_FLAG_DEBUG_ROWS) != 0;
-    int nsub = 3;                                      // largest sub-chunk = a third of the job (see plan_subchunks)
+    const int nsub = 3;                                // largest sub-chunk = a third of the job (see plan_subchunks)
     if (p->stereo && !whole && n_blocks >= 8) blocks = std::min(blocks, (n_blocks + nsub - 1) / nsub);
     if (const char* e = std::getenv("DY4_SUBCHUNK_BLOCKS")) blocks = std::max(1, atoi(e));
     if (whole) blocks = std::max(blocks, n_blocks);
     if (p->ws_blocks >= blocks && (p->ws_blocks == blocks || whole || n_blocks < 8 || !p->stereo)) return DY4_OK;
     if (p->ws_blocks > 0) {
         CU(cudaDeviceSynchronize());
-        for (auto& w : p->ws) {
-            cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab);
-            w = dy4_pipeline::WorkSet();
-        }
+        for (auto& w : p->ws) { cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); w = dy4_pipeline::WorkSet(); }
         p->ws_blocks = 0;
     }
     p->ws_stride = (size_t)blocks * p->mp.if_per_block;
     const size_t bytes = (size_t)p->n_streams * p->ws_stride * sizeof(float);
-    for (int i = 0; i < (p->stereo ? dy4_pipeline::NSETS : 1); i++) {
-        auto& w = p->ws[i];
-        CU(cudaMalloc(&w.w_if, bytes));
-        if (p->stereo) {
-            CU(cudaMalloc(&w.pilot, bytes));
-            CU(cudaMalloc(&w.sband, bytes));
-            CU(cudaMalloc(&w.nco, bytes));
+    if (p->stereo)
+        for (auto& w : p->ws) {
             CU(cudaMalloc(&w.theta, 2 * bytes));
             CU(cudaMalloc(&w.inv, 2 * bytes));
-            // padded: the serial loop copies whole chunks of 64 rows
-            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 512 * sizeof(float4)));
+            if (p->pll_table) CU(cudaMalloc(&w.tab, 8 * bytes + 512 * sizeof(float4)));      // padded: the serial loop copies whole chunks of 128 rows
         }
-    }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 3 * dy4_pipeline::NSETS * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
     if (p->pll_table && !p->pll_risk) { CU(cudaMalloc(&p->pll_risk, (size_t)p->n_streams * sizeof(int))); CU(cudaMemset(p->pll_risk, 0, (size_t)p->n_streams * sizeof(int))); }
     if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));   // [NSETS][S][8] predictor state + [NSETS][S] turns
@@ -222,7 +216,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
         for (int i = 0; i < dy4_pipeline::NSETS; i++) {
-            CU(cudaEventCreateWithFlags(&p->ev_bpf[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_back[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_prep[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_pll[i], cudaEventDisableTiming));
         }
@@ -240,10 +234,32 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
-            for (int i = 0; i < dy4_pipeline::NSETS; i++) CU(cudaEventCreateWithFlags(&p->ev_rds_set[i], cudaEventDisableTiming));
         }
     }
     p->ws_blocks = blocks;
+    return DY4_OK;
+}
+
+// blocks of one call that fit the call rows' budget (IF, pilot, stereo band, NCO: 16 bytes per IF sample; mono: 4)
+int max_call_blocks(const dy4_pipeline* p)
+{
+    size_t budget = 32ull << 30;
+    if (const char* e = std::getenv("DY4_WS_BYTES")) budget = 4 * std::strtoull(e, nullptr, 10);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * (p->stereo ? 16 : 4);
+    return (int)std::max<size_t>(1, std::min<size_t>(budget / per_block, 1 << 20));
+}
+
+int ensure_call_rows(dy4_pipeline* p, int n_blocks)
+{
+    if (n_blocks <= p->c_blocks) return DY4_OK;
+    if (p->c_blocks > 0) CU(cudaDeviceSynchronize());
+    cudaFree(p->c_if); cudaFree(p->c_pilot); cudaFree(p->c_sband); cudaFree(p->c_nco);
+    p->c_if = p->c_pilot = p->c_sband = p->c_nco = nullptr; p->c_blocks = 0;
+    p->c_stride = (size_t)n_blocks * p->mp.if_per_block;
+    const size_t bytes = (size_t)p->n_streams * p->c_stride * sizeof(float);
+    CU(cudaMalloc(&p->c_if, bytes));
+    if (p->stereo) { CU(cudaMalloc(&p->c_pilot, bytes)); CU(cudaMalloc(&p->c_sband, bytes)); CU(cudaMalloc(&p->c_nco, bytes)); }
+    p->c_blocks = n_blocks;
     return DY4_OK;
 }
 
@@ -259,38 +275,43 @@ struct Timer {
     ~Timer() { if (p->prof) { cudaEventRecord(e1, st); p->recs.push_back({k, e0, e1}); } }
 };
 
-struct SubChunk {                        // one sub-chunk of the job: where its input and outputs live
-    const uint8_t* iq; int nb;
-    int16_t* pcm; float* audio; float* d_if;
-    int set; float* if_tail_in; float* if_tail_out;
+struct SubChunk {                        // one sub-chunk of a call: blocks [b, b + nb)
+    int b, nb;
+    int16_t* pcm; float* audio;
+    int set;
     int fresh = 0;                       // table-driven PLL: leading samples of a fresh stream left to the direct loop
     int pred_carry = 0;                  // table-driven PLL: the prediction continues from the previous sub-chunk's (not the first of a call)
 };
 
-float* if_tail_slot(dy4_pipeline* p, long long seq) { return p->if_tail + (size_t)(seq % (dy4_pipeline::NSETS + 1)) * p->n_streams * DY4_IF_TAIL; }
+// IF history of the sub-chunk that starts at block b of the call: the carried tail for b == 0, else the samples before it in the call rows
+struct Hist { const float* tail; long long stride; };
+Hist if_history(const dy4_pipeline* p, int b)
+{
+    if (b == 0) return {p->if_tail, (long long)DY4_IF_TAIL};
+    return {p->c_if + (size_t)b * p->mp.if_per_block - DY4_IF_TAIL, (long long)p->c_stride};
+}
 
-// front half on the main stream: uint8 IQ -> IF -> (pilot, stereo band); leaves the IQ and IF history for the successor
-int run_front(dy4_pipeline* p, const SubChunk& c, size_t row_stride, size_t if_out_stride, cudaStream_t st)
+// FIR work of blocks [b, b + nb) of the call on `st`: uint8 IQ -> IF -> (pilot, stereo band) into the call rows; leaves the IQ history
+int run_fir(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int b, int nb, cudaStream_t st)
 {
     const dy4_mode_params_t& m = p->mp;
-    const int n_if = c.nb * m.if_per_block;
-    auto& w = p->ws[c.set];
+    const int n_if = nb * m.if_per_block;
+    const size_t off = (size_t)b * m.if_per_block;
+    const uint8_t* iq = d_iq + (size_t)b * m.block_size;
     Dy4FrontendArgs fa;
-    fa.iq = c.iq; fa.row_stride = (long long)row_stride; fa.iq_tail = p->iq_tail;
-    fa.if_out = w.w_if; fa.if_stride = (long long)p->ws_stride; fa.n_if = n_if; fa.n_streams = p->n_streams;
+    fa.iq = iq; fa.row_stride = (long long)row_stride; fa.iq_tail = p->iq_tail;
+    fa.if_out = p->c_if + off; fa.if_stride = (long long)p->c_stride; fa.n_if = n_if; fa.n_streams = p->n_streams;
     fa.rf_decim = m.rf_decim; fa.exact = (p->stereo || (p->flags & DY4_FLAG_EXACT_AUDIO)) ? 1 : 0; /* the PLL needs a bit-exact IF; mono does not */ fa.taps_g = p->d_rf_taps; fa.mode = p->mode; fa.neg_zero2 = kNegZero2;
     { Timer t(p, DY4_K_FRONTEND, st); CU(dy4_launch_frontend(fa, st)); }
-    if (c.d_if) CU(cudaMemcpy2DAsync(c.d_if, if_out_stride * sizeof(float), w.w_if, p->ws_stride * sizeof(float),
-                                     (size_t)n_if * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
     Dy4TailArgs ta{};
-    ta.iq = c.iq; ta.row_stride = (long long)row_stride; ta.row_bytes = (long long)c.nb * m.block_size; ta.iq_tail = p->iq_tail;
-    ta.if_in = w.w_if; ta.if_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.if_tail = c.if_tail_out;
-    ta.mix_tail = nullptr; ta.n_streams = p->n_streams;
+    ta.iq = iq; ta.row_stride = (long long)row_stride; ta.row_bytes = (long long)nb * m.block_size; ta.iq_tail = p->iq_tail;
+    ta.n_streams = p->n_streams;
     { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
     if (p->stereo) {
+        const Hist h = if_history(p, b);
         Dy4BpfArgs ba;
-        ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
-        ba.pilot = w.pilot; ba.sband = w.sband; ba.out_stride = (long long)p->ws_stride;
+        ba.if_in = p->c_if + off; ba.if_stride = (long long)p->c_stride; ba.if_tail = h.tail; ba.if_tail_stride = h.stride;
+        ba.pilot = p->c_pilot + off; ba.sband = p->c_sband + off; ba.out_stride = (long long)p->c_stride;
         ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = p->mode; ba.variant = 0; ba.neg_zero2 = kNegZero2;
         // the stereo band only has to be bit-exact when the audio is asked to be (DY4_FLAG_EXACT_AUDIO)
         const bool mixed = !(p->flags & DY4_FLAG_EXACT_AUDIO);
@@ -351,15 +372,17 @@ int run_rds(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
 {
     const dy4_mode_params_t& m = p->mp;
     const int n_if = c.nb * m.if_per_block;
-    auto& w = p->ws[c.set];
+    const size_t off = (size_t)c.b * m.if_per_block;
+    const Hist h = if_history(p, c.b);
     Dy4BpfArgs ba;
-    ba.if_in = w.w_if; ba.if_stride = (long long)p->ws_stride; ba.if_tail = c.if_tail_in;
+    ba.if_in = p->c_if + off; ba.if_stride = (long long)p->c_stride; ba.if_tail = h.tail; ba.if_tail_stride = h.stride;
     ba.pilot = p->rds_f; ba.sband = nullptr; ba.out_stride = (long long)p->ws_stride;
     ba.n_if = n_if; ba.n_streams = p->n_streams; ba.mode = 4; ba.variant = 1; ba.neg_zero2 = kNegZero2;
     {
         Timer t(p, DY4_K_RDS_BPF, st);
         CU(dy4_launch_bpf(ba, st));                               // RDS channel extraction, 54-60 kHz
-        ba.if_in = p->rds_f; ba.if_tail = p->rds_tail; ba.pilot = p->rds_carrier; ba.mode = 5; ba.variant = 2;
+        ba.if_in = p->rds_f; ba.if_stride = (long long)p->ws_stride; ba.if_tail = p->rds_tail; ba.if_tail_stride = 0;
+        ba.pilot = p->rds_carrier; ba.mode = 5; ba.variant = 2;
         CU(dy4_launch_bpf(ba, st));                               // squaring + 113.5-114.5 kHz carrier extraction
     }
     Dy4RdsArgs ra{};
@@ -385,20 +408,22 @@ int run_rds(dy4_pipeline* p, const SubChunk& c, cudaStream_t st)
     return run_rds_decode(p, st);
 }
 
-// the serial part, on its own stream: pilot -> NCO row
-// `parts`: the reciprocal pre-pass rides at the end of front(c) and the NCO pass at the start of back(c), both on the
-// main stream; only the serial loop is queued on the PLL stream, so consecutive loops run back to back there.
+// the PLL of one sub-chunk: pilot (call rows) -> NCO row (call rows), scratch in the sub-chunk's workspace set.
+// `parts`: prediction + table (or, for the direct loop, the reciprocal pre-pass), the serial loop, the NCO pass — queued on
+// different streams (process_device).
 int run_pll(dy4_pipeline* p, const SubChunk& c, cudaStream_t st, int parts)
 {
     const dy4_mode_params_t& m = p->mp;
     auto& w = p->ws[c.set];
+    const size_t off = (size_t)c.b * m.if_per_block;
     Dy4PllArgs pa;
-    pa.in = w.pilot; pa.in_stride = (long long)p->ws_stride; pa.nco = w.nco; pa.nco_stride = (long long)p->ws_stride;
+    pa.in = p->c_pilot + off; pa.in_stride = (long long)p->c_stride; pa.nco = p->c_nco + off; pa.nco_stride = (long long)p->c_stride;
     pa.theta = w.theta; pa.inv = w.inv; pa.wide_stride = (long long)p->ws_stride; pa.nco0 = p->ws_nco0 + (size_t)c.set * p->n_streams;
     pa.state = p->pll_state; pa.n = c.nb * m.if_per_block; pa.n_streams = p->n_streams;
     pa.tab = w.tab; pa.tab_stride = 2 * (long long)p->ws_stride; pa.risk = p->pll_risk; pa.tstart = p->ws_nco0 + (size_t)(dy4_pipeline::NSETS + c.set) * p->n_streams;
     if (w.tab) {
-        pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8; pa.pred_in = p->pred_state + (size_t)((c.set + dy4_pipeline::NSETS - 1) % dy4_pipeline::NSETS) * p->n_streams * 8;
+        pa.pred_out = p->pred_state + (size_t)c.set * p->n_streams * 8;
+        pa.pred_in = p->pred_state + (size_t)((c.set + dy4_pipeline::NSETS - 1) % dy4_pipeline::NSETS) * p->n_streams * 8;
         pa.need = p->pred_state + (size_t)(8 * dy4_pipeline::NSETS + c.set) * p->n_streams;      // written by the loop NSETS launches back, complete by now
         pa.pred_carry = c.pred_carry; pa.fresh = c.fresh; pa.nco0b = p->ws_nco0 + (size_t)(2 * dy4_pipeline::NSETS + c.set) * p->n_streams;
     }
@@ -412,10 +437,11 @@ int run_back(dy4_pipeline* p, const SubChunk& c, size_t pcm_stride, size_t audio
 {
     const dy4_mode_params_t& m = p->mp;
     const int n_if = c.nb * m.if_per_block, n_audio = c.nb * m.audio_per_block;
-    auto& w = p->ws[c.set];
+    const size_t off = (size_t)c.b * m.if_per_block;
+    const Hist h = if_history(p, c.b);
     Dy4AudioArgs aa;
-    aa.if_in = w.w_if; aa.if_stride = (long long)p->ws_stride; aa.if_tail = c.if_tail_in;
-    aa.nco = w.nco; aa.sband = w.sband; aa.bb_stride = (long long)p->ws_stride; aa.mix_tail = p->mix_tail;
+    aa.if_in = p->c_if + off; aa.if_stride = (long long)p->c_stride; aa.if_tail = h.tail; aa.if_tail_stride = h.stride;
+    aa.nco = p->stereo ? p->c_nco + off : nullptr; aa.sband = p->stereo ? p->c_sband + off : nullptr; aa.bb_stride = (long long)p->c_stride; aa.mix_tail = p->mix_tail;
     aa.audio = c.audio; aa.audio_stride = (long long)audio_stride; aa.pcm = c.pcm; aa.pcm_stride = (long long)pcm_stride;
     aa.n_if = n_if; aa.n_audio = n_audio; aa.n_streams = p->n_streams; aa.stereo = p->stereo;
     aa.up = m.audio_upsample; aa.down = m.audio_decim; aa.exact = (p->flags & DY4_FLAG_EXACT_AUDIO) ? 1 : 0;
@@ -423,22 +449,22 @@ int run_back(dy4_pipeline* p, const SubChunk& c, size_t pcm_stride, size_t audio
     if (c.audio || c.pcm) { Timer t(p, DY4_K_AUDIO, st); CU(dy4_launch_audio(aa, st)); }
     if (p->stereo) {
         Dy4TailArgs ta{};
-        ta.nco = w.nco; ta.sband = w.sband; ta.bb_stride = (long long)p->ws_stride; ta.n_if = n_if; ta.mix_tail = p->mix_tail;
+        ta.nco = p->c_nco + off; ta.sband = p->c_sband + off; ta.bb_stride = (long long)p->c_stride; ta.n_if = n_if; ta.mix_tail = p->mix_tail;
         ta.n_streams = p->n_streams;
         { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
     }
-    p->last_n_if = n_if; p->last_set = c.set;
+    p->last_n_if = n_if; p->last_off = off;
     return DY4_OK;
 }
 
-// Optional per-sub-chunk hooks of the host-facing path: wait for that sub-chunk's upload before its front half,
+// Optional per-sub-chunk hooks of the host-facing path: wait for that sub-chunk's upload before its FIR work,
 // start the download of its PCM after its back half.  Arguments: first block and number of blocks of the sub-chunk.
 struct Hooks { std::function<int(int, int, int)> before_front, after_back; };   // (index, first block, blocks)
 
 // The sub-chunks of a stereo job grow geometrically — 1, 2, 4, ... blocks up to the workspace size, then that size —
 // so that (a) only one block's FIR work and, on the host path, one block's upload precede the first PLL launch, and
 // every later upload (PCIe moves a block ~2x faster than the PLL consumes it) lands before it is needed, while
-// (b) most of the job runs in large launches (front-end wave balance, few PLL launches).  Mono: uniform sub-chunks.
+// (b) most of the job runs in large launches (few PLL launches).  Mono: uniform sub-chunks.
 // (Ending the job on small sub-chunks as well — so that little follows the last serial loop — was measured: the two extra
 // launches cost more than the shorter tail saves, 7.34 against 7.20 ms per step.)
 std::vector<std::pair<int, int>> plan_subchunks(int n_blocks, int sb, bool geometric)
@@ -451,6 +477,22 @@ std::vector<std::pair<int, int>> plan_subchunks(int n_blocks, int sb, bool geome
     return v;
 }
 
+// RDS: RRC rows of the whole call (read back by dy4_pipeline_rds_read), sized before its first window
+int rds_begin_call(dy4_pipeline* p, int n_blocks)
+{
+    if (!(p->flags & DY4_FLAG_RDS)) return DY4_OK;
+    const size_t need = ((size_t)n_blocks * p->mp.if_per_block * 19 + 119) / 120 + 8;
+    if (need > p->rds_out_cap) {
+        if (p->s_rds) CU(cudaStreamSynchronize(p->s_rds));
+        cudaFree(p->rds_out); p->rds_out = nullptr;
+        CU(cudaMalloc(&p->rds_out, (size_t)p->n_streams * 2 * need * sizeof(float)));
+        p->rds_out_cap = need;
+    }
+    p->rds_call_n = 0;
+    return DY4_OK;
+}
+
+// One call: n_blocks whole blocks of every stream, input on the device.
 int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int n_blocks,
                    int16_t* d_pcm, float* d_audio, float* d_if, cudaStream_t st,
                    size_t pcm_stride, size_t audio_stride, size_t if_stride, const Hooks* hooks = nullptr)
@@ -459,53 +501,54 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     const int ch = p->stereo ? 2 : 1;
     int rc = ensure_workspace(p, n_blocks);
     if (rc) return rc;
+    if ((rc = ensure_call_rows(p, n_blocks))) return rc;
     const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
-    if (p->flags & DY4_FLAG_RDS) {                     // RRC rows of the whole call (read back by dy4_pipeline_rds_read)
-        const size_t need = ((size_t)n_blocks * m.if_per_block * 19 + 119) / 120 + 8;
-        if (need > p->rds_out_cap) {
-            CU(cudaStreamSynchronize(p->s_rds));
-            cudaFree(p->rds_out); p->rds_out = nullptr;
-            CU(cudaMalloc(&p->rds_out, (size_t)p->n_streams * 2 * need * sizeof(float)));
-            p->rds_out_cap = need;
-        }
-        p->rds_call_n = 0;
-    }
     auto sub = [&](int b, int nb, long long seq) {
         SubChunk c;
-        c.nb = nb;
-        c.iq = d_iq + (size_t)b * m.block_size;
+        c.b = b; c.nb = nb;
         c.pcm = d_pcm ? d_pcm + (size_t)b * m.audio_per_block * ch : nullptr;
         c.audio = d_audio ? d_audio + (size_t)b * m.audio_per_block * ch : nullptr;
-        c.d_if = d_if ? d_if + (size_t)b * m.if_per_block : nullptr;
         c.set = p->stereo ? (int)(seq % dy4_pipeline::NSETS) : 0;
-        c.if_tail_in = if_tail_slot(p, seq);
-        c.if_tail_out = if_tail_slot(p, seq + 1);
         return c;
+    };
+    // the IF history the NEXT call starts from, and the caller's copy of the IF rows: after everything that reads them
+    auto finish_call = [&]() -> int {
+        if (d_if) CU(cudaMemcpy2DAsync(d_if, if_stride * sizeof(float), p->c_if, p->c_stride * sizeof(float),
+                                       (size_t)n_blocks * m.if_per_block * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+        Dy4TailArgs ta{};
+        ta.if_in = p->c_if; ta.if_stride = (long long)p->c_stride; ta.n_if = n_blocks * m.if_per_block; ta.if_tail = p->if_tail; ta.n_streams = p->n_streams;
+        { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
+        return DY4_OK;
     };
     if (!p->stereo) {                                  // mono: no serial stage, one stream
         for (size_t i = 0; i < plan.size(); i++, p->seq++) {
             const int b = plan[i].first;
             const SubChunk c = sub(b, plan[i].second, p->seq);
             if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
-            if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
+            if ((rc = run_fir(p, d_iq, row_stride, b, c.nb, st))) return rc;
             if ((rc = run_back(p, c, pcm_stride, audio_stride, st))) return rc;
             if (hooks && (rc = hooks->after_back((int)i, b, c.nb))) return rc;
         }
-        return DY4_OK;
+        return finish_call();
     }
     // stereo: software pipeline over three streams and NSETS = 3 workspace sets.
-    //   main stream:  front(0) front(1) front(2) back(0) front(3) back(1) ...  back(last)      FIR kernels; NCO row + audio
-    //   aux stream:          prep(0)  prep(1)  prep(2) ...                                      prediction + table (FP64)
-    //   PLL stream:                  loop(0)   loop(1)   loop(2) ...                            the serial loops, back to back
-    // front(c) -> prep(c) -> loop(c) -> back(c) by events; the main stream runs up to two sub-chunks ahead of the loop, so the
-    // geometric growth of the sub-chunks (front + prep of c+1 is twice the work of c's) does not leave the PLL stream waiting.
-    // The buffers of set c % 3 are next written by front(c+3), queued after back(c), their last reader.
+    //   main stream:  fir(piece 0) fir(piece 1) ... back(0) back(1) ...  back(last)             FIR kernels; NCO row + audio
+    //   aux stream:        prep(0)  prep(1)  prep(2) ...                                         prediction + table (FP64)
+    //   PLL stream:                loop(0)   loop(1)   loop(2) ...                               the serial loops, back to back
+    // FIR PIECES are full-wave launches over many sub-chunks: with the input on the device, piece 0 is the first sub-chunk
+    // (one block: the first serial loop starts after 1/48 of the FIR work) and piece 1 everything else; on the host path
+    // (hooks) every sub-chunk is its own piece, gated on ITS upload.  fir(piece) -> prep(c) -> loop(c) -> back(c) by events;
+    // prep(c) also waits for back(c - NSETS), the last reader of its workspace set.
+    std::vector<std::pair<int, int>> pieces;           // (first sub-chunk, sub-chunks)
+    if (hooks || plan.size() < 2) for (size_t i = 0; i < plan.size(); i++) pieces.push_back({(int)i, 1});
+    else { pieces.push_back({0, 1}); pieces.push_back({1, (int)plan.size() - 1}); }
+    while (p->ev_fir.size() < pieces.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_fir.push_back(e); }
     CU(cudaEventRecord(p->ev_in, st));
     CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
     const bool fresh_call = p->pll_fresh;              // no sample processed since create / reset: the streams start in this call
     p->pll_fresh = false;
-    // back halves still to be queued (at most NSETS - 1 of them): back(c) follows front(c + NSETS - 1) on the main stream
-    struct Pending { SubChunk c; int b, i; };
+    // back halves still to be queued (at most NSETS - 1 of them)
+    struct Pending { SubChunk c; int i; };
     std::vector<Pending> pend;
     auto flush_back = [&]() -> int {
         const Pending q = pend.front();
@@ -514,60 +557,68 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         int r2;
         if ((r2 = run_pll(p, q.c, st, DY4_PLL_NCO))) return r2;
         if ((r2 = run_back(p, q.c, pcm_stride, audio_stride, st))) return r2;
-        if (hooks && (r2 = hooks->after_back(q.i, q.b, q.c.nb))) return r2;
+        CU(cudaEventRecord(p->ev_back[q.c.set], st));
+        if (hooks && (r2 = hooks->after_back(q.i, q.c.b, q.c.nb))) return r2;
         return DY4_OK;
     };
+    size_t next_piece = 0;
+    std::vector<int> piece_of(plan.size(), 0);
+    for (size_t k = 0; k < pieces.size(); k++) for (int j = 0; j < pieces[k].second; j++) piece_of[pieces[k].first + j] = (int)k;
+    const long long seq0 = p->seq;
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
-        const int b = plan[i].first;
-        SubChunk c = sub(b, plan[i].second, p->seq);
+        SubChunk c = sub(plan[i].first, plan[i].second, p->seq);
+        // the FIR piece this sub-chunk belongs to (queued once, when its first sub-chunk comes up)
+        while (next_piece <= (size_t)piece_of[i]) {
+            const int s0 = pieces[next_piece].first, ns = pieces[next_piece].second;
+            const int b0 = plan[s0].first, nb = plan[s0 + ns - 1].first + plan[s0 + ns - 1].second - b0;
+            if (hooks && (rc = hooks->before_front(s0, b0, nb))) return rc;
+            if ((rc = run_fir(p, d_iq, row_stride, b0, nb, st))) return rc;
+            CU(cudaEventRecord(p->ev_fir[next_piece], st));
+            next_piece++;
+        }
+        cudaEvent_t ev_fir = p->ev_fir[piece_of[i]];
         // Table-driven PLL (dy4_pll.cu).  Sub-chunk 0 starts from the exact carried state; at the START of a stream its first
         // samples go through the direct loop while the PLL acquires lock, and sub-chunk 1 is predicted from the exact state
         // too (its prediction waits for the loop of sub-chunk 0, on the PLL stream); from sub-chunk 2 on the prediction
-        // carries its own state and runs with the FIR kernels on the main stream, beside the serial loop of the sub-chunk before.
+        // carries its own state and runs on the aux stream, beside the serial loop of the sub-chunks before.
         // A CONTINUING stream (not the first call after create / reset) needs none of that: the loop of the previous call has
-        // finished, so sub-chunk 0 is predicted from the exact state on the main stream, sub-chunk 1 carries on from that
-        // prediction, and nothing but the serial loops is queued on the PLL stream.  Should the signal have jumped between two
-        // calls, the loop notices (its picks stop being certain) and finishes that launch with the direct loop's steps.
+        // finished, so sub-chunk 0 is predicted from the exact state, sub-chunk 1 carries on from that prediction, and nothing
+        // but the serial loops is queued on the PLL stream.  Should the signal have jumped between two calls, the loop notices
+        // (its picks stop being certain) and finishes that launch with the direct loop's steps.
         if (fresh_call) c.pred_carry = i < 2 ? 0 : (i == 2 ? 1 : 2);
         else c.pred_carry = i == 0 ? 0 : (i == 1 ? 1 : 2);
         c.fresh = (i == 0 && fresh_call) ? 1536 : 0;                              // DY4_TAB_EARLY (dy4_plltab.h)
         const bool prep_on_pll = p->pll_table && i == 1 && fresh_call;
-        if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
-        // the RDS branch of sub-chunk i-2 read this workspace set and this slot of the IF-tail ring: let it finish first
-        if ((p->flags & DY4_FLAG_RDS) && i >= (size_t)dy4_pipeline::NSETS) CU(cudaStreamWaitEvent(st, p->ev_rds_set[c.set], 0));
-        if ((rc = run_front(p, c, row_stride, if_stride, st))) return rc;
-        if (!p->pll_table && (rc = run_pll(p, c, st, DY4_PLL_PREP))) return rc;   // direct loop: its reciprocal pre-pass rides with the FIR kernels
-        CU(cudaEventRecord(p->ev_bpf[c.set], st));
         if (p->flags & DY4_FLAG_RDS) {                           // the RDS branch needs only the IF rows: beside everything else
-            CU(cudaStreamWaitEvent(p->s_rds, p->ev_bpf[c.set], 0));
+            CU(cudaStreamWaitEvent(p->s_rds, ev_fir, 0));
             if ((rc = run_rds(p, c, p->s_rds))) return rc;
-            CU(cudaEventRecord(p->ev_rds_set[c.set], p->s_rds));
             CU(cudaEventRecord(p->ev_rds, p->s_rds));
         }
+        const bool reuse = p->seq - seq0 >= dy4_pipeline::NSETS || seq0 > 0;      // this workspace set has been used before: wait for its last reader
         if (p->pll_table && !prep_on_pll) {
-            // prediction + table on the AUX stream: FP64-bound, they run beside the FP32-bound FIR kernels of the next sub-chunk
-            // (which the main stream goes on to queue) instead of in line with them.  Ordering: they read the pilot row front(c)
-            // just wrote; the previous prediction (same stream) and, two launches back, the loop's turn report are complete.
-            CU(cudaStreamWaitEvent(p->s_aux, p->ev_bpf[c.set], 0));
+            // prediction + table on the AUX stream: FP64-bound, they run beside the FP32-bound FIR kernels instead of in line
+            // with them.  They read the pilot rows of their FIR piece; the previous prediction (same stream) and, NSETS
+            // launches back, the loop's turn report are complete.
+            CU(cudaStreamWaitEvent(p->s_aux, ev_fir, 0));
+            if (reuse) CU(cudaStreamWaitEvent(p->s_aux, p->ev_back[c.set], 0));
             if (i == 2 && fresh_call) CU(cudaStreamWaitEvent(p->s_aux, p->ev_prep1, 0));
             if ((rc = run_pll(p, c, p->s_aux, DY4_PLL_PREP))) return rc;
             CU(cudaEventRecord(p->ev_prep[c.set], p->s_aux));
             CU(cudaStreamWaitEvent(p->s_pll, p->ev_prep[c.set], 0));
-        } else CU(cudaStreamWaitEvent(p->s_pll, p->ev_bpf[c.set], 0));
-        if (prep_on_pll) {
-            // prediction + table of sub-chunk 1 from the exact state loop(0) leaves; the prediction of sub-chunk 2 (main
-            // stream) continues from this one's state, so it waits for it
-            if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_PREP))) return rc;
-            CU(cudaEventRecord(p->ev_prep1, p->s_pll));
+        } else {
+            CU(cudaStreamWaitEvent(p->s_pll, ev_fir, 0));
+            if (reuse) CU(cudaStreamWaitEvent(p->s_pll, p->ev_back[c.set], 0));
+            if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_PREP))) return rc;          // direct loop: reciprocals; fresh stream: sub-chunk 1 from the exact state
+            if (prep_on_pll) CU(cudaEventRecord(p->ev_prep1, p->s_pll));
         }
         if ((rc = run_pll(p, c, p->s_pll, DY4_PLL_LOOP))) return rc;
         CU(cudaEventRecord(p->ev_pll[c.set], p->s_pll));
-        pend.push_back({c, b, (int)i});
+        pend.push_back({c, (int)i});
         if ((int)pend.size() >= dy4_pipeline::NSETS && (rc = flush_back())) return rc;
     }
     while (!pend.empty()) if ((rc = flush_back())) return rc;
     if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
-    return DY4_OK;
+    return finish_call();
 }
 
 }  // namespace
@@ -626,7 +677,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
         CU(cudaMalloc(&p->rds_counts, S * 4 * sizeof(int)));
     }
     CU(cudaMalloc(&p->iq_tail, S * DY4_IQ_TAIL));
-    CU(cudaMalloc(&p->if_tail, (dy4_pipeline::NSETS + 1) * S * DY4_IF_TAIL * sizeof(float)));
+    CU(cudaMalloc(&p->if_tail, S * DY4_IF_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->mix_tail, S * DY4_MIX_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->pll_state, S * 8 * sizeof(float)));
     int rc = init_state(p, nullptr);
@@ -662,14 +713,16 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
     cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
     cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_groups); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
-    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); for (int i = 0; i < dy4_pipeline::NSETS; i++) cudaEventDestroy(p->ev_rds_set[i]); }
+    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
-    for (auto& w : p->ws) { cudaFree(w.w_if); cudaFree(w.pilot); cudaFree(w.sband); cudaFree(w.nco); cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
+    for (auto& w : p->ws) { cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
+    cudaFree(p->c_if); cudaFree(p->c_pilot); cudaFree(p->c_sband); cudaFree(p->c_nco);
+    for (auto e : p->ev_fir) cudaEventDestroy(e);
     cudaFree(p->ws_nco0); cudaFree(p->pred_state); cudaFree(p->pll_risk);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
         if (p->s_aux) cudaStreamDestroy(p->s_aux);
-        for (int i = 0; i < dy4_pipeline::NSETS; i++) { cudaEventDestroy(p->ev_bpf[i]); cudaEventDestroy(p->ev_pll[i]); if (p->ev_prep[i]) cudaEventDestroy(p->ev_prep[i]); }
+        for (int i = 0; i < dy4_pipeline::NSETS; i++) { cudaEventDestroy(p->ev_back[i]); cudaEventDestroy(p->ev_pll[i]); cudaEventDestroy(p->ev_prep[i]); }
         if (p->ev_prep1) cudaEventDestroy(p->ev_prep1);
         cudaEventDestroy(p->ev_in);
     }
@@ -694,8 +747,17 @@ extern "C" int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size
     CU(cudaSetDevice(p->device));
     const int ch = p->stereo ? 2 : 1;
     const size_t astride = (size_t)n_blocks * m.audio_per_block * ch;
-    return process_device(p, d_iq, row_stride_bytes, n_blocks, d_pcm, d_audio, d_if, (cudaStream_t)stream,
-                          astride, astride, (size_t)n_blocks * m.if_per_block);
+    // the call rows (16 bytes per IF sample) hold a window of the call; very large calls go through in several windows
+    const int window = std::min(n_blocks, max_call_blocks(p));
+    { const int rc = rds_begin_call(p, n_blocks); if (rc) return rc; }
+    for (int w0 = 0; w0 < n_blocks; w0 += window) {
+        const size_t ao = (size_t)w0 * m.audio_per_block * ch;
+        const int rc = process_device(p, d_iq + (size_t)w0 * m.block_size, row_stride_bytes, std::min(window, n_blocks - w0),
+                                      d_pcm ? d_pcm + ao : nullptr, d_audio ? d_audio + ao : nullptr, d_if ? d_if + (size_t)w0 * m.if_per_block : nullptr,
+                                      (cudaStream_t)stream, astride, astride, (size_t)n_blocks * m.if_per_block);
+        if (rc) return rc;
+    }
+    return DY4_OK;
 }
 
 extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
@@ -715,7 +777,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     size_t budget = 4ull << 30;
     if (const char* e = std::getenv("DY4_STAGE_BYTES")) budget = std::strtoull(e, nullptr, 10);
     int window = chunk_blocks > 0 ? chunk_blocks : (int)std::max<size_t>(1, budget / (S * m.block_size));
-    window = std::min(window, n_blocks);
+    window = std::min(std::min(window, n_blocks), max_call_blocks(p));
     if (!p->streams_ready) {
         CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
@@ -736,6 +798,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     const size_t out_stride = (size_t)p->stage_blocks * m.audio_per_block * ch;
     const size_t total_audio = (size_t)n_blocks * m.audio_per_block * ch;                // host output row length
 
+    { const int rc = rds_begin_call(p, n_blocks); if (rc) return rc; }
     for (int w0 = 0; w0 < n_blocks; w0 += window) {
         const int wn = std::min(window, n_blocks - w0);
         int rc = ensure_workspace(p, wn);
@@ -781,12 +844,12 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
 
 extern "C" int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pilot, const float** d_nco, size_t* stride, int* n_if)
 {
-    if (!p || !p->stereo || !p->ws[0].pilot) { dy4_set_error("dy4_pipeline_debug_buffers: no stereo sub-chunk processed yet"); return DY4_ERR_ARG; }
+    if (!p || !p->stereo || !p->c_pilot) { dy4_set_error("dy4_pipeline_debug_buffers: no stereo sub-chunk processed yet"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
-    if (d_pilot) *d_pilot = p->ws[p->last_set].pilot;
-    if (d_nco) *d_nco = p->ws[p->last_set].nco;
-    if (stride) *stride = p->ws_stride;
+    if (d_pilot) *d_pilot = p->c_pilot + p->last_off;
+    if (d_nco) *d_nco = p->c_nco + p->last_off;
+    if (stride) *stride = p->c_stride;
     if (n_if) *n_if = p->last_n_if;
     return DY4_OK;
 }
@@ -919,7 +982,7 @@ extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
     const size_t S = (size_t)p->n_streams;
     char* o = (char*)host_buf;
     CU(cudaMemcpy(o, p->iq_tail, S * DY4_IQ_TAIL, cudaMemcpyDeviceToHost)); o += S * DY4_IQ_TAIL;
-    CU(cudaMemcpy(o, if_tail_slot(p, p->seq), S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
+    CU(cudaMemcpy(o, p->if_tail, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(o, p->mix_tail, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyDeviceToHost)); o += S * DY4_MIX_TAIL * sizeof(float);
     CU(cudaMemcpy(o, p->pll_state, S * 8 * sizeof(float), cudaMemcpyDeviceToHost)); o += S * 8 * sizeof(float);
     if (p->flags & DY4_FLAG_RDS) {
@@ -947,7 +1010,7 @@ extern "C" int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf)
     const size_t S = (size_t)p->n_streams;
     const char* o = (const char*)host_buf;
     CU(cudaMemcpy(p->iq_tail, o, S * DY4_IQ_TAIL, cudaMemcpyHostToDevice)); o += S * DY4_IQ_TAIL;
-    CU(cudaMemcpy(if_tail_slot(p, p->seq), o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
+    CU(cudaMemcpy(p->if_tail, o, S * DY4_IF_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_IF_TAIL * sizeof(float);
     CU(cudaMemcpy(p->mix_tail, o, S * DY4_MIX_TAIL * sizeof(float), cudaMemcpyHostToDevice)); o += S * DY4_MIX_TAIL * sizeof(float);
     CU(cudaMemcpy(p->pll_state, o, S * 8 * sizeof(float), cudaMemcpyHostToDevice)); o += S * 8 * sizeof(float);
     if (p->flags & DY4_FLAG_RDS) {

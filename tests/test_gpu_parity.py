@@ -131,6 +131,34 @@ def test_chunking_and_subchunking_do_not_change_results(dy4, monkeypatch):
         assert np.array_equal(sub[k], one[k]), k
 
 
+def test_call_windows_do_not_change_results(dy4, monkeypatch):
+    """A call whose IF / pilot / stereo-band / NCO rows exceed the row budget goes through in several windows (dy4_pipeline_process):
+    PCM, audio, IF rows and the RDS baseband of the whole call are those of the single-window call."""
+    import torch
+    m = dy4.mode_params(0)
+    S, nb = 3, 20
+    d = dy4.synth.make_batch_torch(0, S, nb * m.block_size // 2, base_seed=91, device="cuda", rds=True)
+
+    def run():
+        p = dy4.Pipeline(0, 1, S, rds=True)
+        out = p.process(d, want=("pcm", "audio", "if"))
+        ri, rq = p.rds_read()
+        torch.cuda.synchronize()
+        dr = p.rds_drain()
+        p.close()
+        return out, ri.cpu().numpy(), rq.cpu().numpy(), dr
+
+    one, ri1, rq1, dr1 = run()
+    monkeypatch.setenv("DY4_WS_BYTES", str(S * m.if_per_block * 16 * 7 // 4))     # rows for 7 blocks: windows of 7, 7, 6
+    win, ri2, rq2, dr2 = run()
+    for k in one:
+        assert torch.equal(one[k], win[k]), k
+    assert ri1.shape == ri2.shape and np.array_equal(bits(ri1), bits(ri2)) and np.array_equal(bits(rq1), bits(rq2))
+    for s in range(S):
+        for k in ("symbols", "bits", "events", "groups"):
+            assert np.array_equal(dr1[s][k], dr2[s][k]), (s, k)
+
+
 @pytest.mark.parametrize("mode,stereo", [(0, 1), (1, 0), (3, 1)])
 def test_host_path_equals_device_path(dy4, mode, stereo):
     import torch
