@@ -129,3 +129,7 @@ cudaError_t dy4_launch_generic_resample(const float* x_ext, int n_hist, int n_ou
 cudaError_t dy4_launch_generic_demod(const float* I, const float* Q, int n, float prev_I, float prev_Q, float* out, cudaStream_t st);
 cudaError_t dy4_launch_u8_to_float(const uint8_t* raw, long long n, float* out, cudaStream_t st);
 cudaError_t dy4_launch_pointwise(int op, const float* a, const float* b, int n, float* out, cudaStream_t st);
+
+// SM partition (dy4_smpart.cu): green contexts that keep the PLL's serial loops on SMs of their own
+int dy4_sm_partition(int device, int loop_sms, int* n_loop, int* n_rest);
+cudaError_t dy4_sm_partition_stream(int device, int loop_sms, int which, int priority, cudaStream_t* s);

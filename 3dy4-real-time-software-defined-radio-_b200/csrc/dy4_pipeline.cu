@@ -77,6 +77,10 @@ struct dy4_pipeline {
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
     cudaStream_t s_aux = nullptr;                    // the PLL's time-parallel FP64 kernels (prediction, table) run here, beside the FP32-bound FIR kernels
+    // SM partition (dy4_smpart.cu): the loops' stream runs on loop_sms SMs of its own, every other stream of a stereo call on the rest;
+    // the caller's stream forks into s_main at the start of a call and joins at its end
+    cudaStream_t s_main = nullptr; cudaEvent_t ev_out = nullptr; int loop_sms = 0, rest_sms = 0;
+    cudaStream_t s_back = nullptr; cudaEvent_t ev_fir_all = nullptr;     // the back halves' stream: not behind the call's FIR launches
     cudaEvent_t ev_back[NSETS] = {}, ev_pll[NSETS] = {}, ev_prep[NSETS] = {}, ev_in = nullptr, ev_prep1 = nullptr;
     std::vector<cudaEvent_t> ev_fir;                 // one per FIR piece of a call
     // host-facing staging
@@ -213,8 +217,31 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     if (p->pll_table && !p->pll_risk) { CU(cudaMalloc(&p->pll_risk, (size_t)p->n_streams * sizeof(int))); CU(cudaMemset(p->pll_risk, 0, (size_t)p->n_streams * sizeof(int))); }
     if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));   // [NSETS][S][8] predictor state + [NSETS][S] turns
     if (p->stereo && !p->s_pll) {
-        CU(cudaStreamCreateWithFlags(&p->s_pll, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
+        // SM partition, opt-in (DY4_LOOP_SMS = SMs set aside for the serial loops, a multiple of 8; dy4_smpart.cu).  The loops
+        // are bound by the issue rate of ONE warp per stream, and warps of other kernels on the same SM sub-partition take issue
+        // slots from it: on SMs of their own, one warp per sub-partition, they run at 14.5 ns per sample instead of 20-25.
+        // It is not the default because the other kernels then have fewer SMs and become the bound (DESIGN.md 4.3.3:
+        // 256 streams 6.69 ms unpartitioned, 6.92 with 32 loop SMs, 7.47 with 64; 128 streams 5.13 -> 4.68 with 32).
+        int want = 0;
+        if (const char* e = std::getenv("DY4_LOOP_SMS")) want = atoi(e);
+        // Stream priorities: a CTA of a higher-priority stream is dispatched before the pending CTAs of a lower one.  Without
+        // them the one-block prediction of the first sub-chunk queues behind every CTA of the call's FIR launches.
+        int pr_least = 0, pr_greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        const int pr_loop = pr_greatest, pr_aux = std::min(pr_least, pr_greatest + 1);
+        if (want > 0 && dy4_sm_partition(p->device, want, &p->loop_sms, &p->rest_sms)) {
+            CU(dy4_sm_partition_stream(p->device, want, 0, pr_loop, &p->s_pll));
+            CU(dy4_sm_partition_stream(p->device, want, 1, pr_aux, &p->s_aux));
+            CU(dy4_sm_partition_stream(p->device, want, 1, pr_least, &p->s_main));
+            CU(dy4_sm_partition_stream(p->device, want, 1, pr_aux, &p->s_back));
+            if ((p->flags & DY4_FLAG_RDS) && !p->s_rds) CU(dy4_sm_partition_stream(p->device, want, 1, pr_least, &p->s_rds));
+            CU(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+        } else {
+            CU(cudaStreamCreateWithPriority(&p->s_pll, cudaStreamNonBlocking, pr_loop));
+            CU(cudaStreamCreateWithPriority(&p->s_aux, cudaStreamNonBlocking, pr_aux));
+            CU(cudaStreamCreateWithPriority(&p->s_back, cudaStreamNonBlocking, pr_aux));
+        }
+        CU(cudaEventCreateWithFlags(&p->ev_fir_all, cudaEventDisableTiming));
         for (int i = 0; i < dy4_pipeline::NSETS; i++) {
             CU(cudaEventCreateWithFlags(&p->ev_back[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_prep[i], cudaEventDisableTiming));
@@ -230,8 +257,8 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         CU(cudaMalloc(&p->rds_nco_i, bytes)); CU(cudaMalloc(&p->rds_nco_q, bytes)); CU(cudaMalloc(&p->rds_theta, 2 * bytes));
         p->rds_cap = (p->ws_stride * 19 + 119) / 120 + 4;
         CU(cudaMalloc(&p->rds_lp, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
-        if (!p->s_rds) {
-            CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
+        if (!p->ev_rds) {
+            if (!p->s_rds) CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
         }
@@ -459,7 +486,7 @@ int run_back(dy4_pipeline* p, const SubChunk& c, size_t pcm_stride, size_t audio
 
 // Optional per-sub-chunk hooks of the host-facing path: wait for that sub-chunk's upload before its FIR work,
 // start the download of its PCM after its back half.  Arguments: first block and number of blocks of the sub-chunk.
-struct Hooks { std::function<int(int, int, int)> before_front, after_back; };   // (index, first block, blocks)
+struct Hooks { std::function<int(int, int, int, cudaStream_t)> before_front, after_back; };   // (index, first block, blocks, the stream the sub-chunk's kernels are on)
 
 // The sub-chunks of a stereo job grow geometrically — 1, 2, 4, ... blocks up to the workspace size, then that size —
 // so that (a) only one block's FIR work and, on the host path, one block's upload precede the first PLL launch, and
@@ -524,58 +551,79 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         for (size_t i = 0; i < plan.size(); i++, p->seq++) {
             const int b = plan[i].first;
             const SubChunk c = sub(b, plan[i].second, p->seq);
-            if (hooks && (rc = hooks->before_front((int)i, b, c.nb))) return rc;
+            if (hooks && (rc = hooks->before_front((int)i, b, c.nb, st))) return rc;
             if ((rc = run_fir(p, d_iq, row_stride, b, c.nb, st))) return rc;
             if ((rc = run_back(p, c, pcm_stride, audio_stride, st))) return rc;
-            if (hooks && (rc = hooks->after_back((int)i, b, c.nb))) return rc;
+            if (hooks && (rc = hooks->after_back((int)i, b, c.nb, st))) return rc;
         }
         return finish_call();
     }
-    // stereo: software pipeline over three streams and NSETS = 3 workspace sets.
-    //   main stream:  fir(piece 0) fir(piece 1) ... back(0) back(1) ...  back(last)             FIR kernels; NCO row + audio
-    //   aux stream:        prep(0)  prep(1)  prep(2) ...                                         prediction + table (FP64)
-    //   PLL stream:                loop(0)   loop(1)   loop(2) ...                               the serial loops, back to back
+    // stereo: software pipeline over four streams and NSETS = 3 workspace sets.
+    //   main stream:  fir(piece 0) fir(piece 1) ...                               ... if_tail      FIR kernels of the whole call, up front
+    //   aux stream:        prep(0)  prep(1)  prep(2) ...                                          prediction + table (FP64)
+    //   PLL stream:                loop(0)   loop(1)   loop(2) ...                                the serial loops, back to back
+    //   back stream:                        back(0)   back(1)  ...  back(last)                    NCO row + audio
     // FIR PIECES are full-wave launches over many sub-chunks: with the input on the device, piece 0 is the first sub-chunk
-    // (one block: the first serial loop starts after 1/48 of the FIR work) and piece 1 everything else; on the host path
-    // (hooks) every sub-chunk is its own piece, gated on ITS upload.  fir(piece) -> prep(c) -> loop(c) -> back(c) by events;
-    // prep(c) also waits for back(c - NSETS), the last reader of its workspace set.
+    // (one block: the first serial loop starts after 1/48 of the FIR work) and piece 1 everything else (more pieces were
+    // measured: their smaller launches cost more than the earlier start of sub-chunks 1..3 saves, 6.97 against 6.69 ms); on the
+    // host path (hooks) every sub-chunk is its own piece, gated on ITS upload, and the back halves stay on the main stream.
+    // fir(piece) -> prep(c) -> loop(c) -> back(c) by events; prep(c) also waits for back(c - NSETS), the last reader of its
+    // workspace set.  The loops' stream has the highest priority, aux and back the next, the FIR launches the lowest.
     std::vector<std::pair<int, int>> pieces;           // (first sub-chunk, sub-chunks)
-    if (hooks || plan.size() < 2) for (size_t i = 0; i < plan.size(); i++) pieces.push_back({(int)i, 1});
-    else { pieces.push_back({0, 1}); pieces.push_back({1, (int)plan.size() - 1}); }
+    if (hooks) for (size_t i = 0; i < plan.size(); i++) pieces.push_back({(int)i, 1});
+    else {                                             // {first sub-chunk}, {the rest}
+        pieces.push_back({0, 1});
+        if (plan.size() > 1) pieces.push_back({1, (int)plan.size() - 1});
+    }
     while (p->ev_fir.size() < pieces.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->ev_fir.push_back(e); }
     CU(cudaEventRecord(p->ev_in, st));
     CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
+    cudaStream_t const caller = st;
+    if (p->s_main) {                                   // SM partition: the call's own kernels run on the SMs the loops do not use
+        CU(cudaStreamWaitEvent(p->s_main, p->ev_in, 0));
+        st = p->s_main;
+    }
     const bool fresh_call = p->pll_fresh;              // no sample processed since create / reset: the streams start in this call
     p->pll_fresh = false;
     // back halves still to be queued (at most NSETS - 1 of them)
     struct Pending { SubChunk c; int i; };
     std::vector<Pending> pend;
+    // the back halves run on a stream of their own when the input is on the device (on the main stream they would sit behind
+    // every FIR launch of the call, and so would the predictions that wait for their workspace set)
+    cudaStream_t sb = hooks ? st : p->s_back;
+    if (sb != st) CU(cudaStreamWaitEvent(sb, p->ev_in, 0));
     auto flush_back = [&]() -> int {
         const Pending q = pend.front();
         pend.erase(pend.begin());
-        CU(cudaStreamWaitEvent(st, p->ev_pll[q.c.set], 0));
+        CU(cudaStreamWaitEvent(sb, p->ev_pll[q.c.set], 0));
         int r2;
-        if ((r2 = run_pll(p, q.c, st, DY4_PLL_NCO))) return r2;
-        if ((r2 = run_back(p, q.c, pcm_stride, audio_stride, st))) return r2;
-        CU(cudaEventRecord(p->ev_back[q.c.set], st));
-        if (hooks && (r2 = hooks->after_back(q.i, q.c.b, q.c.nb))) return r2;
+        if ((r2 = run_pll(p, q.c, sb, DY4_PLL_NCO))) return r2;
+        if ((r2 = run_back(p, q.c, pcm_stride, audio_stride, sb))) return r2;
+        CU(cudaEventRecord(p->ev_back[q.c.set], sb));
+        if (hooks && (r2 = hooks->after_back(q.i, q.c.b, q.c.nb, sb))) return r2;
         return DY4_OK;
     };
-    size_t next_piece = 0;
     std::vector<int> piece_of(plan.size(), 0);
     for (size_t k = 0; k < pieces.size(); k++) for (int j = 0; j < pieces[k].second; j++) piece_of[pieces[k].first + j] = (int)k;
+    size_t next_piece = 0;
+    auto queue_piece = [&]() -> int {
+        const int s0 = pieces[next_piece].first, ns = pieces[next_piece].second;
+        const int b0 = plan[s0].first, nb = plan[s0 + ns - 1].first + plan[s0 + ns - 1].second - b0;
+        int r2;
+        if (hooks && (r2 = hooks->before_front(s0, b0, nb, st))) return r2;
+        if ((r2 = run_fir(p, d_iq, row_stride, b0, nb, st))) return r2;
+        CU(cudaEventRecord(p->ev_fir[next_piece], st));
+        next_piece++;
+        return DY4_OK;
+    };
+    // input on the device: every FIR piece is queued before anything else of the call (nothing they wait for; the back halves
+    // queued on the same stream later wait for the loops).  Host path: a piece is queued when its sub-chunk comes up, so that
+    // the back halves (and the downloads behind them) are not held up by uploads still to come.
+    if (!hooks) while (next_piece < pieces.size()) if ((rc = queue_piece())) return rc;
     const long long seq0 = p->seq;
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
         SubChunk c = sub(plan[i].first, plan[i].second, p->seq);
-        // the FIR piece this sub-chunk belongs to (queued once, when its first sub-chunk comes up)
-        while (next_piece <= (size_t)piece_of[i]) {
-            const int s0 = pieces[next_piece].first, ns = pieces[next_piece].second;
-            const int b0 = plan[s0].first, nb = plan[s0 + ns - 1].first + plan[s0 + ns - 1].second - b0;
-            if (hooks && (rc = hooks->before_front(s0, b0, nb))) return rc;
-            if ((rc = run_fir(p, d_iq, row_stride, b0, nb, st))) return rc;
-            CU(cudaEventRecord(p->ev_fir[next_piece], st));
-            next_piece++;
-        }
+        while (next_piece <= (size_t)piece_of[i]) if ((rc = queue_piece())) return rc;
         cudaEvent_t ev_fir = p->ev_fir[piece_of[i]];
         // Table-driven PLL (dy4_pll.cu).  Sub-chunk 0 starts from the exact carried state; at the START of a stream its first
         // samples go through the direct loop while the PLL acquires lock, and sub-chunk 1 is predicted from the exact state
@@ -617,8 +665,17 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if ((int)pend.size() >= dy4_pipeline::NSETS && (rc = flush_back())) return rc;
     }
     while (!pend.empty()) if ((rc = flush_back())) return rc;
+    if (sb != st) {                                    // join: the call's last back half
+        CU(cudaEventRecord(p->ev_fir_all, sb));
+        CU(cudaStreamWaitEvent(st, p->ev_fir_all, 0));
+    }
     if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));
-    return finish_call();
+    if ((rc = finish_call())) return rc;
+    if (st != caller) {
+        CU(cudaEventRecord(p->ev_out, st));
+        CU(cudaStreamWaitEvent(caller, p->ev_out, 0));
+    }
+    return DY4_OK;
 }
 
 }  // namespace
@@ -722,6 +779,8 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
         if (p->s_aux) cudaStreamDestroy(p->s_aux);
+        if (p->s_main) { cudaStreamDestroy(p->s_main); cudaEventDestroy(p->ev_out); }
+        if (p->s_back) { cudaStreamDestroy(p->s_back); cudaEventDestroy(p->ev_fir_all); }
         for (int i = 0; i < dy4_pipeline::NSETS; i++) { cudaEventDestroy(p->ev_back[i]); cudaEventDestroy(p->ev_pll[i]); cudaEventDestroy(p->ev_prep[i]); }
         if (p->ev_prep1) cudaEventDestroy(p->ev_prep1);
         cudaEventDestroy(p->ev_in);
@@ -818,13 +877,13 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
             CU(cudaEventRecord(p->ev_up[i], p->s_h2d));
         }
         Hooks hooks;
-        hooks.before_front = [&](int i, int, int) -> int {
-            CU(cudaStreamWaitEvent(p->s_compute, p->ev_up[i], 0));
+        hooks.before_front = [&](int i, int, int, cudaStream_t cs) -> int {
+            CU(cudaStreamWaitEvent(cs, p->ev_up[i], 0));
             return DY4_OK;
         };
-        hooks.after_back = [&](int i, int b, int nb) -> int {
+        hooks.after_back = [&](int i, int b, int nb, cudaStream_t cs) -> int {
             const size_t na = (size_t)nb * m.audio_per_block * ch, off = (size_t)b * m.audio_per_block * ch;
-            CU(cudaEventRecord(p->ev_done[i], p->s_compute));
+            CU(cudaEventRecord(p->ev_done[i], cs));
             CU(cudaStreamWaitEvent(p->s_d2h, p->ev_done[i], 0));
             if (h_pcm) CU(cudaMemcpy2DAsync(h_pcm + (size_t)w0 * m.audio_per_block * ch + off, total_audio * sizeof(int16_t), p->d_pcm_stage + off,
                                             out_stride * sizeof(int16_t), na * sizeof(int16_t), S, cudaMemcpyDeviceToHost, p->s_d2h));
@@ -916,6 +975,14 @@ extern "C" int dy4_pipeline_rds_drain(dy4_pipeline_t* p, int8_t* h_symbols, size
     return DY4_OK;
 }
 
+extern "C" int dy4_pipeline_sm_partition(dy4_pipeline_t* p, int* loop_sms, int* rest_sms)
+{
+    if (!p) { dy4_set_error("dy4_pipeline_sm_partition: bad arguments"); return DY4_ERR_ARG; }
+    if (loop_sms) *loop_sms = p->s_main ? p->loop_sms : 0;
+    if (rest_sms) *rest_sms = p->s_main ? p->rest_sms : 0;
+    return DY4_OK;
+}
+
 extern "C" int dy4_pipeline_pll_risk(dy4_pipeline_t* p, int32_t* h_counts, int reset)
 {
     if (!p || !h_counts) { dy4_set_error("dy4_pipeline_pll_risk: bad arguments"); return DY4_ERR_ARG; }
@@ -939,10 +1006,16 @@ extern "C" int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long
 {
     if (!p) return DY4_ERR_ARG;
     CU(cudaSetDevice(p->device));
+    const bool trace = std::getenv("DY4_TRACE") != nullptr && !p->recs.empty();      // development: the timeline of every timed launch
     for (auto& r : p->recs) {
         CU(cudaEventSynchronize(r.e1));
         float t = 0.f;
         CU(cudaEventElapsedTime(&t, r.e0, r.e1));
+        if (trace) {
+            float t0 = 0.f;
+            CU(cudaEventElapsedTime(&t0, p->recs.front().e0, r.e0));
+            std::fprintf(stderr, "dy4-trace k=%d start=%.4f end=%.4f ms\n", r.k, t0, t0 + t);
+        }
         p->acc_ms[r.k] += t; p->acc_n[r.k] += 1;
         p->pool.push_back(r.e0); p->pool.push_back(r.e1);
     }

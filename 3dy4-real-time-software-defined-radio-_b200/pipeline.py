@@ -157,6 +157,12 @@ class Pipeline:
         check(lib.dy4_pipeline_pll_risk(self._h, C.c_void_p(out.ctypes.data), int(reset)), "dy4_pipeline_pll_risk")
         return out
 
+    def sm_partition(self):
+        """(loop SMs, other SMs) of the opt-in SM partition (DY4_LOOP_SMS), (0, 0) when unpartitioned (dy4_pipeline_sm_partition)."""
+        a, b = C.c_int(0), C.c_int(0)
+        check(lib.dy4_pipeline_sm_partition(self._h, C.byref(a), C.byref(b)), "dy4_pipeline_sm_partition")
+        return a.value, b.value
+
     def profile(self, enable=True):
         check(lib.dy4_pipeline_profile(self._h, int(enable)), "dy4_pipeline_profile")
 

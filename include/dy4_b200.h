@@ -232,6 +232,10 @@ int dy4_pipeline_profile_get(dy4_pipeline_t* p, double* ms, long long* launches,
  * than the reference's glibc could produce a different float.  One count per stream (table-driven PLL loop; streams on the direct
  * loop and mono receivers report 0), accumulated since create / the last call with reset != 0.  h_counts: int32[n_streams]. */
 int dy4_pipeline_pll_risk(dy4_pipeline_t* p, int32_t* h_counts, int reset);
+/* SM partition of a stereo pipeline (opt-in, environment DY4_LOOP_SMS=<multiple of 8>; CUDA green contexts): SMs that run only
+ * the PLL's serial loops / SMs for everything else.  Both 0 when the pipeline runs unpartitioned (the default, or green
+ * contexts unavailable) or has not processed a stereo call yet. */
+int dy4_pipeline_sm_partition(dy4_pipeline_t* p, int* loop_sms, int* rest_sms);
 /* total kernels launched by this library in this process */
 long long dy4_launch_count(void);
 

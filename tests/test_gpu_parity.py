@@ -159,6 +159,33 @@ def test_call_windows_do_not_change_results(dy4, monkeypatch):
             assert np.array_equal(dr1[s][k], dr2[s][k]), (s, k)
 
 
+def test_sm_partition_does_not_change_results(dy4, monkeypatch):
+    """DY4_LOOP_SMS (opt-in, dy4_smpart.cu): the serial loops on a green context of 32 SMs, every other kernel on the rest; the
+    caller's stream forks into the partition's streams and joins at the end of the call.  Same bits out, call after call."""
+    import torch
+    m = dy4.mode_params(0)
+    S, nb = 24, 12
+    d = dy4.synth.make_batch_torch(0, S, 2 * nb * m.block_size // 2, base_seed=301, device="cuda")
+
+    def run():
+        p = dy4.Pipeline(0, 1, S)
+        a = p.process(d[:, :nb * m.block_size], want=("pcm", "audio"))
+        b = p.process(d[:, nb * m.block_size:], want=("pcm", "audio"))
+        torch.cuda.synchronize()
+        part = p.sm_partition()
+        p.close()
+        return a, b, part
+
+    *one, part = run()
+    assert part == (0, 0)
+    monkeypatch.setenv("DY4_LOOP_SMS", "32")
+    *two, part = run()
+    assert part[0] >= 32 and sum(part) == torch.cuda.get_device_properties(0).multi_processor_count, part
+    for x, y in zip(one, two):
+        for k in x:
+            assert torch.equal(x[k], y[k]), k
+
+
 @pytest.mark.parametrize("mode,stereo", [(0, 1), (1, 0), (3, 1)])
 def test_host_path_equals_device_path(dy4, mode, stereo):
     import torch
