@@ -81,6 +81,13 @@ struct dy4_pipeline {
     // the caller's stream forks into s_main at the start of a call and joins at its end
     cudaStream_t s_main = nullptr; cudaEvent_t ev_out = nullptr; int loop_sms = 0, rest_sms = 0;
     cudaStream_t s_back = nullptr; cudaEvent_t ev_fir_all = nullptr;     // the back halves' stream: not behind the call's FIR launches
+    // DY4_FLAG_PIPELINED: consecutive device-path calls overlap.  Two sets of call rows and two IF histories alternate, so that a
+    // call's FIR launches can run while the call before is still being read; no join to the caller's stream at the end of a call.
+    bool pipelined = false;
+    float* rows_alt[4] = {nullptr, nullptr, nullptr, nullptr}; float* if_tail_alt[2] = {nullptr, nullptr};    // with if_tail: a ring of three IF histories
+    const float* call_hist = nullptr;                // IF history of the call being queued (if_tail moves on as soon as its FIR work is queued)
+    cudaEvent_t ev_call_done[2] = {nullptr, nullptr}, ev_main_done = nullptr;
+    int call_parity = 0;
     cudaEvent_t ev_back[NSETS] = {}, ev_pll[NSETS] = {}, ev_prep[NSETS] = {}, ev_in = nullptr, ev_prep1 = nullptr;
     std::vector<cudaEvent_t> ev_fir;                 // one per FIR piece of a call
     // host-facing staging
@@ -148,6 +155,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
     CU(cudaMemsetAsync(p->if_tail, 0, S * DY4_IF_TAIL * sizeof(float), st));
     p->seq = 0;
     p->pll_fresh = true;
+    if (p->pred_state) CU(cudaMemsetAsync(p->pred_state, 0, dy4_pipeline::NSETS * S * 9 * sizeof(double), st));
     CU(cudaMemsetAsync(p->mix_tail, 0, S * DY4_MIX_TAIL * sizeof(float), st));
     std::vector<float> h(S * 8, 0.0f);
     for (size_t s = 0; s < S; s++) { h[s * 8 + 0] = 1.0f; h[s * 8 + 5] = 1.0f; }   // PLLState, project.cpp:46-53
@@ -171,6 +179,14 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
         p->rds_left = 0; p->rds_consumed = 0; p->rds_blocks_since_drain = 0;
     }
     CU(cudaStreamSynchronize(st));
+    return DY4_OK;
+}
+
+// everything this pipeline has queued, on every stream of its own, is done
+int quiesce(dy4_pipeline* p)
+{
+    for (cudaStream_t s : {p->s_main, p->s_aux, p->s_pll, p->s_back, p->s_rds}) if (s) CU(cudaStreamSynchronize(s));
+    CU(cudaDeviceSynchronize());
     return DY4_OK;
 }
 
@@ -201,7 +217,7 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
     if (whole) blocks = std::max(blocks, n_blocks);
     if (p->ws_blocks >= blocks && (p->ws_blocks == blocks || whole || n_blocks < 8 || !p->stereo)) return DY4_OK;
     if (p->ws_blocks > 0) {
-        CU(cudaDeviceSynchronize());
+        { const int rq = quiesce(p); if (rq) return rq; }
         for (auto& w : p->ws) { cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); w = dy4_pipeline::WorkSet(); }
         p->ws_blocks = 0;
     }
@@ -215,7 +231,10 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         }
     if (p->stereo && !p->ws_nco0) CU(cudaMalloc(&p->ws_nco0, 3 * dy4_pipeline::NSETS * (size_t)p->n_streams * sizeof(float)));   // one row per workspace set: NCO carry, sample counter, second NCO carry
     if (p->pll_table && !p->pll_risk) { CU(cudaMalloc(&p->pll_risk, (size_t)p->n_streams * sizeof(int))); CU(cudaMemset(p->pll_risk, 0, (size_t)p->n_streams * sizeof(int))); }
-    if (p->pll_table && !p->pred_state) CU(cudaMalloc(&p->pred_state, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));   // [NSETS][S][8] predictor state + [NSETS][S] turns
+    if (p->pll_table && !p->pred_state) {              // [NSETS][S][8] predictor state + [NSETS][S] turns
+        CU(cudaMalloc(&p->pred_state, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));
+        CU(cudaMemset(p->pred_state, 0, dy4_pipeline::NSETS * (size_t)p->n_streams * 9 * sizeof(double)));
+    }
     if (p->stereo && !p->s_pll) {
         // SM partition, opt-in (DY4_LOOP_SMS = SMs set aside for the serial loops, a multiple of 8; dy4_smpart.cu).  The loops
         // are bound by the issue rate of ONE warp per stream, and warps of other kernels on the same SM sub-partition take issue
@@ -223,6 +242,10 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         // It is not the default because the other kernels then have fewer SMs and become the bound (DESIGN.md 4.3.3:
         // 256 streams 6.69 ms unpartitioned, 6.92 with 32 loop SMs, 7.47 with 64; 128 streams 5.13 -> 4.68 with 32).
         int want = 0;
+        // Pipelined calls (DY4_FLAG_PIPELINED) are the case the partition is made for: the other kernels of the NEXT call run
+        // while this call's loops do, so the loops' SMs are never idle and the rest never waits for a ramp.  32 SMs hold 256
+        // loop warps two to a sub-partition (18.7 ns per sample), 128 one to a sub-partition (14.5).
+        if (p->pipelined && p->pll_table && p->n_streams <= 256) want = std::min(32, std::max(8, (p->n_streams + 31) / 32 * 8));
         if (const char* e = std::getenv("DY4_LOOP_SMS")) want = atoi(e);
         // Stream priorities: a CTA of a higher-priority stream is dispatched before the pending CTAs of a lower one.  Without
         // them the one-block prediction of the first sub-chunk queues behind every CTA of the call's FIR launches.
@@ -240,8 +263,16 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
             CU(cudaStreamCreateWithPriority(&p->s_pll, cudaStreamNonBlocking, pr_loop));
             CU(cudaStreamCreateWithPriority(&p->s_aux, cudaStreamNonBlocking, pr_aux));
             CU(cudaStreamCreateWithPriority(&p->s_back, cudaStreamNonBlocking, pr_aux));
+            if (p->pipelined) {                            // the FIR launches need a stream that is never joined to the caller's
+                CU(cudaStreamCreateWithPriority(&p->s_main, cudaStreamNonBlocking, pr_least));
+                CU(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+            }
         }
         CU(cudaEventCreateWithFlags(&p->ev_fir_all, cudaEventDisableTiming));
+        if (p->pipelined) {
+            for (auto& e : p->ev_call_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p->ev_main_done, cudaEventDisableTiming));
+        }
         for (int i = 0; i < dy4_pipeline::NSETS; i++) {
             CU(cudaEventCreateWithFlags(&p->ev_back[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_prep[i], cudaEventDisableTiming));
@@ -272,20 +303,22 @@ int max_call_blocks(const dy4_pipeline* p)
 {
     size_t budget = 32ull << 30;
     if (const char* e = std::getenv("DY4_WS_BYTES")) budget = 4 * std::strtoull(e, nullptr, 10);
-    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * (p->stereo ? 16 : 4);
+    const size_t per_block = (size_t)p->n_streams * p->mp.if_per_block * (p->stereo ? (p->pipelined ? 32 : 16) : 4);
     return (int)std::max<size_t>(1, std::min<size_t>(budget / per_block, 1 << 20));
 }
 
 int ensure_call_rows(dy4_pipeline* p, int n_blocks)
 {
     if (n_blocks <= p->c_blocks) return DY4_OK;
-    if (p->c_blocks > 0) CU(cudaDeviceSynchronize());
+    if (p->c_blocks > 0) { int rq = quiesce(p); if (rq) return rq; }
     cudaFree(p->c_if); cudaFree(p->c_pilot); cudaFree(p->c_sband); cudaFree(p->c_nco);
+    for (auto& r : p->rows_alt) { cudaFree(r); r = nullptr; }
     p->c_if = p->c_pilot = p->c_sband = p->c_nco = nullptr; p->c_blocks = 0;
     p->c_stride = (size_t)n_blocks * p->mp.if_per_block;
     const size_t bytes = (size_t)p->n_streams * p->c_stride * sizeof(float);
     CU(cudaMalloc(&p->c_if, bytes));
     if (p->stereo) { CU(cudaMalloc(&p->c_pilot, bytes)); CU(cudaMalloc(&p->c_sband, bytes)); CU(cudaMalloc(&p->c_nco, bytes)); }
+    if (p->stereo && p->pipelined) for (auto& r : p->rows_alt) CU(cudaMalloc(&r, bytes));
     p->c_blocks = n_blocks;
     return DY4_OK;
 }
@@ -314,7 +347,7 @@ struct SubChunk {                        // one sub-chunk of a call: blocks [b, 
 struct Hist { const float* tail; long long stride; };
 Hist if_history(const dy4_pipeline* p, int b)
 {
-    if (b == 0) return {p->if_tail, (long long)DY4_IF_TAIL};
+    if (b == 0) return {p->call_hist, (long long)DY4_IF_TAIL};
     return {p->c_if + (size_t)b * p->mp.if_per_block - DY4_IF_TAIL, (long long)p->c_stride};
 }
 
@@ -529,7 +562,15 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     int rc = ensure_workspace(p, n_blocks);
     if (rc) return rc;
     if ((rc = ensure_call_rows(p, n_blocks))) return rc;
-    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS));
+    const bool overlap = p->pipelined && p->stereo && !hooks && p->s_main;        // this call is not joined to the caller's stream
+    // the geometric ramp serves a call that starts on an idle device; an overlapped call's first sub-chunks are prepared while
+    // the loops of the call before are still running, and uniform sub-chunks keep the predictions two whole launches ahead
+    const auto plan = plan_subchunks(n_blocks, p->ws_blocks, p->stereo && !(p->flags & DY4_FLAG_DEBUG_ROWS) && !(overlap && !p->pll_fresh));
+    if (overlap) {                                     // the other set of call rows: the previous call's are still being read
+        std::swap(p->c_if, p->rows_alt[0]); std::swap(p->c_pilot, p->rows_alt[1]); std::swap(p->c_sband, p->rows_alt[2]); std::swap(p->c_nco, p->rows_alt[3]);
+        p->call_parity ^= 1;
+    }
+    p->call_hist = p->if_tail;
     auto sub = [&](int b, int nb, long long seq) {
         SubChunk c;
         c.b = b; c.nb = nb;
@@ -579,9 +620,14 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     CU(cudaEventRecord(p->ev_in, st));
     CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));     // the PLL stream starts after whatever precedes this call on `st`
     cudaStream_t const caller = st;
-    if (p->s_main) {                                   // SM partition: the call's own kernels run on the SMs the loops do not use
+    if (p->s_main) {                                   // SM partition / pipelined calls: the FIR launches run on a stream of the pipeline's own
         CU(cudaStreamWaitEvent(p->s_main, p->ev_in, 0));
         st = p->s_main;
+        if (overlap) {
+            // this call's rows, and the IF history slot it writes for the next call (a ring of three), were last read by the
+            // call before the previous one
+            CU(cudaStreamWaitEvent(st, p->ev_call_done[p->call_parity], 0));
+        }
     }
     const bool fresh_call = p->pll_fresh;              // no sample processed since create / reset: the streams start in this call
     p->pll_fresh = false;
@@ -620,6 +666,16 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
     // queued on the same stream later wait for the loops).  Host path: a piece is queued when its sub-chunk comes up, so that
     // the back halves (and the downloads behind them) are not held up by uploads still to come.
     if (!hooks) while (next_piece < pieces.size()) if ((rc = queue_piece())) return rc;
+    if (overlap) {                                     // the IF rows are complete on this stream: the caller's copy, and the next call's history
+        if (d_if) CU(cudaMemcpy2DAsync(d_if, if_stride * sizeof(float), p->c_if, p->c_stride * sizeof(float),
+                                       (size_t)n_blocks * m.if_per_block * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
+        Dy4TailArgs ta{};
+        ta.if_in = p->c_if; ta.if_stride = (long long)p->c_stride; ta.n_if = n_blocks * m.if_per_block; ta.if_tail = p->if_tail_alt[0]; ta.n_streams = p->n_streams;
+        { Timer t(p, DY4_K_TAILS, st); CU(dy4_launch_tails(ta, st)); }
+        float* const hist = p->if_tail;                // p->call_hist keeps pointing at it for the rest of this call
+        p->if_tail = p->if_tail_alt[0]; p->if_tail_alt[0] = p->if_tail_alt[1]; p->if_tail_alt[1] = hist;
+        CU(cudaEventRecord(p->ev_main_done, st));
+    }
     const long long seq0 = p->seq;
     for (size_t i = 0; i < plan.size(); i++, p->seq++) {
         SubChunk c = sub(plan[i].first, plan[i].second, p->seq);
@@ -633,7 +689,10 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         // finished, so sub-chunk 0 is predicted from the exact state, sub-chunk 1 carries on from that prediction, and nothing
         // but the serial loops is queued on the PLL stream.  Should the signal have jumped between two calls, the loop notices
         // (its picks stop being certain) and finishes that launch with the direct loop's steps.
+        // PIPELINED calls: the loops of the previous call are still running when this call's first prediction is queued, so it
+        // too carries on from the previous prediction (which ended where this call starts).
         if (fresh_call) c.pred_carry = i < 2 ? 0 : (i == 2 ? 1 : 2);
+        else if (overlap) c.pred_carry = 2;
         else c.pred_carry = i == 0 ? 0 : (i == 1 ? 1 : 2);
         c.fresh = (i == 0 && fresh_call) ? 1536 : 0;                              // DY4_TAB_EARLY (dy4_plltab.h)
         const bool prep_on_pll = p->pll_table && i == 1 && fresh_call;
@@ -665,6 +724,11 @@ int process_device(dy4_pipeline* p, const uint8_t* d_iq, size_t row_stride, int 
         if ((int)pend.size() >= dy4_pipeline::NSETS && (rc = flush_back())) return rc;
     }
     while (!pend.empty()) if ((rc = flush_back())) return rc;
+    if (overlap) {                                     // no join: the call is done when its last back half (and RDS sub-chunk) is
+        if (p->flags & DY4_FLAG_RDS) CU(cudaStreamWaitEvent(sb, p->ev_rds, 0));
+        CU(cudaEventRecord(p->ev_call_done[p->call_parity], sb));
+        return DY4_OK;
+    }
     if (sb != st) {                                    // join: the call's last back half
         CU(cudaEventRecord(p->ev_fir_all, sb));
         CU(cudaStreamWaitEvent(st, p->ev_fir_all, 0));
@@ -689,6 +753,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
     dy4_pipeline* p = new (std::nothrow) dy4_pipeline();
     if (!p) return DY4_ERR_NOMEM;
     p->mode = mode; p->stereo = stereo ? 1 : 0; p->n_streams = n_streams; p->device = device; p->flags = flags; p->mp = mp;
+    p->pipelined = (flags & DY4_FLAG_PIPELINED) && stereo;
 
     // coefficient generation as project.cpp:260-273
     float rf[DY4_NTAPS], pilot[DY4_NTAPS], sb[DY4_NTAPS];
@@ -735,6 +800,7 @@ extern "C" int dy4_pipeline_create(int mode, int stereo, int n_streams, int devi
     }
     CU(cudaMalloc(&p->iq_tail, S * DY4_IQ_TAIL));
     CU(cudaMalloc(&p->if_tail, S * DY4_IF_TAIL * sizeof(float)));
+    if (p->pipelined) for (auto& t : p->if_tail_alt) CU(cudaMalloc(&t, S * DY4_IF_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->mix_tail, S * DY4_MIX_TAIL * sizeof(float)));
     CU(cudaMalloc(&p->pll_state, S * 8 * sizeof(float)));
     int rc = init_state(p, nullptr);
@@ -747,7 +813,7 @@ extern "C" int dy4_pipeline_reset(dy4_pipeline_t* p)
 {
     if (!p) return DY4_ERR_ARG;
     CU(cudaSetDevice(p->device));
-    CU(cudaDeviceSynchronize());
+    { const int rq = quiesce(p); if (rq) return rq; }
     return init_state(p, nullptr);
 }
 
@@ -757,7 +823,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
 {
     if (!p) return DY4_OK;
     cudaSetDevice(p->device);
-    cudaDeviceSynchronize();
+    quiesce(p);
     if (p->pll_table && std::getenv("DY4_PLL_STATS")) {                       // development counters of the serial PLL loop
         long long v[4];
         if (dy4_debug_pll_stats(v) == 0 && v[1] > 0)
@@ -774,7 +840,10 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
     cudaFree(p->c_if); cudaFree(p->c_pilot); cudaFree(p->c_sband); cudaFree(p->c_nco);
+    for (auto r : p->rows_alt) cudaFree(r);
+    for (auto t : p->if_tail_alt) cudaFree(t);
     for (auto e : p->ev_fir) cudaEventDestroy(e);
+    for (auto e : {p->ev_call_done[0], p->ev_call_done[1], p->ev_main_done}) if (e) cudaEventDestroy(e);
     cudaFree(p->ws_nco0); cudaFree(p->pred_state); cudaFree(p->pll_risk);
     if (p->s_pll) {
         cudaStreamDestroy(p->s_pll);
@@ -819,6 +888,16 @@ extern "C" int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size
     return DY4_OK;
 }
 
+extern "C" int dy4_pipeline_flush(dy4_pipeline_t* p, void* stream)
+{
+    if (!p) { dy4_set_error("dy4_pipeline_flush: bad arguments"); return DY4_ERR_ARG; }
+    if (!p->pipelined || !p->ev_main_done) return DY4_OK;       // calls are joined to their stream when they end
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (cudaEvent_t e : {p->ev_main_done, p->ev_call_done[0], p->ev_call_done[1], p->ev_rds}) if (e) CU(cudaStreamWaitEvent(st, e, 0));
+    return DY4_OK;
+}
+
 extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                                          int16_t* h_pcm, float* h_audio, int chunk_blocks)
 {
@@ -827,6 +906,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     const dy4_mode_params_t& m = p->mp;
     if (row_stride_bytes < (size_t)n_blocks * m.block_size) { dy4_set_error("dy4_pipeline_process_host: row stride too small"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
+    if (p->pipelined) { const int rq = quiesce(p); if (rq) return rq; }      // device-path calls still in flight
     const int ch = p->stereo ? 2 : 1;
     const size_t S = (size_t)p->n_streams;
     // A "window" of blocks is resident in device staging at a time (DY4_STAGE_BYTES of input, default 4 GiB, or
@@ -844,7 +924,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
         p->streams_ready = true;
     }
     if (p->stage_blocks < window || (h_audio && !p->stage_audio)) {
-        CU(cudaDeviceSynchronize());
+        { const int rq = quiesce(p); if (rq) return rq; }
         cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);
         p->d_stage = nullptr; p->d_pcm_stage = nullptr; p->d_audio_stage = nullptr;
         CU(cudaMalloc(&p->d_stage, S * window * m.block_size));
@@ -905,7 +985,7 @@ extern "C" int dy4_pipeline_debug_buffers(dy4_pipeline_t* p, const float** d_pil
 {
     if (!p || !p->stereo || !p->c_pilot) { dy4_set_error("dy4_pipeline_debug_buffers: no stereo sub-chunk processed yet"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
-    CU(cudaDeviceSynchronize());
+    { const int rq = quiesce(p); if (rq) return rq; }
     if (d_pilot) *d_pilot = p->c_pilot + p->last_off;
     if (d_nco) *d_nco = p->c_nco + p->last_off;
     if (stride) *stride = p->c_stride;
@@ -930,6 +1010,7 @@ extern "C" int dy4_pipeline_rds_read(dy4_pipeline_t* p, float* d_rrc_i, float* d
     if (p->rds_call_n <= 0) return DY4_OK;
     if (row_stride < (size_t)p->rds_call_n) { dy4_set_error("dy4_pipeline_rds_read: row stride smaller than the sample count"); return DY4_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->pipelined && p->ev_rds) CU(cudaStreamWaitEvent(st, p->ev_rds, 0));       // not joined at the end of the call
     if (d_rrc_i) CU(cudaMemcpy2DAsync(d_rrc_i, row_stride * sizeof(float), p->rds_out, 2 * p->rds_out_cap * sizeof(float),
                                       (size_t)p->rds_call_n * sizeof(float), p->n_streams, cudaMemcpyDeviceToDevice, st));
     if (d_rrc_q) CU(cudaMemcpy2DAsync(d_rrc_q, row_stride * sizeof(float), p->rds_out + p->rds_out_cap, 2 * p->rds_out_cap * sizeof(float),
@@ -987,7 +1068,7 @@ extern "C" int dy4_pipeline_pll_risk(dy4_pipeline_t* p, int32_t* h_counts, int r
 {
     if (!p || !h_counts) { dy4_set_error("dy4_pipeline_pll_risk: bad arguments"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
-    CU(cudaDeviceSynchronize());
+    { const int rq = quiesce(p); if (rq) return rq; }
     const size_t S = (size_t)p->n_streams;
     if (!p->pll_risk) { std::memset(h_counts, 0, S * sizeof(int32_t)); return DY4_OK; }     // mono, or the direct loop: nothing counted
     CU(cudaMemcpy(h_counts, p->pll_risk, S * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1051,7 +1132,7 @@ extern "C" int dy4_pipeline_get_state(dy4_pipeline_t* p, void* host_buf)
 {
     if (!p || !host_buf) return DY4_ERR_ARG;
     CU(cudaSetDevice(p->device));
-    CU(cudaDeviceSynchronize());
+    { const int rq = quiesce(p); if (rq) return rq; }
     const size_t S = (size_t)p->n_streams;
     char* o = (char*)host_buf;
     CU(cudaMemcpy(o, p->iq_tail, S * DY4_IQ_TAIL, cudaMemcpyDeviceToHost)); o += S * DY4_IQ_TAIL;
@@ -1079,7 +1160,7 @@ extern "C" int dy4_pipeline_set_state(dy4_pipeline_t* p, const void* host_buf)
     if (p) p->pll_fresh = false;                     // whatever the restored streams are, they are not at sample 0 by construction
     if (!p || !host_buf) return DY4_ERR_ARG;
     CU(cudaSetDevice(p->device));
-    CU(cudaDeviceSynchronize());
+    { const int rq = quiesce(p); if (rq) return rq; }
     const size_t S = (size_t)p->n_streams;
     const char* o = (const char*)host_buf;
     CU(cudaMemcpy(p->iq_tail, o, S * DY4_IQ_TAIL, cudaMemcpyHostToDevice)); o += S * DY4_IQ_TAIL;

@@ -14,6 +14,7 @@ from .modes import mode_params
 FLAG_EXACT_AUDIO = 1
 FLAG_DEBUG_ROWS = 2
 FLAG_RDS = 4
+FLAG_PIPELINED = 8
 KERNELS = ("frontend", "twin_bpf", "pll", "audio", "tails", "rds_bpf", "rds_pll", "rds_baseband", "pll_aux")
 
 
@@ -23,13 +24,14 @@ def launch_count():
 
 
 class Pipeline:
-    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False, debug_rows=False, rds=False):
+    def __init__(self, mode, stereo, n_streams, device=0, exact_audio=False, debug_rows=False, rds=False, pipelined=False):
         self.mode, self.stereo, self.n_streams, self.device = int(mode), bool(stereo), int(n_streams), int(device)
         self.params = mode_params(mode)
         self.channels = 2 if stereo else 1
         self._h = C.c_void_p()
         check(lib.dy4_pipeline_create(self.mode, int(self.stereo), self.n_streams, self.device,
-                                      (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0) | (FLAG_RDS if rds else 0),
+                                      (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0) | (FLAG_RDS if rds else 0)
+                                      | (FLAG_PIPELINED if pipelined else 0),
                                       C.byref(self._h)), "dy4_pipeline_create")
 
     def close(self):
@@ -76,6 +78,15 @@ class Pipeline:
                                        ptr("pcm"), ptr("audio"), ptr("if"), C.c_void_p(stream.cuda_stream)),
               "dy4_pipeline_process")
         return out
+
+    def flush(self, stream=None):
+        """pipelined=True (DY4_FLAG_PIPELINED): process() calls overlap on the device and are not joined to their stream; flush()
+        makes `stream` (default: the current stream) wait for all of them.  Call it before reading any output, before
+        overwriting an input, and keep the output tensors alive until then.  A no-op otherwise."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        check(lib.dy4_pipeline_flush(self._h, C.c_void_p(stream.cuda_stream)), "dy4_pipeline_flush")
 
     # ---- host buffers (H2D / compute / D2H overlapped inside the library) ------------------------
     def process_host(self, iq, n_blocks=None, want=("pcm",), out=None, chunk_blocks=0):

@@ -198,7 +198,8 @@ def run_gpu_arm(args):
     d_iq = dy4_b200.synth.make_batch_torch(MODE, min(S, 512), nb * m.block_size // 2, base_seed=65 + lo, device=dev, rds=RDS, periodic=periodic)
     if S > 512:                                      # very large batches: tile 512 distinct streams (generation time, not a kernel matter)
         d_iq = d_iq.repeat((S + 511) // 512, 1)[:S].contiguous()
-    pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, rds=RDS)
+    overlap = bool(STEREO) and not args.no_overlap  # consecutive steps overlap on the device (DY4_FLAG_PIPELINED); one flush before the closing event
+    pipe = dy4_b200.Pipeline(MODE, STEREO, S, device=local_rank, rds=RDS, pipelined=overlap)
     nch = 2 if STEREO else 1
     out = {"pcm": torch.empty((S, n_audio * nch), dtype=torch.int16, device=dev)}
     max_steps_between_resets = max(1, int(55.0 / (nb * (m.block_size / 2) / m.rf_Fs)))   # float PLL sample counter saturates at 2^24 (~69.9 s)
@@ -212,6 +213,7 @@ def run_gpu_arm(args):
 
     for i in range(args.warmup):                     # the streams start here (step 0 resets) ...
         step(i)
+    pipe.flush()
     torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ------------------------------------------------------------
@@ -226,6 +228,7 @@ def run_gpu_arm(args):
     e0.record()
     for i in range(args.steps):                      # ... and simply continue through the timed region
         step(args.warmup + i)
+    pipe.flush()                                     # pipelined calls: the stream waits for every step's last kernel
     e1.record()
     torch.cuda.synchronize(dev)
     shard.barrier()
@@ -422,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="dy4", choices=["dy4", "reference"])
     ap.add_argument("--chunk-blocks", type=int, default=0, help="blocks per H2D chunk in the e2e leg (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="join every step to the stream before the next is queued (default: steps overlap on the device)")
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: BASELINE configs[1], 256)")
     ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STREAM, help="blocks per stream per step (default 47 = 1.003 s)")
     ap.add_argument("--mode", type=int, default=MODE, help="receiver mode 0..3 (default 0)")

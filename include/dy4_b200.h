@@ -149,6 +149,13 @@ typedef struct dy4_pipeline dy4_pipeline_t;
                                      19/120 resampler (1919 taps) and 101-tap RRC -> 38 kS/s.  Read the result of the
                                      last process call with dy4_pipeline_rds_read. */
 
+#define DY4_FLAG_PIPELINED 8u     /* stereo, dy4_pipeline_process only: consecutive calls OVERLAP on the device.  A call returns once
+                                     it is queued and is NOT joined to `stream` when it ends: its FIR kernels run while the PLL's
+                                     serial loops of the call before are still going (on SMs of their own where CUDA green contexts
+                                     are available).  The caller must call dy4_pipeline_flush (or synchronise the device) before it
+                                     reads the outputs or overwrites the input of ANY earlier call; results are the same bits.
+                                     Every other entry point (state, reset, RDS read / drain, host path) drains the queue itself. */
+
 /* Create a receiver for `n_streams` independent streams in `mode` (0..3), mono (stereo=0)
  * or stereo (stereo=1), on CUDA device `device`.  All carried state starts as in
  * project.cpp:240-255 (zero history, PLL at feedbackI=1, nco_state=1). */
@@ -171,6 +178,9 @@ int dy4_pipeline_reset(dy4_pipeline_t* p);
  */
 int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stride_bytes, int n_blocks,
                          int16_t* d_pcm, float* d_audio, float* d_if, void* stream);
+/* DY4_FLAG_PIPELINED: make `stream` wait for every call queued so far (outputs complete, inputs no longer read).
+ * Without the flag calls are joined to their stream when they end and this is a no-op. */
+int dy4_pipeline_flush(dy4_pipeline_t* p, void* stream);
 
 /*
  * Same, HOST pointers (pinned memory recommended): the input is uploaded in

@@ -159,6 +159,41 @@ def test_call_windows_do_not_change_results(dy4, monkeypatch):
             assert np.array_equal(dr1[s][k], dr2[s][k]), (s, k)
 
 
+@pytest.mark.parametrize("rds", [False, True])
+def test_pipelined_calls_do_not_change_results(dy4, rds):
+    """DY4_FLAG_PIPELINED: consecutive calls overlap on the device (two sets of call rows, IF history moved on as soon as a call's
+    FIR work is queued, the prediction carried across calls, loops on SMs of their own).  Six calls of uneven length queued
+    back to back, outputs read after one flush: the bits of the call-by-call pipeline; state and RDS output as well."""
+    import torch
+    m = dy4.mode_params(0)
+    S = 24
+    cuts = [0, 9, 10, 22, 30, 31, 44]
+    d = dy4.synth.make_batch_torch(0, S, cuts[-1] * m.block_size // 2, base_seed=411, device="cuda", rds=rds)
+
+    def run(pipelined):
+        p = dy4.Pipeline(0, 1, S, rds=rds, pipelined=pipelined)
+        outs = [p.process(d[:, a * m.block_size:b * m.block_size], want=("pcm", "audio", "if")) for a, b in zip(cuts, cuts[1:])]
+        p.flush()
+        torch.cuda.synchronize()
+        part = p.sm_partition()
+        state = p.get_state().copy()
+        dr = p.rds_drain() if rds else None
+        p.close()
+        return outs, state, dr, part
+
+    one, st1, dr1, part1 = run(False)
+    two, st2, dr2, part2 = run(True)
+    assert part1 == (0, 0) and part2[0] >= 8, (part1, part2)
+    for x, y in zip(one, two):
+        for k in x:
+            assert torch.equal(x[k], y[k]), k
+    assert np.array_equal(st1, st2)
+    if rds:
+        for s in range(S):
+            for k in ("symbols", "bits", "events", "groups"):
+                assert np.array_equal(dr1[s][k], dr2[s][k]), (s, k)
+
+
 def test_sm_partition_does_not_change_results(dy4, monkeypatch):
     """DY4_LOOP_SMS (opt-in, dy4_smpart.cu): the serial loops on a green context of 32 SMs, every other kernel on the rest; the
     caller's stream forks into the partition's streams and joins at the end of the call.  Same bits out, call after call."""
