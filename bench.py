@@ -160,7 +160,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def workload_config():
+def workload_config(overlap=False):
     return {
         "workload": "%smode %d %s FM (8-bit IQ -> IF -> %s int16 PCM), %d independent synthetic streams per GPU x %d blocks"
                     % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU, STEREO) == (0, 256, 1) else "", MODE, "stereo" if STEREO else "mono",
@@ -171,6 +171,10 @@ def workload_config():
         "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32; the PLL's f64 libm results reproduced exactly); "
                       "audio resamplers fused f32 (PCM within 1 LSB)",
         "parallelism": "streams partitioned across GPUs, one process per GPU, no collective on the data path",
+        "calls": "one dy4_pipeline_process call per step; " + (
+            "steps are queued back to back and OVERLAP on the device (DY4_FLAG_PIPELINED: step k+1's FIR kernels run beside step k's PLL loops), "
+            "one dy4_pipeline_flush before the closing event - every step's PCM is complete inside the timed region" if overlap else
+            "every step is joined to the stream before the next starts"),
     }
 
 
@@ -236,8 +240,20 @@ def run_gpu_arm(args):
     launches = dy4_b200.launch_count() - launches0
     prof = pipe.profile_get(reset=True)
     pipe.profile(False)
+    loop_sms, rest_sms = pipe.sm_partition()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # one step alone on an idle device, queue to flush: the LATENCY of a call (the timed region above measures throughput)
+    lat = []
+    for i in range(2):
+        torch.cuda.synchronize(dev)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        step(args.warmup + args.steps + i)
+        pipe.flush()
+        l1.record()
+        torch.cuda.synchronize(dev)
+        lat.append(l0.elapsed_time(l1))
     ms_max = shard.max_over_ranks(ms, dev)
     total_launches = int(shard.sum_over_ranks(launches, dev))
     value = world * pairs_per_step * args.steps / (ms_max * 1e-3) / 1e6
@@ -370,6 +386,10 @@ def run_gpu_arm(args):
         "frac_of_exact_ceiling": round(fe["fp32_TFLOPs"] / EXACT_MAC_CEILING_TFLOPS, 4) if STEREO else None,
         "hbm": {"achieved": fe["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": round(fe["GBps"] / hbm_peak, 4), "peak_source": hbm_src},
         "share_of_step": fe["share"], "avg_launch_ms": fe["avg_ms"],
+        "sms": rest_sms or 148,
+        "sms_note": ("in the timed region this kernel runs on %d of the 148 SMs (the PLL's serial loops own the other %d, DESIGN.md 4.3.3) and shares them with "
+                     "the next sub-chunks' prediction / table kernels; `achieved` is against the whole GPU's peak all the same - whole_job_launches has "
+                     "the kernel alone on all SMs" % (rest_sms, loop_sms)) if rest_sms else None,
         "algorithmic_bytes": int(alg["frontend"]["bytes"] * pairs_per_step),
         "traffic": int(NCU_FRONTEND_DRAM_BYTES_PER_PAIR * pairs_per_step),
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per IQ pair from profiles/r2_ncu_k_frontend_stream.md (ncu --set full, whole-job launch), scaled to this launch",
@@ -386,7 +406,8 @@ def run_gpu_arm(args):
                     "loop": "table-driven (k_pll_predict -> k_pll_table_ops: exact two-candidate rows -> k_pll_sel: serial picks, certified per lane; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
                     "note": ("serial recurrence per stream, one warp per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
                              "pll_aux), the serial loop is float adds, one compare and selects - bound by the issue rate of a lone warp on that dependent "
-                             "chain (14.9 ns per sample alone, ~25 beside the FIR kernels it shares SM sub-partitions with), not by FLOPs or bytes") if PLL_TABLE else
+                             "chain: 14.5 ns per sample with a sub-partition to itself, 18.5 two warps to a sub-partition (256 streams on the 32 SMs "
+                             "set aside for the loops), 21-25 when FIR kernels share its SMs - not by FLOPs or bytes") if PLL_TABLE else
                             "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
 
     # ---- CPU baseline: the reference's own code on the host cores, bounded sample (N=1 only) ----------------
@@ -400,8 +421,8 @@ def run_gpu_arm(args):
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "ms_per_step": round(ms_max / args.steps, 3), "step_latency_ms": round(min(lat), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(overlap),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": S * nb * m.block_size,
                 "d2h_bytes_per_step": S * n_audio * nch * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
                 "timing": "host clock around the synchronous process_host() calls and the closing barrier, max over ranks",
@@ -409,6 +430,7 @@ def run_gpu_arm(args):
         "oracle_check": oracle_check,
         "signal": "periodic over one step: the streams continue from step to step without a jump" if periodic else "the same buffer again every step: a phase jump per step",
         "gpu_launches": total_launches,
+        "sm_partition": {"loop_sms": loop_sms, "other_sms": rest_sms} if loop_sms else None,
         "roofline": roofline, "kernels": kernels, "pll": pll_info, "cpu_baseline": cpu,
         "clocks": sampler.result(),
     }
@@ -420,7 +442,7 @@ def main():
     global STREAMS_PER_GPU, BLOCKS_PER_STREAM, MODE, RDS, STEREO
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dy4", choices=["dy4", "reference"])
     ap.add_argument("--chunk-blocks", type=int, default=0, help="blocks per H2D chunk in the e2e leg (0 = library default)")
