@@ -366,6 +366,9 @@ __device__ __noinline__ float spec_replay_integ(unsigned base, int j, float gi, 
 // Rows arrive chain-ready (k_pll_table_ops) by one bulk asynchronous copy per 128 samples straight into the ring the
 // chain reads: the warp neither waits on global memory nor spends issue slots on it.
 // ====================================================================================================================
+#ifndef DY4_SEL_PACKED
+#define DY4_SEL_PACKED 1
+#endif
 template <int B>
 __global__ void __launch_bounds__(32)
 k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __restrict__ tab, long long tab_stride,
@@ -458,8 +461,17 @@ k_pll_sel(const float* __restrict__ in, long long in_stride, const float4* __res
             float T;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(T) : "r"(base + 32u * i + 16u));
             cph |= __float_as_uint(p0) & mask[i];
+#if DY4_SEL_PACKED
+            // both candidates at once: packed float adds (add.rn.f32x2 rounds each half like add.rn.f32)
+            float i_lo, i_hi, t_lo, t_hi;
+            asm("{\n.reg .b64 ii, axy, azw, ic, tc;\nmov.b64 ii, {%4, %4};\nmov.b64 axy, {%5, %6};\nmov.b64 azw, {%7, %8};\n"
+                "add.rn.f32x2 ic, ii, axy;\nadd.rn.f32x2 tc, azw, ic;\nmov.b64 {%0, %1}, ic;\nmov.b64 {%2, %3}, tc;\n}\n"
+                : "=f"(i_lo), "=f"(i_hi), "=f"(t_lo), "=f"(t_hi) : "f"(i0), "f"(A.x), "f"(A.y), "f"(A.z), "f"(A.w));
+            const float p_lo = __fadd_rn(p0, t_lo), p_hi = __fadd_rn(p0, t_hi);
+#else
             const float i_lo = __fadd_rn(i0, A.x), i_hi = __fadd_rn(i0, A.y);                          // filter.cpp:207, both candidates
             const float p_lo = __fadd_rn(p0, __fadd_rn(A.z, i_lo)), p_hi = __fadd_rn(p0, __fadd_rn(A.w, i_hi));     // :210
+#endif
             const bool up = p0 > T;                                                                    // trigArg rounds to the upper candidate
             i0 = up ? i_hi : i_lo;
             p0 = up ? p_hi : p_lo;

@@ -131,6 +131,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ready, self.armed = threading.Event(), False
 
     def run(self):
         try:
@@ -145,15 +146,18 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
             }
+            self.ready.set()                         # NVML is up: the timed region may start
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.01)
+                if self.armed:                       # only samples taken while the timed region runs count
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.002)
         except Exception as e:      # NVML missing: report that, do not fail the bench
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+            self.ready.set()
 
     def result(self):
         s = sorted(self.samples)
@@ -227,14 +231,17 @@ def run_gpu_arm(args):
     pipe.profile_get(reset=True)
     launches0 = dy4_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.ready.wait(timeout=10)
     shard.barrier()
     torch.cuda.synchronize(dev)
+    sampler.armed = True
     e0.record()
     for i in range(args.steps):                      # ... and simply continue through the timed region
         step(args.warmup + i)
     pipe.flush()                                     # pipelined calls: the stream waits for every step's last kernel
     e1.record()
     torch.cuda.synchronize(dev)
+    sampler.armed = False
     shard.barrier()
     ms = e0.elapsed_time(e1)
     launches = dy4_b200.launch_count() - launches0
