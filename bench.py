@@ -412,8 +412,8 @@ def run_gpu_arm(args):
                     "stream_samples_per_s": round(S * n_if / (pll_ms_per_step * 1e-3), 0),
                     "loop": "table-driven (k_pll_predict -> k_pll_table_ops: exact two-candidate rows -> k_pll_sel: serial picks, certified per lane; DESIGN.md 4.3)" if PLL_TABLE else "direct (dy4_pllmath.h in the serial loop)",
                     "note": ("serial recurrence per stream, one warp per stream: the transcendental work runs beforehand in time-parallel kernels (counted in "
-                             "pll_aux), the serial loop is float adds, one compare and selects - bound by the issue rate of a lone warp on that dependent "
-                             "chain: 14.5 ns per sample with a sub-partition to itself, 18.5 two warps to a sub-partition (256 streams on the 32 SMs "
+                             "pll_aux), the serial loop is (packed) float adds, one compare and selects - bound by the issue rate of a lone warp on that dependent "
+                             "chain: 14.5 ns per sample with a sub-partition to itself, 17.8 two warps to a sub-partition (256 streams on the 32 SMs "
                              "set aside for the loops), 21-25 when FIR kernels share its SMs - not by FLOPs or bytes") if PLL_TABLE else
                             "serial recurrence per stream, one thread per stream: bound by the latency of its dependent FP64 chain, not by FLOPs or bytes"}
 
