@@ -194,6 +194,44 @@ def test_pipelined_calls_do_not_change_results(dy4, rds):
                 assert np.array_equal(dr1[s][k], dr2[s][k]), (s, k)
 
 
+@pytest.mark.parametrize("case", ["jumps", "no_partition", "direct_loop", "windows"])
+def test_pipelined_calls_edge_cases(dy4, monkeypatch, case):
+    """Overlapped calls where the carried prediction is of no use or the schedule differs: unrelated signals from call to call (the
+    loop falls back to direct steps and the turn report re-centres the prediction), more than 256 streams (no SM partition), the
+    direct PLL loop (no table), and calls cut into windows.  Always the bits of joined calls."""
+    import torch
+    m = dy4.mode_params(0)
+    S = 300 if case == "no_partition" else 20
+    nb = 9
+    if case == "direct_loop":
+        monkeypatch.setenv("DY4_PLL_TABLE_MAX", "0")
+    if case == "windows":
+        monkeypatch.setenv("DY4_WS_BYTES", str(S * m.if_per_block * 32 * 4 // 4))     # rows for 4 blocks (two sets): windows of 4, 4, 1
+    chunks = [dy4.synth.make_batch_torch(0, S, nb * m.block_size // 2, base_seed=500 + (97 * k if case == "jumps" else 0), device="cuda")
+              for k in range(4)]
+    if case != "jumps":                                            # one continuous signal
+        d = dy4.synth.make_batch_torch(0, S, 4 * nb * m.block_size // 2, base_seed=500, device="cuda")
+        chunks = [d[:, k * nb * m.block_size:(k + 1) * nb * m.block_size] for k in range(4)]
+
+    def run(pipelined):
+        p = dy4.Pipeline(0, 1, S, pipelined=pipelined)
+        outs = [p.process(c, want=("pcm", "audio")) for c in chunks]
+        p.flush()
+        torch.cuda.synchronize()
+        part = p.sm_partition()
+        state = p.get_state().copy()
+        p.close()
+        return outs, state, part
+
+    one, st1, _ = run(False)
+    two, st2, part = run(True)
+    assert (part[0] > 0) == (case in ("jumps", "windows")), (case, part)
+    for x, y in zip(one, two):
+        for k in x:
+            assert torch.equal(x[k], y[k]), (case, k)
+    assert np.array_equal(st1, st2)
+
+
 def test_sm_partition_does_not_change_results(dy4, monkeypatch):
     """DY4_LOOP_SMS (opt-in, dy4_smpart.cu): the serial loops on a green context of 32 SMs, every other kernel on the rest; the
     caller's stream forks into the partition's streams and joins at the end of the call.  Same bits out, call after call."""

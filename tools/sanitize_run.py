@@ -19,6 +19,15 @@ for mode in (0, 1, 2, 3):
             p.process_host(iq, want=("pcm",))
             st = p.get_state(); p.set_state(st)
             p.close()
+# overlapped calls (DY4_FLAG_PIPELINED): two sets of call rows, IF history ring, loops on SMs of their own where green contexts exist
+m = dy4_b200.mode_params(0)
+iq = torch.from_numpy(dy4_b200.synth.make_batch(0, 5, 40 * m.block_size // 2, base_seed=9)).cuda()
+p = dy4_b200.Pipeline(0, 1, 5, pipelined=True)
+outs = [p.process(iq[:, a * m.block_size:b * m.block_size], want=("pcm", "audio", "if")) for a, b in ((0, 9), (9, 10), (10, 26), (26, 40))]
+p.flush(); torch.cuda.synchronize()
+st = p.get_state(); p.set_state(st); p.reset()
+outs = [p.process(iq[:, :12 * m.block_size], want=("pcm",)) for _ in range(3)]
+p.close()
 m = dy4_b200.mode_params(0)
 iq = dy4_b200.synth.make_batch(0, 3, 19 * m.block_size // 2, base_seed=77, rds=True)
 p = dy4_b200.Pipeline(0, 1, 3, rds=True)
