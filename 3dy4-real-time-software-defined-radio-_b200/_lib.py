@@ -78,6 +78,7 @@ def _load():
         "dy4_pipeline_pll_risk": (i, [vp, vp, i]),
         "dy4_pipeline_sm_partition": (i, [vp, vp, vp]),
         "dy4_pipeline_flush": (i, [vp, vp]),
+        "dy4_pipeline_sync": (i, [vp]),
         "dy4_pipeline_profile": (i, [vp, i]),
         "dy4_pipeline_profile_get": (i, [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]),
         "dy4_pipeline_state_size": (sz, [vp]),

@@ -95,6 +95,10 @@ struct dy4_pipeline {
     int stage_blocks = 0; bool stage_audio = false;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;          // one pair per sub-chunk of a window
+    // host path of a DY4_FLAG_PIPELINED pipeline: whole calls alternate between two staging sets, so that the upload of call k+1 runs
+    // beside the kernels of call k (process_host_overlapped)
+    struct HostSet { uint8_t* d_iq = nullptr; int16_t* d_pcm = nullptr; float* d_audio = nullptr; cudaEvent_t done = nullptr; bool used = false; };
+    HostSet hset[2]; int hset_blocks = 0; bool hset_audio = false; int host_parity = 0; cudaEvent_t ev_h_up = nullptr;
     bool streams_ready = false;
     // profiling
     bool prof = false;
@@ -185,7 +189,7 @@ int init_state(dy4_pipeline* p, cudaStream_t st)
 // everything this pipeline has queued, on every stream of its own, is done
 int quiesce(dy4_pipeline* p)
 {
-    for (cudaStream_t s : {p->s_main, p->s_aux, p->s_pll, p->s_back, p->s_rds}) if (s) CU(cudaStreamSynchronize(s));
+    for (cudaStream_t s : {p->s_h2d, p->s_compute, p->s_main, p->s_aux, p->s_pll, p->s_back, p->s_rds, p->s_d2h}) if (s) CU(cudaStreamSynchronize(s));
     CU(cudaDeviceSynchronize());
     return DY4_OK;
 }
@@ -855,6 +859,8 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
         cudaEventDestroy(p->ev_in);
     }
     cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);
+    for (auto& h : p->hset) { cudaFree(h.d_iq); cudaFree(h.d_pcm); cudaFree(h.d_audio); if (h.done) cudaEventDestroy(h.done); }
+    if (p->ev_h_up) cudaEventDestroy(p->ev_h_up);
     for (auto e : p->ev_up) cudaEventDestroy(e);
     for (auto e : p->ev_done) cudaEventDestroy(e);
     if (p->streams_ready) { cudaStreamDestroy(p->s_compute); cudaStreamDestroy(p->s_h2d); cudaStreamDestroy(p->s_d2h); }
@@ -898,6 +904,84 @@ extern "C" int dy4_pipeline_flush(dy4_pipeline_t* p, void* stream)
     return DY4_OK;
 }
 
+namespace {
+int ensure_host_streams(dy4_pipeline* p)
+{
+    if (p->streams_ready) return DY4_OK;
+    CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    p->streams_ready = true;
+    return DY4_OK;
+}
+
+// Host path of a DY4_FLAG_PIPELINED pipeline.  A call (or a window of it) is uploaded WHOLE into one of two staging sets — when
+// the caller's rows are contiguous (row stride = row bytes) as ONE 1-D copy, 55 GB/s on this pool where row-pitched copies reach
+// 50 — then queued as an overlapped device call (process_device: not joined), and its PCM comes back on the download stream
+// once it is done.  Nothing waits for anything but data: the upload of call k+1 runs beside the kernels of call k, so a step
+// costs max(upload, kernels) instead of their partly overlapped sum.  The call returns when everything is QUEUED; the host
+// arrays are valid after dy4_pipeline_sync (or any other entry point, which all drain the queue).
+int process_host_overlapped(dy4_pipeline* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks, int16_t* h_pcm, float* h_audio, int chunk_blocks)
+{
+    const dy4_mode_params_t& m = p->mp;
+    const int ch = 2;
+    const size_t S = (size_t)p->n_streams;
+    size_t budget = 4ull << 30;
+    if (const char* e = std::getenv("DY4_STAGE_BYTES")) budget = std::strtoull(e, nullptr, 10);
+    int window = chunk_blocks > 0 ? chunk_blocks : (int)std::max<size_t>(1, budget / (S * m.block_size));
+    window = std::min(std::min(window, n_blocks), max_call_blocks(p));
+    int rc = ensure_host_streams(p);
+    if (rc) return rc;
+    if (p->hset_blocks < window || (h_audio && !p->hset_audio)) {
+        if ((rc = quiesce(p))) return rc;
+        for (auto& h : p->hset) {
+            cudaFree(h.d_iq); cudaFree(h.d_pcm); cudaFree(h.d_audio);
+            h.d_iq = nullptr; h.d_pcm = nullptr; h.d_audio = nullptr; h.used = false;
+            CU(cudaMalloc(&h.d_iq, S * window * m.block_size));
+            CU(cudaMalloc(&h.d_pcm, S * window * m.audio_per_block * ch * sizeof(int16_t)));
+            if (h_audio) CU(cudaMalloc(&h.d_audio, S * window * m.audio_per_block * ch * sizeof(float)));
+            if (!h.done) CU(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+        }
+        if (!p->ev_h_up) CU(cudaEventCreateWithFlags(&p->ev_h_up, cudaEventDisableTiming));
+        p->hset_blocks = window; p->hset_audio = h_audio != nullptr;
+    }
+    const size_t total_audio = (size_t)n_blocks * m.audio_per_block * ch;                // host output row length
+    if ((rc = rds_begin_call(p, n_blocks))) return rc;
+    for (int w0 = 0; w0 < n_blocks; w0 += window) {
+        const int wn = std::min(window, n_blocks - w0);
+        auto& h = p->hset[p->host_parity ^= 1];
+        if (h.used) CU(cudaEventSynchronize(h.done));                                    // the call that last used this set has delivered its PCM
+        const size_t in_bytes = (size_t)wn * m.block_size, na = (size_t)wn * m.audio_per_block * ch;
+        const uint8_t* src = h_iq + (size_t)w0 * m.block_size;
+        if (row_stride_bytes == in_bytes) CU(cudaMemcpyAsync(h.d_iq, src, S * in_bytes, cudaMemcpyHostToDevice, p->s_h2d));
+        else CU(cudaMemcpy2DAsync(h.d_iq, in_bytes, src, row_stride_bytes, in_bytes, S, cudaMemcpyHostToDevice, p->s_h2d));
+        CU(cudaEventRecord(p->ev_h_up, p->s_h2d));
+        CU(cudaStreamWaitEvent(p->s_compute, p->ev_h_up, 0));
+        if ((rc = process_device(p, h.d_iq, in_bytes, wn, h_pcm ? h.d_pcm : nullptr, h_audio ? h.d_audio : nullptr, nullptr, p->s_compute, na, na, 0))) return rc;
+        if ((rc = dy4_pipeline_flush(p, p->s_d2h))) return rc;                           // the download stream waits for this call (and those before it)
+        const size_t ao = (size_t)w0 * m.audio_per_block * ch;
+        if (h_pcm) {
+            if (total_audio == na) CU(cudaMemcpyAsync(h_pcm, h.d_pcm, S * na * sizeof(int16_t), cudaMemcpyDeviceToHost, p->s_d2h));
+            else CU(cudaMemcpy2DAsync(h_pcm + ao, total_audio * sizeof(int16_t), h.d_pcm, na * sizeof(int16_t), na * sizeof(int16_t), S, cudaMemcpyDeviceToHost, p->s_d2h));
+        }
+        if (h_audio) {
+            if (total_audio == na) CU(cudaMemcpyAsync(h_audio, h.d_audio, S * na * sizeof(float), cudaMemcpyDeviceToHost, p->s_d2h));
+            else CU(cudaMemcpy2DAsync(h_audio + ao, total_audio * sizeof(float), h.d_audio, na * sizeof(float), na * sizeof(float), S, cudaMemcpyDeviceToHost, p->s_d2h));
+        }
+        CU(cudaEventRecord(h.done, p->s_d2h));
+        h.used = true;
+    }
+    return DY4_OK;
+}
+}  // namespace
+
+extern "C" int dy4_pipeline_sync(dy4_pipeline_t* p)
+{
+    if (!p) { dy4_set_error("dy4_pipeline_sync: bad arguments"); return DY4_ERR_ARG; }
+    CU(cudaSetDevice(p->device));
+    return quiesce(p);
+}
+
 extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                                          int16_t* h_pcm, float* h_audio, int chunk_blocks)
 {
@@ -906,7 +990,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     const dy4_mode_params_t& m = p->mp;
     if (row_stride_bytes < (size_t)n_blocks * m.block_size) { dy4_set_error("dy4_pipeline_process_host: row stride too small"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
-    if (p->pipelined) { const int rq = quiesce(p); if (rq) return rq; }      // device-path calls still in flight
+    if (p->pipelined) return process_host_overlapped(p, h_iq, row_stride_bytes, n_blocks, h_pcm, h_audio, chunk_blocks);
     const int ch = p->stereo ? 2 : 1;
     const size_t S = (size_t)p->n_streams;
     // A "window" of blocks is resident in device staging at a time (DY4_STAGE_BYTES of input, default 4 GiB, or
@@ -917,12 +1001,7 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     if (const char* e = std::getenv("DY4_STAGE_BYTES")) budget = std::strtoull(e, nullptr, 10);
     int window = chunk_blocks > 0 ? chunk_blocks : (int)std::max<size_t>(1, budget / (S * m.block_size));
     window = std::min(std::min(window, n_blocks), max_call_blocks(p));
-    if (!p->streams_ready) {
-        CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
-        p->streams_ready = true;
-    }
+    { const int rs = ensure_host_streams(p); if (rs) return rs; }
     if (p->stage_blocks < window || (h_audio && !p->stage_audio)) {
         { const int rq = quiesce(p); if (rq) return rq; }
         cudaFree(p->d_stage); cudaFree(p->d_pcm_stage); cudaFree(p->d_audio_stage);

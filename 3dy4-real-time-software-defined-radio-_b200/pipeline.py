@@ -28,6 +28,7 @@ class Pipeline:
         self.mode, self.stereo, self.n_streams, self.device = int(mode), bool(stereo), int(n_streams), int(device)
         self.params = mode_params(mode)
         self.channels = 2 if stereo else 1
+        self.pipelined, self._in_flight = bool(pipelined) and bool(stereo), []
         self._h = C.c_void_p()
         check(lib.dy4_pipeline_create(self.mode, int(self.stereo), self.n_streams, self.device,
                                       (FLAG_EXACT_AUDIO if exact_audio else 0) | (FLAG_DEBUG_ROWS if debug_rows else 0) | (FLAG_RDS if rds else 0)
@@ -36,8 +37,9 @@ class Pipeline:
 
     def close(self):
         if self._h:
-            lib.dy4_pipeline_destroy(self._h)
+            lib.dy4_pipeline_destroy(self._h)        # drains everything queued first
             self._h = C.c_void_p()
+            self._in_flight.clear()
 
     def __del__(self):
         try:
@@ -88,10 +90,18 @@ class Pipeline:
             stream = torch.cuda.current_stream(self.device)
         check(lib.dy4_pipeline_flush(self._h, C.c_void_p(stream.cuda_stream)), "dy4_pipeline_flush")
 
+    def sync(self):
+        """Block until everything queued on this pipeline is done (dy4_pipeline_sync).  pipelined=True: process_host() returns when the
+        call is queued; read its outputs (and reuse its input) after sync()."""
+        check(lib.dy4_pipeline_sync(self._h), "dy4_pipeline_sync")
+        self._in_flight.clear()
+
     # ---- host buffers (H2D / compute / D2H overlapped inside the library) ------------------------
     def process_host(self, iq, n_blocks=None, want=("pcm",), out=None, chunk_blocks=0):
         """iq: uint8 host array/tensor [n_streams, >= n_blocks*block_size] (pinned torch tensor recommended).
-        Synchronous.  Returns numpy arrays (or fills the arrays/tensors passed in `out`)."""
+        Synchronous — unless the pipeline was made with pipelined=True: then the call returns when it is queued (its upload runs
+        beside the kernels of the call before) and outputs / input are the caller's again after sync().
+        Returns numpy arrays (or fills the arrays/tensors passed in `out`)."""
         p = self.params
         a = _host_view(iq)
         assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[0] == self.n_streams and a.strides[1] == 1
@@ -109,6 +119,8 @@ class Pipeline:
         row_stride = a.strides[0] if self.n_streams > 1 else n_blocks * p.block_size
         check(lib.dy4_pipeline_process_host(self._h, C.c_void_p(a.ctypes.data), row_stride, int(n_blocks),
                                             hp("pcm"), hp("audio"), int(chunk_blocks)), "dy4_pipeline_process_host")
+        if self.pipelined:
+            self._in_flight.append((a, out))         # the copies are still running: keep the buffers alive until sync()
         return out
 
     def rds_read(self, stream=None):

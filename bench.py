@@ -272,14 +272,16 @@ def run_gpu_arm(args):
     # in its slice, so after the barrier rank 0 holds the whole batch's PCM: that IS the path's host-side gather.
     shared = shard.SharedRows("dy4_bench_pcm_%s" % os.environ.get("MASTER_PORT", str(os.getpid())), S * world, n_audio * nch, np.int16, rank, world)
     h_pcm = torch.from_numpy(shared.mine)
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 8))
     pipe.reset()
     pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)   # warm-up (allocates staging)
+    pipe.sync()
     torch.cuda.synchronize(dev)
     shard.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):                       # the streams continue from step to step, as in the device-resident leg
         pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)
+    pipe.sync()                                      # overlapped calls: every upload, kernel and download of the steps above is done
     torch.cuda.synchronize(dev)
     shard.barrier()                                  # every rank's slice has landed: rank 0 now holds the gathered PCM
     e2e_ms = shard.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
@@ -290,6 +292,7 @@ def run_gpu_arm(args):
     pipe.process_host(h_iq, n_blocks=nb, want=("pcm",), out={"pcm": h_pcm}, chunk_blocks=args.chunk_blocks)
     pipe.reset()
     pipe.process(d_iq, n_blocks=nb, want=("pcm",), out=out)
+    pipe.flush()
     torch.cuda.synchronize(dev)
     pcm_matches = bool(torch.equal(h_pcm.to(dev), out["pcm"]))
     gather_info = {"kind": "shared pinned host array (/dev/shm, cudaHostRegister): each rank's D2H copies land in its slice of rank 0's buffer",
@@ -303,8 +306,13 @@ def run_gpu_arm(args):
         chk = oracle.load("ref") if oracle.have_ref() else oracle.load("oracle")
         nbc = min(4, nb)
         small = d_iq[:2, :nbc * m.block_size].contiguous()
-        pc = dy4_b200.Pipeline(MODE, STEREO, 2, device=local_rank)
-        got = pc.process(small, n_blocks=nbc, want=("pcm",))["pcm"].cpu().numpy()
+        pc = dy4_b200.Pipeline(MODE, STEREO, 2, device=local_rank, pipelined=overlap)        # as the timed path: two calls, overlapped
+        h1 = nbc // 2
+        parts = [pc.process(small[:, :h1 * m.block_size], n_blocks=h1, want=("pcm",))["pcm"],
+                 pc.process(small[:, h1 * m.block_size:], n_blocks=nbc - h1, want=("pcm",))["pcm"]] if h1 else [pc.process(small, n_blocks=nbc, want=("pcm",))["pcm"]]
+        pc.flush()
+        torch.cuda.synchronize(dev)
+        got = torch.cat(parts, 1).cpu().numpy()
         pc.close()
         worst = 0
         for s_ in range(2):
@@ -432,7 +440,9 @@ def run_gpu_arm(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(overlap),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": S * nb * m.block_size,
                 "d2h_bytes_per_step": S * n_audio * nch * 2, "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-                "timing": "host clock around the synchronous process_host() calls and the closing barrier, max over ranks",
+                "timing": ("host clock around the process_host() calls (queued back to back: the upload of step k+1 runs beside the kernels of step k), the closing "
+                           "dy4_pipeline_sync and the barrier, max over ranks") if overlap else
+                          "host clock around the synchronous process_host() calls and the closing barrier, max over ranks",
                 "pcm_equals_device_path": pcm_matches, "gather": gather_info},
         "oracle_check": oracle_check,
         "signal": "periodic over one step: the streams continue from step to step without a jump" if periodic else "the same buffer again every step: a phase jump per step",

@@ -154,7 +154,9 @@ typedef struct dy4_pipeline dy4_pipeline_t;
                                      serial loops of the call before are still going (on SMs of their own where CUDA green contexts
                                      are available).  The caller must call dy4_pipeline_flush (or synchronise the device) before it
                                      reads the outputs or overwrites the input of ANY earlier call; results are the same bits.
-                                     Every other entry point (state, reset, RDS read / drain, host path) drains the queue itself. */
+                                     dy4_pipeline_process_host overlaps the same way (whole calls alternate between two staging sets; the
+                                     host arrays are valid after dy4_pipeline_sync).  Every other entry point (state, reset, RDS read /
+                                     drain) drains the queue itself. */
 
 /* Create a receiver for `n_streams` independent streams in `mode` (0..3), mono (stereo=0)
  * or stereo (stereo=1), on CUDA device `device`.  All carried state starts as in
@@ -181,6 +183,10 @@ int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stri
 /* DY4_FLAG_PIPELINED: make `stream` wait for every call queued so far (outputs complete, inputs no longer read).
  * Without the flag calls are joined to their stream when they end and this is a no-op. */
 int dy4_pipeline_flush(dy4_pipeline_t* p, void* stream);
+/* Block the calling thread until everything this pipeline has queued is done, on every stream of its own (device calls, uploads,
+ * downloads).  With DY4_FLAG_PIPELINED dy4_pipeline_process_host returns when the call is QUEUED — its upload runs beside the
+ * kernels of the call before — and the host arrays are valid after this. */
+int dy4_pipeline_sync(dy4_pipeline_t* p);
 
 /*
  * Same, HOST pointers (pinned memory recommended): the input is uploaded in

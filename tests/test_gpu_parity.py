@@ -232,6 +232,33 @@ def test_pipelined_calls_edge_cases(dy4, monkeypatch, case):
     assert np.array_equal(st1, st2)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_pipelined_host_path(dy4, pinned):
+    """process_host on a pipelined pipeline: whole calls through two staging sets, queued back to back (contiguous rows go up as
+    one 1-D copy, a column slab of a wider array as a 2-D copy), outputs read after sync().  Bits of the synchronous host path."""
+    import torch
+    m = dy4.mode_params(0)
+    S, nb, calls = 6, 5, 5
+    iq = dy4.synth.make_batch(0, S, calls * nb * m.block_size // 2, base_seed=733)
+    whole = torch.from_numpy(iq).pin_memory().numpy() if pinned else iq
+    chunks = [np.ascontiguousarray(whole[:, k * nb * m.block_size:(k + 1) * nb * m.block_size]) if k % 2 else whole[:, k * nb * m.block_size:(k + 1) * nb * m.block_size]
+              for k in range(calls)]                          # odd calls: contiguous rows; even calls: a slab of the wide array
+
+    def run(pipelined):
+        p = dy4.Pipeline(0, 1, S, pipelined=pipelined)
+        outs = [p.process_host(c, want=("pcm", "audio")) for c in chunks]
+        p.sync()
+        state = p.get_state().copy()
+        p.close()
+        return outs, state
+
+    one, st1 = run(False)
+    two, st2 = run(True)
+    for x, y in zip(one, two):
+        assert np.array_equal(x["pcm"], y["pcm"]) and np.array_equal(bits(x["audio"]), bits(y["audio"]))
+    assert np.array_equal(st1, st2)
+
+
 def test_sm_partition_does_not_change_results(dy4, monkeypatch):
     """DY4_LOOP_SMS (opt-in, dy4_smpart.cu): the serial loops on a green context of 32 SMs, every other kernel on the rest; the
     caller's stream forks into the partition's streams and joins at the end of the call.  Same bits out, call after call."""
