@@ -2,13 +2,16 @@
 //
 // Replaces the reference's block loop, src/project.cpp:289-318: per block it
 // reads stdin, spawns frontend()/backend() threads joined through threadSafeQ,
-// converts to int16 and writes stdout.  Here a "chunk" of whole blocks of ALL
-// streams goes through five kernels on one CUDA stream
-//     front end -> twin BPF -> PLL -> audio -> tails
-// with the carried state (project.cpp:25-53) resident on the device, and the
-// host-facing variant overlaps host->device copies, compute and device->host
-// copies of successive chunks on three streams with events (double-buffered
-// staging) instead of a queue between two threads.
+// converts to int16 and writes stdout.  Here a CALL of whole blocks of ALL
+// streams goes through
+//     front end -> band-pass pair -> PLL (predict, table, serial loop, NCO row) -> audio -> tails
+// with the carried state (project.cpp:25-53) resident on the device: the FIR
+// kernels over the whole call, everything else over sub-chunks of it, on four
+// CUDA streams joined by events (process_device).  Consecutive
+// calls can overlap (DY4_FLAG_PIPELINED), the serial loops then on SMs of their
+// own (dy4_smpart.cu).  The host-facing variants overlap host->device copies,
+// kernels and device->host copies (sub-chunk by sub-chunk, or call by call when
+// calls overlap) instead of a queue between two threads.
 #include "../../include/dy4_b200.h"
 #include "dy4_common.cuh"
 #include "dy4_kernels.h"

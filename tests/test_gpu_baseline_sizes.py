@@ -49,7 +49,7 @@ def test_config1_length_stereo_ten_seconds(dy4, checker):
     torch.cuda.synchronize()
     pilot, nco = p.debug_pilot_nco()
     p.close()
-    q = dy4.Pipeline(0, 1, S)                                       # the bench's path: geometric sub-chunks, two CUDA streams
+    q = dy4.Pipeline(0, 1, S)                                       # joined calls: geometric sub-chunks, four CUDA streams
     out2 = q.process(d, want=("pcm", "audio"))
     torch.cuda.synchronize()
     q.close()
