@@ -37,7 +37,8 @@ def cpu_parallel(checker, mode, stereo, iq_rows, want):
 
 def test_config1_length_stereo_ten_seconds(dy4, checker):
     """468 blocks of mode 0 stereo, 16 streams: IF and NCO bit-exact over 2.4 M PLL steps, audio / PCM within tolerance — both
-    in one launch per kernel (debug rows, where the pilot / NCO rows can be read back) and through the pipelined sub-chunks."""
+    in one launch per kernel (debug rows, where the pilot / NCO rows can be read back), through the pipelined sub-chunks of one
+    call, and as ten overlapped calls (DY4_FLAG_PIPELINED)."""
     import torch
     m = dy4.mode_params(0)
     S, nb = 16, 468
@@ -53,6 +54,12 @@ def test_config1_length_stereo_ten_seconds(dy4, checker):
     out2 = q.process(d, want=("pcm", "audio"))
     torch.cuda.synchronize()
     q.close()
+    r = dy4.Pipeline(0, 1, S, pipelined=True)                       # the bench's path: overlapped calls of 48 blocks (and a last one of 36)
+    parts = [r.process(d[:, b * m.block_size:min(b + 48, nb) * m.block_size], want=("pcm",))["pcm"] for b in range(0, nb, 48)]
+    r.flush()
+    torch.cuda.synchronize()
+    r.close()
+    assert torch.equal(torch.cat(parts, 1), out2["pcm"])
     worst = 0.0
     for s in range(S):
         ref = refs[s]
