@@ -994,6 +994,9 @@ extern "C" int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq,
     if (row_stride_bytes < (size_t)n_blocks * m.block_size) { dy4_set_error("dy4_pipeline_process_host: row stride too small"); return DY4_ERR_ARG; }
     CU(cudaSetDevice(p->device));
     if (p->pipelined) return process_host_overlapped(p, h_iq, row_stride_bytes, n_blocks, h_pcm, h_audio, chunk_blocks);
+    // device-path calls are asynchronous on the CALLER's stream, this call runs on streams of the pipeline's own: whatever is still
+    // queued must be through before it touches the carried state
+    { const int rq = quiesce(p); if (rq) return rq; }
     const int ch = p->stereo ? 2 : 1;
     const size_t S = (size_t)p->n_streams;
     // A "window" of blocks is resident in device staging at a time (DY4_STAGE_BYTES of input, default 4 GiB, or

@@ -176,7 +176,9 @@ int dy4_pipeline_reset(dy4_pipeline_t* p);
  *   d_if        float [n_streams][n_blocks*if_per_block]                 or NULL
  *   stream      a cudaStream_t (as void*), NULL = the default stream
  * Successive calls continue the same streams (state is carried on the device),
- * exactly as successive blocks do in the reference.  Asynchronous on `stream`.
+ * exactly as successive blocks do in the reference.  Asynchronous on `stream`;
+ * successive calls on one pipeline must be issued on the same stream (or ordered
+ * by the caller): the carried state is read and written in stream order.
  */
 int dy4_pipeline_process(dy4_pipeline_t* p, const uint8_t* d_iq, size_t row_stride_bytes, int n_blocks,
                          int16_t* d_pcm, float* d_audio, float* d_if, void* stream);
@@ -194,8 +196,9 @@ int dy4_pipeline_sync(dy4_pipeline_t* p);
  * bytes, and each sub-chunk's PCM/audio goes back device->host on a third stream
  * as soon as it exists — the replacement for the reference's stdin reader + queue.
  * chunk_blocks > 0 caps the blocks resident in device staging at once (default:
- * DY4_STAGE_BYTES of input, 4 GiB).  Synchronous: returns when all outputs are in
- * host memory.
+ * DY4_STAGE_BYTES of input, 4 GiB).  Synchronous: waits for whatever dy4_pipeline_process
+ * calls are still queued on the device, and returns when all outputs are in host memory
+ * (DY4_FLAG_PIPELINED: returns when queued, see dy4_pipeline_sync).
  */
 int dy4_pipeline_process_host(dy4_pipeline_t* p, const uint8_t* h_iq, size_t row_stride_bytes, int n_blocks,
                               int16_t* h_pcm, float* h_audio, int chunk_blocks);

@@ -259,6 +259,41 @@ def test_pipelined_host_path(dy4, pinned):
     assert np.array_equal(st1, st2)
 
 
+def test_pipelined_calls_random_lengths(dy4):
+    """Thirty overlapped calls of random length (1 .. 20 blocks: one sub-chunk, uniform sub-chunks, row and workspace regrowth on the
+    way), device and host path mixed, against the same calls joined one by one."""
+    import torch
+    m = dy4.mode_params(0)
+    S = 33
+    rng = np.random.default_rng(12)
+    lens = [int(x) for x in rng.integers(1, 21, size=30)]
+    total = sum(lens)
+    d = dy4.synth.make_batch_torch(0, S, total * m.block_size // 2, base_seed=911, device="cuda")
+    h = d.cpu().pin_memory()
+    host_calls = set(int(x) for x in rng.choice(30, size=8, replace=False))
+
+    def run(pipelined):
+        p = dy4.Pipeline(0, 1, S, pipelined=pipelined)
+        outs, b = [], 0
+        for k, nb in enumerate(lens):
+            sl = slice(b * m.block_size, (b + nb) * m.block_size)
+            if k in host_calls:
+                outs.append(p.process_host(h[:, sl].numpy(), n_blocks=nb, want=("pcm",))["pcm"])
+            else:
+                outs.append(p.process(d[:, sl], n_blocks=nb, want=("pcm",))["pcm"])
+            b += nb
+        p.flush()
+        p.sync()
+        torch.cuda.synchronize()
+        outs = [o if isinstance(o, np.ndarray) else o.cpu().numpy() for o in outs]
+        p.close()
+        return outs
+
+    one, two = run(False), run(True)
+    for k, (x, y) in enumerate(zip(one, two)):
+        assert np.array_equal(x, y), (k, lens[k], k in host_calls)
+
+
 def test_sm_partition_does_not_change_results(dy4, monkeypatch):
     """DY4_LOOP_SMS (opt-in, dy4_smpart.cu): the serial loops on a green context of 32 SMs, every other kernel on the rest; the
     caller's stream forks into the partition's streams and joins at the end of the call.  Same bits out, call after call."""
