@@ -164,7 +164,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def workload_config(overlap=False):
+def workload_config(overlap=None):        # overlap: how the GPU arm issues its calls (None: the reference arm, where it does not apply)
     return {
         "workload": "%smode %d %s FM (8-bit IQ -> IF -> %s int16 PCM), %d independent synthetic streams per GPU x %d blocks"
                     % ("BASELINE configs[1]: " if (MODE, STREAMS_PER_GPU, STEREO) == (0, 256, 1) else "", MODE, "stereo" if STEREO else "mono",
@@ -175,7 +175,7 @@ def workload_config(overlap=False):
         "arithmetic": "front end, pilot/stereo BPF and PLL bit-exact to the reference (unfused f32; the PLL's f64 libm results reproduced exactly); "
                       "audio resamplers fused f32 (PCM within 1 LSB)",
         "parallelism": "streams partitioned across GPUs, one process per GPU, no collective on the data path",
-        "calls": "one dy4_pipeline_process call per step; " + (
+        "calls": None if overlap is None else "one dy4_pipeline_process call per step; " + (
             "steps are queued back to back and OVERLAP on the device (DY4_FLAG_PIPELINED: step k+1's FIR kernels run beside step k's PLL loops), "
             "one dy4_pipeline_flush before the closing event - every step's PCM is complete inside the timed region" if overlap else
             "every step is joined to the stream before the next starts"),
