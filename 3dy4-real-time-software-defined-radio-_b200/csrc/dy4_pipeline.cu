@@ -75,7 +75,7 @@ struct dy4_pipeline {
     int8_t *rds_sym = nullptr, *rds_bits = nullptr;
     size_t rds_sym_cap = 0, rds_bits_cap = 0, rds_ev_cap = 0, rds_grp_cap = 0;
     long long rds_blocks_since_drain = 0;
-    cudaStream_t s_rds = nullptr; cudaEvent_t ev_if = nullptr, ev_rds = nullptr;
+    cudaStream_t s_rds = nullptr; cudaEvent_t ev_rds = nullptr;
     bool pll_table = false;                          // table-driven PLL loop (dy4_plltab.h)
     bool pll_fresh = true;                           // no sample processed since create / reset: the next PLL launch starts the streams
     cudaStream_t s_pll = nullptr;                    // the serial PLL chain runs here, beside the FIR kernels of the next sub-chunk
@@ -297,7 +297,6 @@ int ensure_workspace(dy4_pipeline* p, int n_blocks)
         CU(cudaMalloc(&p->rds_lp, (size_t)p->n_streams * 2 * p->rds_cap * sizeof(float)));
         if (!p->ev_rds) {
             if (!p->s_rds) CU(cudaStreamCreateWithFlags(&p->s_rds, cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&p->ev_if, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&p->ev_rds, cudaEventDisableTiming));
         }
     }
@@ -843,7 +842,7 @@ extern "C" int dy4_pipeline_destroy(dy4_pipeline_t* p)
     cudaFree(p->rds_f); cudaFree(p->rds_carrier); cudaFree(p->rds_nco_i); cudaFree(p->rds_nco_q); cudaFree(p->rds_theta); cudaFree(p->rds_lp); cudaFree(p->rds_out);
     cudaFree(p->rds_tail); cudaFree(p->rds_mix_tail); cudaFree(p->rds_lp_tail); cudaFree(p->rds_pll_state); cudaFree(p->d_rds_poly); cudaFree(p->d_rds_rrc);
     cudaFree(p->rds_acc); cudaFree(p->rds_dec_state); cudaFree(p->rds_counts); cudaFree(p->rds_events); cudaFree(p->rds_groups); cudaFree(p->rds_sym); cudaFree(p->rds_bits);
-    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_if); cudaEventDestroy(p->ev_rds); }
+    if (p->s_rds) { cudaStreamDestroy(p->s_rds); cudaEventDestroy(p->ev_rds); }
     cudaFree(p->iq_tail); cudaFree(p->if_tail); cudaFree(p->mix_tail); cudaFree(p->pll_state);
     for (auto& w : p->ws) { cudaFree(w.theta); cudaFree(w.inv); cudaFree(w.tab); }
     cudaFree(p->c_if); cudaFree(p->c_pilot); cudaFree(p->c_sband); cudaFree(p->c_nco);

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr double kTwoPiHi = 6.283185307179586, kTwoPiLo = 2.4492935982947064e-16, kInvTwoPi = 0.15915494309189535;
+constexpr double kTwoPiHi = 6.283185307179586, kInvTwoPi = 0.15915494309189535;
 constexpr double kPi = 3.141592653589793;
 
 // The detector needs the phase argument reduced to (-pi, pi].  Reducing w*k + phase from scratch every sample (it reaches
