@@ -259,6 +259,34 @@ def test_pipelined_host_path(dy4, pinned):
     assert np.array_equal(st1, st2)
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_pipelined_calls_other_modes(dy4, mode):
+    """Overlapped calls in modes 1-3 (other block sizes and IF rates; modes 2 and 3 through the polyphase audio kernels), device and
+    host path, exact and default audio arithmetic: the bits of joined calls."""
+    import torch
+    m = dy4.mode_params(mode)
+    S = 10
+    cuts = [0, 3, 4, 13, 14, 22]
+    d = dy4.synth.make_batch_torch(mode, S, cuts[-1] * m.block_size // 2, base_seed=1200 + mode, device="cuda")
+    h = d.cpu().pin_memory()
+    for exact in (False, True):
+        def run(pipelined):
+            p = dy4.Pipeline(mode, 1, S, exact_audio=exact, pipelined=pipelined)
+            outs = []
+            for k, (a, b) in enumerate(zip(cuts, cuts[1:])):
+                sl = slice(a * m.block_size, b * m.block_size)
+                o = p.process_host(h[:, sl].numpy(), want=("pcm",)) if k == 2 else p.process(d[:, sl], want=("pcm",))
+                outs.append(o["pcm"])
+            p.flush()
+            p.sync()
+            torch.cuda.synchronize()
+            outs = [o if isinstance(o, np.ndarray) else o.cpu().numpy() for o in outs]
+            p.close()
+            return outs
+        for k, (x, y) in enumerate(zip(run(False), run(True))):
+            assert np.array_equal(x, y), (mode, exact, k)
+
+
 def test_pipelined_calls_random_lengths(dy4):
     """Thirty overlapped calls of random length (1 .. 20 blocks: one sub-chunk, uniform sub-chunks, row and workspace regrowth on the
     way), device and host path mixed, against the same calls joined one by one."""
